@@ -1,0 +1,391 @@
+#!/usr/bin/env python
+"""bench.py -- encode Mpixel/s of the B200 JPEG encode path on BASELINE.json's headline
+configuration: a batch of 8K (7680x4320) RGB frames, 4:4:4, quality 75, one image stream per
+GPU (configs[3]); frames are independent, so ranks shard the batch with no collective
+("scaling": "weak": every GPU encodes FRAMES frames per step).
+
+A step = one pass of the whole hot path (K1 transform, K3 bit lengths, K4 scan, K5 pack,
+K6 stuffing -> complete JFIF streams) over one batch of synthetic frames.
+  value : frames are resident in HBM when the timed region starts (device-resident encode)
+  e2e   : the same batch through the C-ABI host-buffer call (jpgb200_encode_batch_host):
+          pinned host frames in, JFIF bytes out, H2D and D2H inside the timed region
+  roofline : K1 (fused colour->FDCT->quantise->zig-zag), algorithmic 9 B/pixel, timed with
+          CUDA events on its own stream inside the timed region, against the measured HBM
+          copy bandwidth in MEASURED_PEAKS.json
+  cpu_baseline : the reference's own C stage functions (oracle/_ref/ref_harness, built from
+          the unmodified sources) on a bounded crop of frame 0, one core
+
+`--impl reference` times the reference's CPU implementation on all host cores instead.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+W, H, QUALITY, RATIO = 7680, 4320, 75, 0
+NPX = W * H
+SEED = 1003  # 1000 + config index
+KIND = 0     # "natural"
+METRIC = "encode Mpixel/s (8K RGB, 4:4:4 q75)"
+UNIT = "Mpixel/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--frames", type=int, default=256, help="frames per GPU per step")
+    ap.add_argument("--e2e-frames", type=int, default=64, help="frames per GPU per e2e step")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks and throttle reasons DURING the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.rows = []
+        self.proc = None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for i, nm in enumerate(names):
+                if f[5 + i].lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+# reference arm: the reference's own CPU code (oracle/_ref), all host cores
+# ---------------------------------------------------------------------------------------------
+
+def write_crop_bmp(path, w, h, frame, x0=0, y0=0):
+    import oracle_lib as O
+    import numpy as np
+
+    # identical bytes to the GPU's synthetic frame: generate the crop's pixels of the 8K frame
+    full_rows = [O.synth_plane(W, y0 + h, SEED, frame, c, KIND)[y0:y0 + h, x0:x0 + w] for c in range(3)]
+    O.write_bmp(path, np.ascontiguousarray(full_rows[0]), np.ascontiguousarray(full_rows[1]),
+                np.ascontiguousarray(full_rows[2]), w, h)
+
+
+def ref_harness_path():
+    import oracle_lib as O
+
+    if os.path.exists(O.REF_HARNESS):
+        return O.REF_HARNESS
+    return None
+
+
+def time_reference_procs(bmps, quality, harness):
+    """one process per BMP (the reference rewrites its global tables: one image per process)"""
+    outs = [b + ".json" for b in bmps]
+    t0 = time.time()
+    procs = [subprocess.Popen([harness, "time", b, str(quality), o], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+             for b, o in zip(bmps, outs)]
+    for p in procs:
+        p.wait()
+    wall = time.time() - t0
+    inner = [json.load(open(o))["seconds"] for o in outs]
+    return wall, inner
+
+
+def cpu_baseline_one_core(tmp):
+    """bounded sample: a 1920x1080 crop of frame 0 through the unmodified reference, 1 core"""
+    harness = ref_harness_path()
+    cw, ch = 1920, 1080
+    if harness:
+        bmp = os.path.join(tmp, "crop.bmp")
+        write_crop_bmp(bmp, cw, ch, 0)
+        wall, inner = time_reference_procs([bmp], QUALITY, harness)
+        return {"value": cw * ch / inner[0] / 1e6, "unit": UNIT, "cores": 1, "kind": "reference",
+                "sample": "1920x1080 crop of frame 0, stages preprocess..dpcm + histogram loops (the reference has no "
+                          "bitstream writer), built -O0 -g as shipped (src/Makefile:2), %.1f s" % inner[0]}
+    import oracle_lib as O
+    import numpy as np
+
+    planes = [np.ascontiguousarray(O.synth_plane(W, ch, SEED, 0, c, KIND)[:, :cw]) for c in range(3)]
+    t = O.time_encode(planes[0], planes[1], planes[2], cw, ch, QUALITY, RATIO, threads=1)
+    return {"value": cw * ch / t / 1e6, "unit": UNIT, "cores": 1, "kind": "port",
+            "sample": "1920x1080 crop of frame 0 through oracle/jpgb200_oracle.c (FP64 restatement), %.2f s" % t}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import oracle_lib as O
+
+    O.lib()
+    harness = ref_harness_path()
+    cores = os.cpu_count() or 1
+    cw, ch = 640, 360  # per-process crop: ~1.7 s of reference time each
+    tmp = tempfile.mkdtemp(prefix="jpgb200_ref_")
+    bmps = []
+    for i in range(cores):
+        p = os.path.join(tmp, "crop%d.bmp" % i)
+        write_crop_bmp(p, cw, ch, i % 4, x0=(i * cw) % (W - cw))
+        bmps.append(p)
+    times = []
+    kind = "reference" if harness else "port"
+    for step in range(args.warmup + args.steps):
+        if harness:
+            wall, _ = time_reference_procs(bmps, QUALITY, harness)
+        else:
+            import numpy as np
+
+            t0 = time.time()
+            for b in bmps[:1]:
+                r, g, bb, w_, h_ = O.bmp_load(b)
+                O.coefficients(r, g, bb, w_, h_, QUALITY, RATIO, threads=cores)
+            wall = (time.time() - t0)
+        if step >= args.warmup:
+            times.append(wall)
+    npx_step = cw * ch * (cores if harness else 1)
+    total = sum(times)
+    value = npx_step * len(times) / total / 1e6
+    sample = ("%d processes x one %dx%d crop of the 8K synthetic frames per step, unmodified reference stage functions "
+              "(preprocess..dpcm + histogram loops; it has no bitstream writer), -O0 -g as shipped" % (cores, cw, ch)) \
+        if harness else "oracle port, %d threads, one %dx%d crop per step" % (cores, cw, ch)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": 1e3 * total / len(times), "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "7680x4320 RGB frames, 4:4:4, q75 (bounded crops)", "sample": sample},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------
+
+def run_b200(args):
+    import numpy as np
+    import torch
+
+    import __graft_entry__ as ge
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the encode path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dist = None
+    if world > 1:
+        import torch.distributed as dist_mod
+
+        dist = dist_mod
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    pkg = ge.load_package()
+    enc = pkg.Encoder(local_rank)
+    stream = torch.cuda.Stream()  # a real (non-default) stream so torch events bracket our kernels
+    torch.cuda.set_stream(stream)
+    enc.set_stream(stream.cuda_stream)
+
+    F = args.frames
+    cap = NPX  # bytes reserved per output stream (1 B/pixel; natural frames need ~0.3)
+    planes = torch.empty((F, 3, H, W), dtype=torch.uint8, device="cuda")
+    out = torch.empty((F, cap), dtype=torch.uint8, device="cuda")
+    lens = torch.zeros((F,), dtype=torch.int64, device="cuda")
+    frame_bytes = 3 * NPX
+    for f in range(F):
+        enc.synth_device(planes.data_ptr() + f * frame_bytes, W, H, SEED, rank * F + f, KIND)
+    torch.cuda.synchronize()
+
+    def step():
+        enc.encode_batch_device(planes.data_ptr(), F, W, H, QUALITY, RATIO, out.data_ptr(), cap, lens.data_ptr())
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    enc.reset_profile()
+    enc.set_profiling(True)
+    launches0 = enc.launch_count()
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    ev0.record(stream)
+    for _ in range(args.steps):
+        step()
+    ev1.record(stream)
+    barrier()
+    clocks = sampler.stop()
+    ms_total = ev0.elapsed_time(ev1)
+    launches = enc.launch_count() - launches0
+    ktimes = enc.kernel_times()
+    enc.set_profiling(False)
+    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total = float(t.item())
+    ms_per_step = ms_total / args.steps
+    value = world * F * NPX / (ms_per_step * 1e-3) / 1e6
+    lens_host = lens.cpu().numpy()
+    assert (lens_host > 623).all() and (lens_host <= cap).all(), "an encode failed (length word out of range)"
+    bytes_per_px = float(lens_host.mean()) / NPX
+
+    # ---- roofline of the dominant kernel (K1) from the live event timings
+    peak, peak_src = measured_peak()
+    k1_ms, k1_n = ktimes["k1_transform"]
+    k1_avg_s = k1_ms * 1e-3 / max(k1_n, 1)
+    achieved = 9.0 * NPX / k1_avg_s / 1e9
+    traffic = None
+    tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    if os.path.exists(tp):
+        try:
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "kernel": "k1_transform<0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": 9 * NPX, "avg_launch_us": k1_avg_s * 1e6,
+                "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()}}
+
+    # ---- e2e: host buffers through the C ABI, copies inside the timed region
+    e2e = None
+    if not args.no_e2e:
+        EF = args.e2e_frames
+        ring = 4
+        pins, pouts = [], []
+        for i in range(ring):
+            a, p = pkg.binding.pinned_empty(frame_bytes)
+            torch.cuda.synchronize()
+            src = planes[i].contiguous().view(-1)
+            a[:] = src.cpu().numpy()
+            pins.append((a, p))
+        for i in range(2 * ring):
+            o, p = pkg.binding.pinned_empty(cap)
+            pouts.append((o, p))
+        enc.set_stream(None)
+        in_ptrs = [pins[i % ring][1] for i in range(EF)]
+        out_ptrs = [pouts[i % (2 * ring)][1] for i in range(EF)]
+
+        def estep():
+            return enc.encode_batch_host(in_ptrs, W, H, QUALITY, RATIO, out_ptrs, cap)
+
+        for _ in range(max(1, min(args.warmup, 3))):
+            el = estep()
+        barrier()
+        l0 = enc.launch_count()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            el = estep()
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        launches_e2e = enc.launch_count() - l0
+        e2e = {"value": world * EF * NPX * args.steps / dt / 1e6, "unit": UNIT,
+               "h2d_bytes_per_step": EF * frame_bytes, "d2h_bytes_per_step": int(sum(el)) + 8 * EF,
+               "frames_per_step": EF, "ms_per_step": 1e3 * dt / args.steps, "gpu_launches": launches_e2e,
+               "timer": "host perf_counter around jpgb200_encode_batch_host, stream-synchronised, max over ranks"}
+        enc.set_stream(stream.cuda_stream)
+        for _, p in pins + pouts:
+            pkg.binding.pinned_free(p)
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        tmp = tempfile.mkdtemp(prefix="jpgb200_cpu_")
+        cpu = cpu_baseline_one_core(tmp)
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic",
+            "config": {"workload": "batch of %d synthetic 7680x4320 RGB frames per GPU, 4:4:4, q75 (BASELINE.json configs[3])" % F,
+                       "frames_per_gpu_per_step": F, "width": W, "height": H, "quality": QUALITY, "sampling": "4:4:4",
+                       "distribution": "natural (16x16 cells + iid noise, SURVEY.md 8(d))", "seed": SEED,
+                       "compressed_bytes_per_pixel": bytes_per_px,
+                       "l2_policy": "inputs larger than L2: %d distinct frames = %.1f GB per step" % (F, F * frame_bytes / 1e9),
+                       "sharding": "frames independent, one image stream per GPU, no collective"},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+        }
+        print(json.dumps(line), flush=True)
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,147 @@
+/*
+ * include/jpgb200.h -- C ABI of libjpgb200.so, the B200 (sm_100a) JPEG encode hot path.
+ *
+ * This is the drop-in boundary for the encode path of matthewT53/JPEG-Encoder-and-Decoder:
+ * plain pointers and sizes, no CUDA or torch types.  The host-side mirror of the
+ * reference's own C API (encode_bmp_to_jpeg, the per-stage JpgData functions, bmp_*) lives
+ * in jpeg-encoder-and-decoder_b200/host/ and calls only the functions declared here.
+ * Each entry point cites the reference interface it replaces (relative to
+ * /root/reference/).  There is no CPU fallback: every function returns
+ * JPGB200_ERR_NO_DEVICE when no CUDA device is usable.
+ *
+ * Conventions
+ *   - r,g,b are the three u8 planes exactly as bmp_GetRed/Green/Blue deliver them
+ *     (src/headers/bitmap.h:34-44; top-down raster, no row padding).
+ *   - sample_ratio: 0 = NO_CHROMA_SUBSAMPLING (4:4:4), 1 = HORIZONTAL_SUBSAMPLING (4:2:2)
+ *     (src/headers/jpg_encode.h:13-14).  4:2:0 is not built (src/downsample.c:29 is a stub).
+ *   - width % 8 == 0 (4:4:4) or % 16 == 0 (4:2:2), height % 8 == 0: the reference's padding
+ *     path is broken (src/preprocess.c:83-98,131-152), so other sizes are rejected.
+ *   - quality 24..97: outside it the reference's scale_table yields zero divisors or
+ *     entries above 255 (src/quantise.c:81-83).
+ *   - "device" pointers are CUDA device addresses on the context's GPU, passed as plain
+ *     pointer values.
+ */
+#ifndef JPGB200_H
+#define JPGB200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define JPGB200_OK 0
+#define JPGB200_ERR_NO_DEVICE (-1)
+#define JPGB200_ERR_BAD_DIMS (-2)
+#define JPGB200_ERR_BAD_QUALITY (-3)
+#define JPGB200_ERR_CUDA (-4)
+#define JPGB200_ERR_OUT_TOO_SMALL (-5)
+#define JPGB200_ERR_BAD_ARG (-6)
+#define JPGB200_ERR_NOMEM (-7)
+
+#define JPGB200_DC_REF_RECURRENCE 0 /* d[i]=dc[i]-d[i-1], what dpcm() computes (src/dpcm.c:10-12) */
+#define JPGB200_DC_SPEC_DIFF 1      /* d[i]=dc[i]-dc[i-1], what a decodable stream needs        */
+#define JPGB200_SYM_REF 0           /* AC histogram index run|size (src/huffman.c:218)          */
+#define JPGB200_SYM_SPEC 1          /* (run<<4)|size                                            */
+
+#define JPGB200_NUM_KERNELS 8 /* K1 transform, K3 bits, K4 scan, zero, K5 pack, K6 count, K6 scan, K6 scatter */
+
+typedef struct jpgb200_ctx jpgb200_ctx;
+
+/* ---- lifetime ---------------------------------------------------------------------- */
+/* One context per GPU (or per host thread); owns a stream and all device workspaces.
+ * Replaces create_jpeg_data (src/jpg_encode.c:54-58), whose JpegData is never freed. */
+int jpgb200_create(jpgb200_ctx **ctx, int device);
+void jpgb200_destroy(jpgb200_ctx *ctx);
+const char *jpgb200_strerror(int code);
+/* text of the last CUDA error seen by this context ("" if none) */
+const char *jpgb200_last_error(const jpgb200_ctx *ctx);
+/* Run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = context's own. */
+int jpgb200_set_stream(jpgb200_ctx *ctx, void *cuda_stream);
+int jpgb200_sync(jpgb200_ctx *ctx);
+/* The 8 bytes the reference reads in front of each plane buffer for block W/8-1
+ * (src/preprocess.c:159,206-210): oob[0..7]=r, [8..15]=g, [16..23]=b.
+ * Default: zeros. */
+int jpgb200_set_oob_bytes(jpgb200_ctx *ctx, const uint8_t oob[24]);
+
+/* ---- the encode path --------------------------------------------------------------- */
+/* Whole pipeline of encode_bmp_to_jpeg after the BMP load (src/jpg_encode.c:32-50):
+ * host planes in, complete JFIF byte stream out (host).  H2D + kernels + D2H. */
+int jpgb200_encode_planar(jpgb200_ctx *ctx, const uint8_t *r, const uint8_t *g, const uint8_t *b, int width,
+                          int height, int quality, int sample_ratio, uint8_t *out, size_t cap, size_t *len);
+/* Same from interleaved RGB24: the body encode_rgb_to_jpeg (src/headers/jpg_encode.h:99,
+ * declared but never defined, and lacking width/height) would need. */
+int jpgb200_encode_rgb(jpgb200_ctx *ctx, const uint8_t *rgb, int width, int height, int quality, int sample_ratio,
+                       uint8_t *out, size_t cap, size_t *len);
+/* Device-resident: planes and output already on the GPU.  d_len (device, 8 bytes) receives
+ * the stream length; nothing is synchronised.  d_planes = r plane, then g, then b. */
+int jpgb200_encode_device(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int width,
+                          int height, int quality, int sample_ratio, uint8_t *d_out, size_t cap,
+                          unsigned long long *d_len);
+/* n frames back to back: frame f reads planes at d_planes + f*3*w*h (r,g,b contiguous),
+ * writes its stream at d_out + f*out_stride and its length to d_lens[f]. */
+int jpgb200_encode_batch_device(jpgb200_ctx *ctx, const uint8_t *d_planes, int n_frames, int width, int height,
+                                int quality, int sample_ratio, uint8_t *d_out, size_t out_stride,
+                                unsigned long long *d_lens);
+/* Host-buffer batch: frames[f] -> host planes (r,g,b contiguous, 3*w*h bytes, ideally
+ * pinned); outs[f] receives the stream, lens[f] its length.  Copies are double-buffered
+ * against the kernels on two streams. */
+int jpgb200_encode_batch_host(jpgb200_ctx *ctx, const uint8_t *const *frames, int n_frames, int width, int height,
+                              int quality, int sample_ratio, uint8_t *const *outs, size_t cap, size_t *lens);
+
+/* JFIF header bytes for (w,h,q,ratio): SOI..SOS, 623 bytes. */
+int jpgb200_jfif_header(int width, int height, int quality, int sample_ratio, uint8_t *out, size_t cap, size_t *len);
+
+/* ---- parity taps (test and staged-mode surface) ------------------------------------- */
+/* Quantised zig-zag coefficients after zig_zag() and before dpcm() (src/jpg_encode.c:44),
+ * int16 [Y blocks | Cb blocks | Cr blocks][64]; blocks per component = (w/8)*(h/8)
+ * (chroma halved for 4:2:2). */
+int jpgb200_coefficients(jpgb200_ctx *ctx, const uint8_t *r, const uint8_t *g, const uint8_t *b, int width,
+                         int height, int quality, int sample_ratio, int16_t *zz_out);
+/* dpcm() on the coefficients of the last jpgb200_coefficients/encode call
+ * (src/dpcm.c:6-21): d_out = int32 [Y | Cb | Cr] DC sequences in the requested mode. */
+int jpgb200_dc_sequence(jpgb200_ctx *ctx, int mode, int32_t *d_out);
+/* The histogram loops of huffman_encode (src/huffman.c:29-42) on the same coefficients:
+ * freq[4][257] = lum_DC, lum_AC, chrom_DC, chrom_AC, freq[*][256] = 1 (src/huffman.c:54). */
+int jpgb200_histograms(jpgb200_ctx *ctx, int dc_mode, int sym_mode, int32_t *freq);
+/* Global bit offset of every block in scan order (n_blocks+1 values, last = total bits),
+ * from the last encode/coefficients call. */
+int jpgb200_block_bit_offsets(jpgb200_ctx *ctx, unsigned long long *offsets);
+long long jpgb200_num_blocks(int width, int height, int sample_ratio, long long n[3]);
+
+/* Block-level stage API used directly by the reference's driver (src/jpg_driver.c:135-144):
+ * n FP64 blocks of 64 values, values[y*8+x] (src/block.c:25-33), processed in place. */
+int jpgb200_stage_dct(jpgb200_ctx *ctx, double *blocks, long long n);                        /* dct_block */
+int jpgb200_stage_quantise(jpgb200_ctx *ctx, double *blocks, long long n, const int table[64]); /* quantise_lum|chr */
+int jpgb200_stage_zigzag(jpgb200_ctx *ctx, const double *blocks, long long n, int *zz);       /* zig_zag_block */
+/* scaled tables as the reference's first scale_table call leaves them (src/quantise.c:74-86) */
+int jpgb200_quant_tables(int quality, int lum[64], int chr[64]);
+
+/* ---- device helpers for hosts without a CUDA runtime of their own ---------------------- */
+int jpgb200_device_count(void);
+int jpgb200_malloc(jpgb200_ctx *ctx, void **dptr, size_t bytes);
+int jpgb200_free(jpgb200_ctx *ctx, void *dptr);
+int jpgb200_host_alloc(void **hptr, size_t bytes); /* pinned */
+int jpgb200_host_free(void *hptr);
+int jpgb200_memcpy_h2d(jpgb200_ctx *ctx, void *dptr, const void *hptr, size_t bytes);
+int jpgb200_memcpy_d2h(jpgb200_ctx *ctx, void *hptr, const void *dptr, size_t bytes);
+/* deterministic synthetic planes [3][h][w] on the device (kind 0 natural, 1 noise) */
+int jpgb200_synth_device(jpgb200_ctx *ctx, uint8_t *d_planes, int width, int height, uint64_t seed, uint32_t frame,
+                         int kind);
+
+/* ---- measurement --------------------------------------------------------------------- */
+/* With profiling on, every kernel launch of the encode path is bracketed by CUDA events on
+ * the launching stream; sums are read back with jpgb200_kernel_times (ms and launch counts
+ * per kernel, JPGB200_NUM_KERNELS entries) and cleared by jpgb200_reset_profile. */
+int jpgb200_set_profiling(jpgb200_ctx *ctx, int on);
+int jpgb200_kernel_times(jpgb200_ctx *ctx, double *ms, long long *launches);
+int jpgb200_reset_profile(jpgb200_ctx *ctx);
+/* kernels launched by this context since creation (bench.py's gpu_launches) */
+long long jpgb200_launch_count(const jpgb200_ctx *ctx);
+const char *jpgb200_kernel_name(int k);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

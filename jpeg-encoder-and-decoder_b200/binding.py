@@ -1,0 +1,281 @@
+"""ctypes binding of libjpgb200.so (include/jpgb200.h) for tests/ and bench.py.
+
+Python is plumbing only: every call goes through the C ABI a C host would use.  If the
+shared library is missing or no CUDA device is usable this module raises -- there is no
+CPU fallback.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libjpgb200.so")
+
+DC_REF, DC_SPEC = 0, 1
+SYM_REF, SYM_SPEC = 0, 1
+NUM_KERNELS = 8
+
+ERR_NO_DEVICE, ERR_BAD_DIMS, ERR_BAD_QUALITY, ERR_CUDA, ERR_OUT_TOO_SMALL, ERR_BAD_ARG, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
+
+_lib = None
+
+# name -> (restype, argtypes); also the list tests check against include/jpgb200.h
+_u8p = C.POINTER(C.c_uint8)
+_vp = C.c_void_p
+_SIGS = {
+    "jpgb200_create": (C.c_int, [C.POINTER(_vp), C.c_int]),
+    "jpgb200_destroy": (None, [_vp]),
+    "jpgb200_strerror": (C.c_char_p, [C.c_int]),
+    "jpgb200_last_error": (C.c_char_p, [_vp]),
+    "jpgb200_set_stream": (C.c_int, [_vp, _vp]),
+    "jpgb200_sync": (C.c_int, [_vp]),
+    "jpgb200_set_oob_bytes": (C.c_int, [_vp, _vp]),
+    "jpgb200_encode_planar": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "jpgb200_encode_rgb": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "jpgb200_encode_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
+    "jpgb200_encode_batch_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
+    "jpgb200_encode_batch_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
+    "jpgb200_jfif_header": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "jpgb200_coefficients": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
+    "jpgb200_dc_sequence": (C.c_int, [_vp, C.c_int, _vp]),
+    "jpgb200_histograms": (C.c_int, [_vp, C.c_int, C.c_int, _vp]),
+    "jpgb200_block_bit_offsets": (C.c_int, [_vp, _vp]),
+    "jpgb200_num_blocks": (C.c_longlong, [C.c_int, C.c_int, C.c_int, _vp]),
+    "jpgb200_stage_dct": (C.c_int, [_vp, _vp, C.c_longlong]),
+    "jpgb200_stage_quantise": (C.c_int, [_vp, _vp, C.c_longlong, _vp]),
+    "jpgb200_stage_zigzag": (C.c_int, [_vp, _vp, C.c_longlong, _vp]),
+    "jpgb200_quant_tables": (C.c_int, [C.c_int, _vp, _vp]),
+    "jpgb200_device_count": (C.c_int, []),
+    "jpgb200_malloc": (C.c_int, [_vp, C.POINTER(_vp), C.c_size_t]),
+    "jpgb200_free": (C.c_int, [_vp, _vp]),
+    "jpgb200_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
+    "jpgb200_host_free": (C.c_int, [_vp]),
+    "jpgb200_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "jpgb200_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
+    "jpgb200_synth_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_int]),
+    "jpgb200_set_profiling": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_kernel_times": (C.c_int, [_vp, _vp, _vp]),
+    "jpgb200_reset_profile": (C.c_int, [_vp]),
+    "jpgb200_launch_count": (C.c_longlong, [_vp]),
+    "jpgb200_kernel_name": (C.c_char_p, [C.c_int]),
+}
+
+
+def exported_names():
+    return sorted(_SIGS)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError("%s is missing: run `python jpeg-encoder-and-decoder_b200/build.py` "
+                               "(the encode path has no CPU fallback)" % LIB_PATH)
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _SIGS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+class Jpgb200Error(RuntimeError):
+    def __init__(self, code, detail=""):
+        self.code = code
+        msg = lib().jpgb200_strerror(code).decode()
+        super().__init__("jpgb200 error %d: %s %s" % (code, msg, detail))
+
+
+def num_blocks(w, h, ratio):
+    n = (C.c_longlong * 3)()
+    t = lib().jpgb200_num_blocks(w, h, ratio, n)
+    if t < 0:
+        raise Jpgb200Error(int(t))
+    return [int(n[0]), int(n[1]), int(n[2])]
+
+
+def quant_tables(quality):
+    lum = np.zeros(64, np.int32)
+    chr_ = np.zeros(64, np.int32)
+    rc = lib().jpgb200_quant_tables(quality, lum.ctypes.data, chr_.ctypes.data)
+    return rc, lum.reshape(8, 8), chr_.reshape(8, 8)
+
+
+def jfif_header(w, h, quality, ratio):
+    out = np.zeros(1024, np.uint8)
+    n = C.c_size_t(0)
+    rc = lib().jpgb200_jfif_header(w, h, quality, ratio, out.ctypes.data, 1024, C.byref(n))
+    if rc:
+        raise Jpgb200Error(rc)
+    return out[: n.value].copy()
+
+
+def _c(a, dtype=np.uint8):
+    return np.ascontiguousarray(a, dtype=dtype).reshape(-1)
+
+
+class Encoder:
+    """One context on one GPU (jpgb200_create / jpgb200_destroy)."""
+
+    def __init__(self, device=0):
+        self._h = _vp()
+        rc = lib().jpgb200_create(C.byref(self._h), device)
+        if rc:
+            raise Jpgb200Error(rc)
+        self.device = device
+
+    def close(self):
+        if self._h:
+            lib().jpgb200_destroy(self._h)
+            self._h = _vp()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc:
+            raise Jpgb200Error(rc, lib().jpgb200_last_error(self._h).decode())
+
+    # ---- configuration
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(lib().jpgb200_set_stream(self._h, cuda_stream_ptr))
+
+    def sync(self):
+        self._ck(lib().jpgb200_sync(self._h))
+
+    def set_oob_bytes(self, oob):
+        oob = _c(oob)
+        assert oob.size == 24
+        self._ck(lib().jpgb200_set_oob_bytes(self._h, oob.ctypes.data))
+
+    # ---- encode
+    def encode_planar(self, r, g, b, w, h, quality, ratio=0, cap=None):
+        r, g, b = _c(r), _c(g), _c(b)
+        cap = cap or (w * h * 3 + 65536)
+        out = np.empty(cap, np.uint8)
+        n = C.c_size_t(0)
+        self._ck(lib().jpgb200_encode_planar(self._h, r.ctypes.data, g.ctypes.data, b.ctypes.data, w, h, quality, ratio,
+                                            out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value].copy()
+
+    def encode_rgb(self, rgb, w, h, quality, ratio=0, cap=None):
+        rgb = _c(rgb)
+        cap = cap or (w * h * 3 + 65536)
+        out = np.empty(cap, np.uint8)
+        n = C.c_size_t(0)
+        self._ck(lib().jpgb200_encode_rgb(self._h, rgb.ctypes.data, w, h, quality, ratio, out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value].copy()
+
+    def encode_device(self, d_r, d_g, d_b, w, h, quality, ratio, d_out, cap, d_len=None):
+        self._ck(lib().jpgb200_encode_device(self._h, d_r, d_g, d_b, w, h, quality, ratio, d_out, cap, d_len))
+
+    def encode_batch_device(self, d_planes, n_frames, w, h, quality, ratio, d_out, out_stride, d_lens=None):
+        self._ck(lib().jpgb200_encode_batch_device(self._h, d_planes, n_frames, w, h, quality, ratio, d_out, out_stride, d_lens))
+
+    def encode_batch_host(self, frame_ptrs, w, h, quality, ratio, out_ptrs, cap):
+        n = len(frame_ptrs)
+        fa = (_vp * n)(*frame_ptrs)
+        oa = (_vp * n)(*out_ptrs)
+        lens = (C.c_size_t * n)()
+        self._ck(lib().jpgb200_encode_batch_host(self._h, fa, n, w, h, quality, ratio, oa, cap, lens))
+        return [int(x) for x in lens]
+
+    # ---- parity taps
+    def coefficients(self, r, g, b, w, h, quality, ratio=0):
+        r, g, b = _c(r), _c(g), _c(b)
+        n = num_blocks(w, h, ratio)
+        zz = np.empty((sum(n), 64), np.int16)
+        self._ck(lib().jpgb200_coefficients(self._h, r.ctypes.data, g.ctypes.data, b.ctypes.data, w, h, quality, ratio, zz.ctypes.data))
+        self._n = n
+        return zz
+
+    def dc_sequence(self, mode):
+        d = np.empty(sum(self._n), np.int32)
+        self._ck(lib().jpgb200_dc_sequence(self._h, mode, d.ctypes.data))
+        return d
+
+    def histograms(self, dc_mode, sym_mode):
+        f = np.zeros((4, 257), np.int32)
+        self._ck(lib().jpgb200_histograms(self._h, dc_mode, sym_mode, f.ctypes.data))
+        return f
+
+    def block_bit_offsets(self):
+        off = np.empty(sum(self._n) + 1, np.uint64)
+        self._ck(lib().jpgb200_block_bit_offsets(self._h, off.ctypes.data))
+        return off
+
+    # ---- staged FP64 block API
+    def stage_dct(self, blocks):
+        b = np.ascontiguousarray(blocks, np.float64).reshape(-1, 64).copy()
+        self._ck(lib().jpgb200_stage_dct(self._h, b.ctypes.data, b.shape[0]))
+        return b
+
+    def stage_quantise(self, blocks, table):
+        b = np.ascontiguousarray(blocks, np.float64).reshape(-1, 64).copy()
+        t = _c(table, np.int32)
+        self._ck(lib().jpgb200_stage_quantise(self._h, b.ctypes.data, b.shape[0], t.ctypes.data))
+        return b
+
+    def stage_zigzag(self, blocks):
+        b = np.ascontiguousarray(blocks, np.float64).reshape(-1, 64)
+        zz = np.zeros((b.shape[0], 64), np.int32)
+        self._ck(lib().jpgb200_stage_zigzag(self._h, b.ctypes.data, b.shape[0], zz.ctypes.data))
+        return zz
+
+    # ---- device helpers
+    def malloc(self, nbytes):
+        p = _vp()
+        self._ck(lib().jpgb200_malloc(self._h, C.byref(p), nbytes))
+        return p.value
+
+    def free(self, p):
+        self._ck(lib().jpgb200_free(self._h, p))
+
+    def h2d(self, dptr, arr):
+        arr = np.ascontiguousarray(arr)
+        self._ck(lib().jpgb200_memcpy_h2d(self._h, dptr, arr.ctypes.data, arr.nbytes))
+
+    def d2h(self, dptr, nbytes):
+        out = np.empty(nbytes, np.uint8)
+        self._ck(lib().jpgb200_memcpy_d2h(self._h, out.ctypes.data, dptr, nbytes))
+        return out
+
+    def synth_device(self, d_planes, w, h, seed, frame=0, kind=0):
+        self._ck(lib().jpgb200_synth_device(self._h, d_planes, w, h, seed, frame, kind))
+
+    # ---- measurement
+    def set_profiling(self, on):
+        self._ck(lib().jpgb200_set_profiling(self._h, 1 if on else 0))
+
+    def reset_profile(self):
+        self._ck(lib().jpgb200_reset_profile(self._h))
+
+    def kernel_times(self):
+        ms = (C.c_double * NUM_KERNELS)()
+        ln = (C.c_longlong * NUM_KERNELS)()
+        self._ck(lib().jpgb200_kernel_times(self._h, ms, ln))
+        names = [lib().jpgb200_kernel_name(i).decode() for i in range(NUM_KERNELS)]
+        return {names[i]: (float(ms[i]), int(ln[i])) for i in range(NUM_KERNELS)}
+
+    def launch_count(self):
+        return int(lib().jpgb200_launch_count(self._h))
+
+
+def pinned_empty(nbytes):
+    """numpy view of pinned host memory (jpgb200_host_alloc); keep the returned owner alive."""
+    p = _vp()
+    rc = lib().jpgb200_host_alloc(C.byref(p), nbytes)
+    if rc:
+        raise Jpgb200Error(rc)
+    buf = (C.c_uint8 * nbytes).from_address(p.value)
+    arr = np.frombuffer(buf, dtype=np.uint8)
+    return arr, p.value
+
+
+def pinned_free(ptr):
+    lib().jpgb200_host_free(ptr)

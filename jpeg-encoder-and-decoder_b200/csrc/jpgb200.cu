@@ -1,0 +1,1046 @@
+/*
+ * libjpgb200.so -- context, launch sequencing and the extern "C" boundary declared in
+ * include/jpgb200.h.  Build: see jpeg-encoder-and-decoder_b200/build.py
+ *   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -shared -Xcompiler -fPIC
+ *
+ * Launch sequence of one encode (one stream, no host synchronisation in between):
+ *   K1 k1_transform   pixels -> int16 zig-zag coefficients           (HBM-bound, 9 B/px)
+ *   K3 k3_block_bits  per-block code length, per-chunk offsets + totals
+ *   K4 k4_scan_chunks device-wide exclusive scan of chunk totals (uint64)
+ *   KZ k_zero_ubuf    clear the words the packer ORs into
+ *   K5 k5_pack        every block writes its codes at its global bit offset
+ *   K6 k6_count / k6_scan / k6_scatter  0xFF00 stuffing by a second length/offset scan,
+ *      header and EOI written by k6_scan
+ * There is no CPU arithmetic path in this library.
+ */
+#include <cuda_runtime.h>
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <vector>
+
+#include "../../include/jpgb200.h"
+#include "entropy.cuh"
+#include "jpgb200_math.cuh"
+#include "jpgb200_tables.h"
+#include "k1_transform.cuh"
+#include "stuffing.cuh"
+#include "taps.cuh"
+
+using namespace jpgb200;
+
+enum { KI_K1 = 0, KI_K3, KI_K4, KI_ZERO, KI_K5, KI_K6COUNT, KI_K6SCAN, KI_K6SCATTER };
+static const char *kKernelNames[JPGB200_NUM_KERNELS] = {"k1_transform", "k3_block_bits", "k4_scan_chunks", "k_zero_ubuf",
+                                                        "k5_pack",      "k6_count",      "k6_scan",        "k6_scatter"};
+
+struct EvPair {
+    int k;
+    cudaEvent_t a, b;
+};
+
+struct jpgb200_ctx {
+    int device;
+    int sm_count;
+    cudaStream_t own_stream, stream, copy_in, copy_out;
+    HuffDev *d_huff;
+    int *d_scan_order;
+    uint8_t oob[24];
+    /* workspaces, grown on demand */
+    uint8_t *d_planes[2];
+    size_t planes_cap;
+    int16_t *d_zz;
+    size_t zz_cap;
+    uint32_t *d_local_off;
+    size_t local_cap;
+    uint32_t *d_cta_bits;
+    unsigned long long *d_cta_base;
+    size_t cta_cap;
+    uint32_t *d_ubuf;
+    size_t ubuf_cap;
+    uint32_t *d_tile_ff;
+    unsigned long long *d_tile_base;
+    size_t tile_cap;
+    EncState *d_state;
+    uint8_t *d_header;
+    int hdr_w, hdr_h, hdr_q, hdr_ratio, hdr_len;
+    uint8_t *d_out[2];
+    size_t out_cap;
+    unsigned long long *d_len;  /* device */
+    unsigned long long *h_len;  /* pinned host, 2 slots, also mapped for kernels */
+    int *d_dc;
+    size_t dc_cap;
+    int *d_tile_sum;
+    size_t tile_sum_cap;
+    int *d_freq;
+    /* geometry of the last transform */
+    int w, h, q, ratio;
+    long long n[3];
+    bool have_bits;
+    /* quantiser cache */
+    int q_cached;
+    float mul[2][64];
+    /* profiling */
+    bool profiling;
+    std::vector<EvPair> pending;
+    std::vector<cudaEvent_t> free_events;
+    double ms[JPGB200_NUM_KERNELS];
+    long long launches[JPGB200_NUM_KERNELS];
+    long long launch_total;
+    char err[256];
+};
+
+#define CK(call)                                                                                         \
+    do {                                                                                                 \
+        cudaError_t e_ = (call);                                                                         \
+        if (e_ != cudaSuccess) {                                                                         \
+            snprintf(ctx->err, sizeof ctx->err, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                                                \
+            return JPGB200_ERR_CUDA;                                                                     \
+        }                                                                                                \
+    } while (0)
+
+/* ---- small host helpers ---------------------------------------------------------------- */
+
+extern "C" const char *jpgb200_strerror(int code)
+{
+    switch (code) {
+    case JPGB200_OK: return "ok";
+    case JPGB200_ERR_NO_DEVICE: return "no usable CUDA device (this library has no CPU fallback)";
+    case JPGB200_ERR_BAD_DIMS: return "width/height must be multiples of 8 (16 wide for 4:2:2)";
+    case JPGB200_ERR_BAD_QUALITY: return "quality must be in 24..97";
+    case JPGB200_ERR_CUDA: return "CUDA error (see jpgb200_last_error)";
+    case JPGB200_ERR_OUT_TOO_SMALL: return "output buffer too small";
+    case JPGB200_ERR_BAD_ARG: return "bad argument";
+    case JPGB200_ERR_NOMEM: return "out of memory";
+    default: return "unknown error";
+    }
+}
+
+extern "C" const char *jpgb200_kernel_name(int k) { return (k >= 0 && k < JPGB200_NUM_KERNELS) ? kKernelNames[k] : ""; }
+
+extern "C" int jpgb200_quant_tables(int quality, int lum[64], int chr[64])
+{
+    if (quality < 1 || quality > 100) return JPGB200_ERR_BAD_QUALITY;
+    int rc = JPGB200_OK;
+    for (int i = 0; i < 64; i++) {
+        lum[i] = scale_quant_entry(kBaseLum[i], quality);
+        chr[i] = scale_quant_entry(kBaseChr[i], quality);
+        if (lum[i] < 1 || lum[i] > 255 || chr[i] < 1 || chr[i] > 255) rc = JPGB200_ERR_BAD_QUALITY;
+    }
+    return rc;
+}
+
+extern "C" long long jpgb200_num_blocks(int w, int h, int ratio, long long n[3])
+{
+    if (w <= 0 || h <= 0 || (h % 8) || (ratio != 0 && ratio != 1)) return JPGB200_ERR_BAD_DIMS;
+    if (w % (ratio ? 16 : 8)) return JPGB200_ERR_BAD_DIMS;
+    long long ny = (long long)(w / 8) * (h / 8);
+    long long nc = ratio ? ny / 2 : ny;
+    if (n) {
+        n[0] = ny;
+        n[1] = nc;
+        n[2] = nc;
+    }
+    return ny + 2 * nc;
+}
+
+/* canonical codes from the tables.h specs (T.81 Annex C) */
+static void build_huff(HuffDev *h)
+{
+    memset(h, 0, sizeof *h);
+    for (int t = 0; t < 4; t++) {
+        HuffSpec sp = huff_spec(t);
+        unsigned code = 0;
+        int k = 0;
+        for (int l = 1; l <= 16; l++) {
+            for (int i = 0; i < sp.nr[l]; i++) {
+                const int sym = sp.vals[k++];
+                const uint32_t e = ((uint32_t)code << 8) | (uint32_t)l;
+                if (t < 2)
+                    h->dc[t][sym] = e;
+                else
+                    h->ac[t - 2][sym] = e;
+                code++;
+            }
+            code <<= 1;
+        }
+    }
+}
+
+static size_t put16(uint8_t *o, size_t p, unsigned v)
+{
+    o[p] = (uint8_t)(v >> 8);
+    o[p + 1] = (uint8_t)v;
+    return p + 2;
+}
+
+/* JFIF marker segments SOI..SOS (T.81 Annex B).  The DQT carries, at zig-zag
+ * position of (v,u), the divisor the reference actually applies there: T'[u][v]. */
+extern "C" int jpgb200_jfif_header(int w, int h, int quality, int ratio, uint8_t *o, size_t cap, size_t *len)
+{
+    int lum[64], chr[64];
+    if (jpgb200_num_blocks(w, h, ratio, NULL) < 0) return JPGB200_ERR_BAD_DIMS;
+    if (w > 65535 || h > 65535) return JPGB200_ERR_BAD_DIMS;
+    if (quality < 24 || quality > 97 || jpgb200_quant_tables(quality, lum, chr)) return JPGB200_ERR_BAD_QUALITY;
+    if (cap < 640) return JPGB200_ERR_OUT_TOO_SMALL;
+    size_t p = 0;
+    p = put16(o, p, 0xFFD8);
+    p = put16(o, p, 0xFFE0);
+    p = put16(o, p, 16);
+    memcpy(o + p, "JFIF\0", 5);
+    p += 5;
+    o[p++] = 1;
+    o[p++] = 1;
+    o[p++] = 0;
+    p = put16(o, p, 1);
+    p = put16(o, p, 1);
+    o[p++] = 0;
+    o[p++] = 0;
+    for (int t = 0; t < 2; t++) {
+        const int *tab = t ? chr : lum;
+        p = put16(o, p, 0xFFDB);
+        p = put16(o, p, 67);
+        o[p++] = (uint8_t)t;
+        for (int v = 0; v < 8; v++)
+            for (int u = 0; u < 8; u++) o[p + kZigZag[v * 8 + u]] = (uint8_t)tab[u * 8 + v];
+        p += 64;
+    }
+    p = put16(o, p, 0xFFC0);
+    p = put16(o, p, 17);
+    o[p++] = 8;
+    p = put16(o, p, (unsigned)h);
+    p = put16(o, p, (unsigned)w);
+    o[p++] = 3;
+    const uint8_t sof[9] = {1, (uint8_t)(ratio == 1 ? 0x21 : 0x11), 0, 2, 0x11, 1, 3, 0x11, 1};
+    memcpy(o + p, sof, 9);
+    p += 9;
+    static const int order[4] = {0, 2, 1, 3};
+    static const uint8_t tcth[4] = {0x00, 0x10, 0x01, 0x11};
+    for (int i = 0; i < 4; i++) {
+        HuffSpec sp = huff_spec(order[i]);
+        p = put16(o, p, 0xFFC4);
+        p = put16(o, p, (unsigned)(2 + 1 + 16 + sp.nvals));
+        o[p++] = tcth[i];
+        memcpy(o + p, sp.nr + 1, 16);
+        p += 16;
+        memcpy(o + p, sp.vals, (size_t)sp.nvals);
+        p += (size_t)sp.nvals;
+    }
+    p = put16(o, p, 0xFFDA);
+    p = put16(o, p, 12);
+    const uint8_t sos[10] = {3, 1, 0x00, 2, 0x11, 3, 0x11, 0, 63, 0};
+    memcpy(o + p, sos, 10);
+    p += 10;
+    if (len) *len = p;
+    return JPGB200_OK;
+}
+
+/* ---- context --------------------------------------------------------------------------- */
+
+extern "C" int jpgb200_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
+{
+    if (!out) return JPGB200_ERR_BAD_ARG;
+    *out = NULL;
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess || n <= 0 || device < 0 || device >= n) return JPGB200_ERR_NO_DEVICE;
+    jpgb200_ctx *ctx = new jpgb200_ctx();
+    memset(ctx->oob, 0, sizeof ctx->oob);
+    ctx->device = device;
+    ctx->q_cached = -1;
+    ctx->hdr_w = -1;
+    ctx->err[0] = 0;
+    cudaDeviceProp prop;
+    if (cudaSetDevice(device) != cudaSuccess || cudaGetDeviceProperties(&prop, device) != cudaSuccess) {
+        delete ctx;
+        return JPGB200_ERR_NO_DEVICE;
+    }
+    ctx->sm_count = prop.multiProcessorCount;
+    HuffDev hh;
+    build_huff(&hh);
+    int rc = [&]() -> int {
+        CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        ctx->stream = ctx->own_stream;
+        CK(cudaMalloc(&ctx->d_huff, sizeof(HuffDev)));
+        CK(cudaMemcpy(ctx->d_huff, &hh, sizeof hh, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&ctx->d_scan_order, 64 * sizeof(int)));
+        CK(cudaMemcpy(ctx->d_scan_order, kZigZag, 64 * sizeof(int), cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&ctx->d_state, sizeof(EncState)));
+        CK(cudaMemset(ctx->d_state, 0, sizeof(EncState)));
+        CK(cudaMalloc(&ctx->d_header, 1024));
+        CK(cudaMalloc(&ctx->d_len, 2 * sizeof(unsigned long long)));
+        CK(cudaHostAlloc(&ctx->h_len, 2 * sizeof(unsigned long long), cudaHostAllocMapped));
+        CK(cudaMalloc(&ctx->d_freq, 4 * 257 * sizeof(int)));
+        return JPGB200_OK;
+    }();
+    if (rc != JPGB200_OK) {
+        fprintf(stderr, "jpgb200_create: %s\n", ctx->err);
+        delete ctx;
+        return rc;
+    }
+    *out = ctx;
+    return JPGB200_OK;
+}
+
+extern "C" void jpgb200_destroy(jpgb200_ctx *ctx)
+{
+    if (!ctx) return;
+    cudaSetDevice(ctx->device);
+    cudaDeviceSynchronize();
+    void *ptrs[] = {ctx->d_huff,     ctx->d_scan_order, ctx->d_planes[0], ctx->d_planes[1], ctx->d_zz,   ctx->d_local_off,
+                    ctx->d_cta_bits, ctx->d_cta_base,   ctx->d_ubuf,      ctx->d_tile_ff,   ctx->d_tile_base,
+                    ctx->d_state,    ctx->d_header,     ctx->d_out[0],    ctx->d_out[1],    ctx->d_len,  ctx->d_dc,
+                    ctx->d_tile_sum, ctx->d_freq};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    if (ctx->h_len) cudaFreeHost(ctx->h_len);
+    for (auto &e : ctx->pending) {
+        cudaEventDestroy(e.a);
+        cudaEventDestroy(e.b);
+    }
+    for (auto &e : ctx->free_events) cudaEventDestroy(e);
+    cudaStreamDestroy(ctx->own_stream);
+    cudaStreamDestroy(ctx->copy_in);
+    cudaStreamDestroy(ctx->copy_out);
+    delete ctx;
+}
+
+extern "C" const char *jpgb200_last_error(const jpgb200_ctx *ctx) { return ctx ? ctx->err : ""; }
+
+extern "C" int jpgb200_set_stream(jpgb200_ctx *ctx, void *s)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_sync(jpgb200_ctx *ctx)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_set_oob_bytes(jpgb200_ctx *ctx, const uint8_t oob[24])
+{
+    if (!ctx || !oob) return JPGB200_ERR_BAD_ARG;
+    memcpy(ctx->oob, oob, 24);
+    return JPGB200_OK;
+}
+
+/* ---- profiling --------------------------------------------------------------------------- */
+
+static cudaEvent_t get_event(jpgb200_ctx *ctx)
+{
+    if (!ctx->free_events.empty()) {
+        cudaEvent_t e = ctx->free_events.back();
+        ctx->free_events.pop_back();
+        return e;
+    }
+    cudaEvent_t e;
+    cudaEventCreate(&e);
+    return e;
+}
+
+struct LaunchScope {
+    jpgb200_ctx *ctx;
+    int k;
+    cudaEvent_t a, b;
+    LaunchScope(jpgb200_ctx *c, int kk) : ctx(c), k(kk)
+    {
+        if (ctx->profiling) {
+            a = get_event(ctx);
+            b = get_event(ctx);
+            cudaEventRecord(a, ctx->stream);
+        }
+    }
+    ~LaunchScope()
+    {
+        ctx->launch_total++;
+        ctx->launches[k]++;
+        if (ctx->profiling) {
+            cudaEventRecord(b, ctx->stream);
+            ctx->pending.push_back({k, a, b});
+        }
+    }
+};
+
+static int resolve_profile(jpgb200_ctx *ctx)
+{
+    if (ctx->pending.empty()) return JPGB200_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (auto &e : ctx->pending) {
+        float ms = 0.f;
+        CK(cudaEventElapsedTime(&ms, e.a, e.b));
+        ctx->ms[e.k] += (double)ms;
+        ctx->free_events.push_back(e.a);
+        ctx->free_events.push_back(e.b);
+    }
+    ctx->pending.clear();
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_set_profiling(jpgb200_ctx *ctx, int on)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    int rc = resolve_profile(ctx);
+    ctx->profiling = on != 0;
+    return rc;
+}
+
+extern "C" int jpgb200_reset_profile(jpgb200_ctx *ctx)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    int rc = resolve_profile(ctx);
+    for (int i = 0; i < JPGB200_NUM_KERNELS; i++) {
+        ctx->ms[i] = 0.0;
+        ctx->launches[i] = 0;
+    }
+    return rc;
+}
+
+extern "C" int jpgb200_kernel_times(jpgb200_ctx *ctx, double *ms, long long *launches)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    int rc = resolve_profile(ctx);
+    for (int i = 0; i < JPGB200_NUM_KERNELS; i++) {
+        if (ms) ms[i] = ctx->ms[i];
+        if (launches) launches[i] = ctx->launches[i];
+    }
+    return rc;
+}
+
+extern "C" long long jpgb200_launch_count(const jpgb200_ctx *ctx) { return ctx ? ctx->launch_total : 0; }
+
+/* ---- workspaces -------------------------------------------------------------------------- */
+
+template <class T>
+static int grow(jpgb200_ctx *ctx, T **p, size_t *cap, size_t need_bytes)
+{
+    if (*cap >= need_bytes && *p) return JPGB200_OK;
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (*p) CK(cudaFree(*p));
+    *p = NULL;
+    *cap = 0;
+    size_t want = need_bytes + need_bytes / 8 + 4096;
+    cudaError_t e = cudaMalloc((void **)p, want);
+    if (e != cudaSuccess) {
+        snprintf(ctx->err, sizeof ctx->err, "cudaMalloc(%zu) failed: %s", want, cudaGetErrorString(e));
+        return JPGB200_ERR_NOMEM;
+    }
+    *cap = want;
+    return JPGB200_OK;
+}
+
+static int validate(int w, int h, int quality, int ratio, long long n[3])
+{
+    if (jpgb200_num_blocks(w, h, ratio, n) < 0) return JPGB200_ERR_BAD_DIMS;
+    if (w > 65535 || h > 65535) return JPGB200_ERR_BAD_DIMS; /* SOF0 fields are 16 bit */
+    if (quality < 24 || quality > 97) return JPGB200_ERR_BAD_QUALITY;
+    return JPGB200_OK;
+}
+
+static long long n_chunks(const long long n[3]) { return (n[1] + EC_MCUS - 1) / EC_MCUS; }
+
+static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_zz)
+{
+    const long long nb = n[0] + n[1] + n[2];
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_zz, &ctx->zz_cap, (size_t)nb * 128 * (size_t)nframes_zz))) return rc;
+    if ((rc = grow(ctx, &ctx->d_local_off, &ctx->local_cap, (size_t)nb * 4))) return rc;
+    const size_t nc = (size_t)n_chunks(n);
+    if (ctx->cta_cap < nc * 8 || !ctx->d_cta_bits) {
+        size_t c1 = 0, c2 = 0;
+        if (ctx->d_cta_bits) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaFree(ctx->d_cta_bits));
+            CK(cudaFree(ctx->d_cta_base));
+            ctx->d_cta_bits = NULL;
+            ctx->d_cta_base = NULL;
+        }
+        if ((rc = grow(ctx, &ctx->d_cta_bits, &c1, nc * 4))) return rc;
+        if ((rc = grow(ctx, &ctx->d_cta_base, &c2, nc * 8))) return rc;
+        ctx->cta_cap = nc * 8;
+    }
+    /* worst case 1658 bits per block (20-bit DC + 63 x 26-bit AC) */
+    const size_t ub = (size_t)nb * 208 + 65536;
+    if ((rc = grow(ctx, &ctx->d_ubuf, &ctx->ubuf_cap, ub))) return rc;
+    const size_t nt = ctx->ubuf_cap / K6_TILE + 2;
+    if (ctx->tile_cap < nt || !ctx->d_tile_ff) {
+        size_t c1 = 0, c2 = 0;
+        if (ctx->d_tile_ff) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaFree(ctx->d_tile_ff));
+            CK(cudaFree(ctx->d_tile_base));
+            ctx->d_tile_ff = NULL;
+            ctx->d_tile_base = NULL;
+        }
+        if ((rc = grow(ctx, &ctx->d_tile_ff, &c1, nt * 4))) return rc;
+        if ((rc = grow(ctx, &ctx->d_tile_base, &c2, nt * 8))) return rc;
+        ctx->tile_cap = nt;
+    }
+    return JPGB200_OK;
+}
+
+static int ensure_tables(jpgb200_ctx *ctx, int w, int h, int quality, int ratio)
+{
+    if (ctx->q_cached != quality) {
+        int lum[64], chr[64];
+        if (jpgb200_quant_tables(quality, lum, chr)) return JPGB200_ERR_BAD_QUALITY;
+        make_quant_multipliers(lum, ctx->mul[0]);
+        make_quant_multipliers(chr, ctx->mul[1]);
+        ctx->q_cached = quality;
+    }
+    if (ctx->hdr_w != w || ctx->hdr_h != h || ctx->hdr_q != quality || ctx->hdr_ratio != ratio) {
+        uint8_t hdr[1024];
+        size_t len = 0;
+        int rc = jpgb200_jfif_header(w, h, quality, ratio, hdr, sizeof hdr, &len);
+        if (rc) return rc;
+        CK(cudaMemcpyAsync(ctx->d_header, hdr, len, cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream)); /* hdr is a stack buffer */
+        ctx->hdr_w = w;
+        ctx->hdr_h = h;
+        ctx->hdr_q = quality;
+        ctx->hdr_ratio = ratio;
+        ctx->hdr_len = (int)len;
+    }
+    return JPGB200_OK;
+}
+
+/* ---- launch sequencing --------------------------------------------------------------------- */
+
+static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w, int h,
+                     int ratio, const long long n[3], int nframes, long long plane_stride, int16_t *zz,
+                     long long zz_stride, int has_halo)
+{
+    K1Params p;
+    p.r = d_r;
+    p.g = d_g;
+    p.b = d_b;
+    p.zz_y = zz;
+    p.zz_cb = zz + n[0] * 64;
+    p.zz_cr = zz + (n[0] + n[1]) * 64;
+    p.plane_stride = plane_stride;
+    p.zz_stride = zz_stride;
+    p.W = w;
+    p.H = h;
+    p.BW = w / 8;
+    p.has_halo = has_halo;
+    memcpy(p.mul, ctx->mul, sizeof p.mul);
+    memcpy(p.oob, ctx->oob, 24);
+    dim3 grid((unsigned)((p.BW + K1_TILE_BLOCKS - 1) / K1_TILE_BLOCKS), (unsigned)(h / 8), (unsigned)nframes);
+    {
+        LaunchScope ls(ctx, KI_K1);
+        if (ratio == 0)
+            k1_transform<0><<<grid, K1_THREADS, 0, ctx->stream>>>(p);
+        else
+            k1_transform<1><<<grid, K1_THREADS, 0, ctx->stream>>>(p);
+    }
+    CK(cudaGetLastError());
+    return JPGB200_OK;
+}
+
+static void fill_ec(jpgb200_ctx *ctx, EcParams &e, const int16_t *zz, const long long n[3])
+{
+    e.zz_y = zz;
+    e.zz_cb = zz + n[0] * 64;
+    e.zz_cr = zz + (n[0] + n[1]) * 64;
+    e.n_mcu = n[1];
+    e.dc_pred[0] = e.dc_pred[1] = e.dc_pred[2] = 0;
+    e.is_last_band = 1;
+    e.local_off = ctx->d_local_off;
+    e.cta_bits = ctx->d_cta_bits;
+    e.cta_base = ctx->d_cta_base;
+    e.bit_base = 0;
+    e.ubuf = ctx->d_ubuf;
+    e.st = ctx->d_state;
+}
+
+/* K3 + K4: bit lengths and their device-wide exclusive scan */
+static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3])
+{
+    EcParams e;
+    fill_ec(ctx, e, zz, n);
+    const unsigned nc = (unsigned)n_chunks(n);
+    {
+        LaunchScope ls(ctx, KI_K3);
+        if (ratio == 0)
+            k3_block_bits<0><<<nc, EcCfg<0>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
+        else
+            k3_block_bits<1><<<nc, EcCfg<1>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
+    }
+    CK(cudaGetLastError());
+    {
+        LaunchScope ls(ctx, KI_K4);
+        k4_scan_chunks<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->d_cta_bits, ctx->d_cta_base, (long long)nc, ctx->d_state,
+                                                           K6_TILE, (unsigned long long)ctx->ubuf_cap);
+    }
+    CK(cudaGetLastError());
+    ctx->have_bits = true;
+    return JPGB200_OK;
+}
+
+/* KZ + K5 + K6: pack and stuff into d_out */
+static int launch_pack(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3], uint8_t *d_out, size_t cap,
+                       unsigned long long *len_out)
+{
+    EcParams e;
+    fill_ec(ctx, e, zz, n);
+    const unsigned nc = (unsigned)n_chunks(n);
+    const unsigned pgrid = (unsigned)ctx->sm_count * 8;
+    {
+        LaunchScope ls(ctx, KI_ZERO);
+        k_zero_ubuf<<<pgrid, 256, 0, ctx->stream>>>(reinterpret_cast<uint4 *>(ctx->d_ubuf), ctx->d_state);
+    }
+    CK(cudaGetLastError());
+    {
+        LaunchScope ls(ctx, KI_K5);
+        if (ratio == 0)
+            k5_pack<0><<<nc, EcCfg<0>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
+        else
+            k5_pack<1><<<nc, EcCfg<1>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
+    }
+    CK(cudaGetLastError());
+    {
+        LaunchScope ls(ctx, KI_K6COUNT);
+        k6_count<<<pgrid, K6_THREADS, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(ctx->d_ubuf), ctx->d_state,
+                                                        ctx->d_tile_ff);
+    }
+    CK(cudaGetLastError());
+    {
+        LaunchScope ls(ctx, KI_K6SCAN);
+        k6_scan<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->d_tile_ff, ctx->d_tile_base, ctx->d_state, ctx->d_header,
+                                                    ctx->hdr_len, d_out, (unsigned long long)cap, len_out);
+    }
+    CK(cudaGetLastError());
+    {
+        LaunchScope ls(ctx, KI_K6SCATTER);
+        k6_scatter<<<pgrid, K6_THREADS, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(ctx->d_ubuf), ctx->d_state,
+                                                          ctx->d_tile_base, d_out, ctx->hdr_len);
+    }
+    CK(cudaGetLastError());
+    return JPGB200_OK;
+}
+
+static int encode_core(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w, int h,
+                       int quality, int ratio, uint8_t *d_out, size_t cap, unsigned long long *len_out)
+{
+    long long n[3];
+    int rc = validate(w, h, quality, ratio, n);
+    if (rc) return rc;
+    if ((rc = ensure_workspace(ctx, n, 1))) return rc;
+    if ((rc = ensure_tables(ctx, w, h, quality, ratio))) return rc;
+    ctx->w = w;
+    ctx->h = h;
+    ctx->q = quality;
+    ctx->ratio = ratio;
+    memcpy(ctx->n, n, sizeof n);
+    if ((rc = launch_k1(ctx, d_r, d_g, d_b, w, h, ratio, n, 1, 0, ctx->d_zz, 0, 0))) return rc;
+    if ((rc = launch_bits(ctx, ctx->d_zz, ratio, n))) return rc;
+    if (d_out) rc = launch_pack(ctx, ctx->d_zz, ratio, n, d_out, cap, len_out);
+    return rc;
+}
+
+/* ---- public encode entry points -------------------------------------------------------------- */
+
+extern "C" int jpgb200_encode_device(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w,
+                                     int h, int quality, int ratio, uint8_t *d_out, size_t cap,
+                                     unsigned long long *d_len)
+{
+    if (!ctx || !d_r || !d_g || !d_b || !d_out) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    return encode_core(ctx, d_r, d_g, d_b, w, h, quality, ratio, d_out, cap, d_len ? d_len : ctx->d_len);
+}
+
+extern "C" int jpgb200_encode_batch_device(jpgb200_ctx *ctx, const uint8_t *d_planes, int n_frames, int w, int h,
+                                           int quality, int ratio, uint8_t *d_out, size_t out_stride,
+                                           unsigned long long *d_lens)
+{
+    if (!ctx || !d_planes || !d_out || n_frames < 0) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)w * h;
+    for (int f = 0; f < n_frames; f++) {
+        const uint8_t *pl = d_planes + (size_t)f * 3 * npx;
+        int rc = encode_core(ctx, pl, pl + npx, pl + 2 * npx, w, h, quality, ratio, d_out + (size_t)f * out_stride,
+                             out_stride, d_lens ? d_lens + f : ctx->d_len);
+        if (rc) return rc;
+    }
+    return JPGB200_OK;
+}
+
+static int ensure_io(jpgb200_ctx *ctx, size_t npx, size_t cap, int slots)
+{
+    int rc;
+    for (int s = 0; s < slots; s++) {
+        size_t c = ctx->planes_cap;
+        if ((rc = grow(ctx, &ctx->d_planes[s], &c, 3 * npx))) return rc;
+        if (s == slots - 1) ctx->planes_cap = c;
+    }
+    for (int s = 0; s < slots; s++) {
+        size_t c = ctx->out_cap;
+        if ((rc = grow(ctx, &ctx->d_out[s], &c, cap))) return rc;
+        if (s == slots - 1) ctx->out_cap = c;
+    }
+    return JPGB200_OK;
+}
+
+static int finish_host(jpgb200_ctx *ctx, uint8_t *d_out, uint8_t *out, size_t cap, size_t *len)
+{
+    unsigned long long l = 0;
+    CK(cudaMemcpyAsync(&l, ctx->d_len, sizeof l, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (l == 0 || l > cap) return JPGB200_ERR_OUT_TOO_SMALL;
+    CK(cudaMemcpyAsync(out, d_out, (size_t)l, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (len) *len = (size_t)l;
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_encode_planar(jpgb200_ctx *ctx, const uint8_t *r, const uint8_t *g, const uint8_t *b, int w, int h,
+                                     int quality, int ratio, uint8_t *out, size_t cap, size_t *len)
+{
+    if (!ctx || !r || !g || !b || !out) return JPGB200_ERR_BAD_ARG;
+    long long n[3];
+    int rc = validate(w, h, quality, ratio, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)w * h;
+    /* slots are re-grown together so both plane buffers always share planes_cap */
+    if (ctx->planes_cap < 3 * npx || ctx->out_cap < cap || !ctx->d_planes[1] || !ctx->d_out[1]) {
+        if ((rc = ensure_io(ctx, npx, cap, 2))) return rc;
+    }
+    uint8_t *dp = ctx->d_planes[0];
+    CK(cudaMemcpyAsync(dp, r, npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dp + npx, g, npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dp + 2 * npx, b, npx, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = encode_core(ctx, dp, dp + npx, dp + 2 * npx, w, h, quality, ratio, ctx->d_out[0], cap, ctx->d_len))) return rc;
+    return finish_host(ctx, ctx->d_out[0], out, cap, len);
+}
+
+extern "C" int jpgb200_encode_rgb(jpgb200_ctx *ctx, const uint8_t *rgb, int w, int h, int quality, int ratio, uint8_t *out,
+                                  size_t cap, size_t *len)
+{
+    if (!ctx || !rgb || !out) return JPGB200_ERR_BAD_ARG;
+    long long n[3];
+    int rc = validate(w, h, quality, ratio, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)w * h;
+    if (ctx->planes_cap < 3 * npx || ctx->out_cap < cap || !ctx->d_planes[1] || !ctx->d_out[1]) {
+        if ((rc = ensure_io(ctx, npx, cap, 2))) return rc;
+    }
+    /* interleaved upload into slot 1, de-interleave into slot 0 */
+    CK(cudaMemcpyAsync(ctx->d_planes[1], rgb, 3 * npx, cudaMemcpyHostToDevice, ctx->stream));
+    uint8_t *dp = ctx->d_planes[0];
+    ks_deinterleave<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(ctx->d_planes[1], dp, dp + npx, dp + 2 * npx,
+                                                                         (long long)npx);
+    ctx->launch_total++;
+    CK(cudaGetLastError());
+    if ((rc = encode_core(ctx, dp, dp + npx, dp + 2 * npx, w, h, quality, ratio, ctx->d_out[0], cap, ctx->d_len))) return rc;
+    return finish_host(ctx, ctx->d_out[0], out, cap, len);
+}
+
+/* Host batch: H2D of frame f+1 and D2H of frame f-1 overlap the kernels of frame f.
+ * The stream length reaches the host through mapped pinned memory written by k6_scan, so the
+ * only host wait per frame is on that frame's own completion event. */
+extern "C" int jpgb200_encode_batch_host(jpgb200_ctx *ctx, const uint8_t *const *frames, int n_frames, int w, int h,
+                                         int quality, int ratio, uint8_t *const *outs, size_t cap, size_t *lens)
+{
+    if (!ctx || !frames || !outs || n_frames < 0) return JPGB200_ERR_BAD_ARG;
+    long long n[3];
+    int rc = validate(w, h, quality, ratio, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)w * h;
+    if (ctx->planes_cap < 3 * npx || ctx->out_cap < cap || !ctx->d_planes[1] || !ctx->d_out[1]) {
+        if ((rc = ensure_io(ctx, npx, cap, 2))) return rc;
+    }
+    if ((rc = ensure_workspace(ctx, n, 1))) return rc;
+    if ((rc = ensure_tables(ctx, w, h, quality, ratio))) return rc;
+    unsigned long long *d_hlen = NULL;
+    CK(cudaHostGetDevicePointer((void **)&d_hlen, ctx->h_len, 0));
+    cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
+    for (int s = 0; s < 2; s++) {
+        CK(cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_done[s], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ev_out[s], cudaEventDisableTiming));
+    }
+    auto drain = [&](int f) -> int {
+        const int s = f & 1;
+        CK(cudaEventSynchronize(ev_done[s]));
+        const unsigned long long l = ctx->h_len[s];
+        if (l == 0 || l > cap) return JPGB200_ERR_OUT_TOO_SMALL;
+        CK(cudaMemcpyAsync(outs[f], ctx->d_out[s], (size_t)l, cudaMemcpyDeviceToHost, ctx->copy_out));
+        CK(cudaEventRecord(ev_out[s], ctx->copy_out));
+        if (lens) lens[f] = (size_t)l;
+        return JPGB200_OK;
+    };
+    rc = JPGB200_OK;
+    for (int f = 0; f < n_frames && rc == JPGB200_OK; f++) {
+        const int s = f & 1;
+        /* slot s is free once frame f-2's kernels (planes) and D2H (out) are done */
+        if (f >= 2) {
+            CK(cudaStreamWaitEvent(ctx->copy_in, ev_done[s], 0));
+            CK(cudaStreamWaitEvent(ctx->stream, ev_out[s], 0));
+        }
+        CK(cudaMemcpyAsync(ctx->d_planes[s], frames[f], 3 * npx, cudaMemcpyHostToDevice, ctx->copy_in));
+        CK(cudaEventRecord(ev_in[s], ctx->copy_in));
+        CK(cudaStreamWaitEvent(ctx->stream, ev_in[s], 0));
+        uint8_t *dp = ctx->d_planes[s];
+        rc = encode_core(ctx, dp, dp + npx, dp + 2 * npx, w, h, quality, ratio, ctx->d_out[s], cap, d_hlen + s);
+        if (rc) break;
+        CK(cudaEventRecord(ev_done[s], ctx->stream));
+        if (f >= 1) rc = drain(f - 1);
+    }
+    if (rc == JPGB200_OK && n_frames >= 1) rc = drain(n_frames - 1);
+    cudaStreamSynchronize(ctx->copy_out);
+    cudaStreamSynchronize(ctx->stream);
+    for (int s = 0; s < 2; s++) {
+        cudaEventDestroy(ev_in[s]);
+        cudaEventDestroy(ev_done[s]);
+        cudaEventDestroy(ev_out[s]);
+    }
+    return rc;
+}
+
+/* ---- parity taps -------------------------------------------------------------------------------- */
+
+extern "C" int jpgb200_coefficients(jpgb200_ctx *ctx, const uint8_t *r, const uint8_t *g, const uint8_t *b, int w, int h,
+                                    int quality, int ratio, int16_t *zz_out)
+{
+    if (!ctx || !r || !g || !b || !zz_out) return JPGB200_ERR_BAD_ARG;
+    long long n[3];
+    int rc = validate(w, h, quality, ratio, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)w * h;
+    if (ctx->planes_cap < 3 * npx || !ctx->d_planes[1] || !ctx->d_out[1]) {
+        if ((rc = ensure_io(ctx, npx, ctx->out_cap ? ctx->out_cap : 4096, 2))) return rc;
+    }
+    uint8_t *dp = ctx->d_planes[0];
+    CK(cudaMemcpyAsync(dp, r, npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dp + npx, g, npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(dp + 2 * npx, b, npx, cudaMemcpyHostToDevice, ctx->stream));
+    if ((rc = encode_core(ctx, dp, dp + npx, dp + 2 * npx, w, h, quality, ratio, NULL, 0, NULL))) return rc;
+    CK(cudaMemcpyAsync(zz_out, ctx->d_zz, (size_t)(n[0] + n[1] + n[2]) * 128, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JPGB200_OK;
+}
+
+static int run_dc_sequence(jpgb200_ctx *ctx, int mode)
+{
+    const long long nb = ctx->n[0] + ctx->n[1] + ctx->n[2];
+    int rc;
+    if ((rc = grow(ctx, &ctx->d_dc, &ctx->dc_cap, (size_t)nb * 4))) return rc;
+    long long off = 0;
+    for (int c = 0; c < 3; c++) {
+        const long long nc = ctx->n[c];
+        const unsigned tiles = (unsigned)((nc + K2_TILE - 1) / K2_TILE);
+        if ((rc = grow(ctx, &ctx->d_tile_sum, &ctx->tile_sum_cap, (size_t)tiles * 4))) return rc;
+        const int16_t *z = ctx->d_zz + off * 64;
+        if (mode == JPGB200_DC_REF_RECURRENCE) {
+            k2_tile_sums<<<tiles, K2_THREADS, 0, ctx->stream>>>(z, nc, ctx->d_tile_sum);
+            k2_scan_tiles<<<1, 1024, 0, ctx->stream>>>(ctx->d_tile_sum, (long long)tiles);
+            ctx->launch_total += 2;
+        }
+        k2_apply<<<tiles, K2_THREADS, 0, ctx->stream>>>(z, nc, ctx->d_tile_sum, mode, 0, ctx->d_dc + off);
+        ctx->launch_total++;
+        CK(cudaGetLastError());
+        off += nc;
+    }
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_dc_sequence(jpgb200_ctx *ctx, int mode, int32_t *d_out)
+{
+    if (!ctx || !d_out || (mode != 0 && mode != 1)) return JPGB200_ERR_BAD_ARG;
+    if (!ctx->d_zz || ctx->n[0] == 0) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = run_dc_sequence(ctx, mode);
+    if (rc) return rc;
+    const long long nb = ctx->n[0] + ctx->n[1] + ctx->n[2];
+    CK(cudaMemcpyAsync(d_out, ctx->d_dc, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_histograms(jpgb200_ctx *ctx, int dc_mode, int sym_mode, int32_t *freq)
+{
+    if (!ctx || !freq || (dc_mode != 0 && dc_mode != 1) || (sym_mode != 0 && sym_mode != 1)) return JPGB200_ERR_BAD_ARG;
+    if (!ctx->d_zz || ctx->n[0] == 0) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc = run_dc_sequence(ctx, dc_mode);
+    if (rc) return rc;
+    CK(cudaMemsetAsync(ctx->d_freq, 0, 4 * 257 * sizeof(int), ctx->stream));
+    long long off = 0;
+    for (int c = 0; c < 3; c++) {
+        const long long nc = ctx->n[c];
+        kh_histograms<<<(unsigned)((nc + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_zz + off * 64, ctx->d_dc + off, nc,
+                                                                            c != 0, sym_mode, ctx->d_freq);
+        ctx->launch_total++;
+        CK(cudaGetLastError());
+        off += nc;
+    }
+    CK(cudaMemcpyAsync(freq, ctx->d_freq, 4 * 257 * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int t = 0; t < 4; t++) freq[t * 257 + 256] = 1; /* the reserved code point, src/huffman.c:54 */
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_block_bit_offsets(jpgb200_ctx *ctx, unsigned long long *offsets)
+{
+    if (!ctx || !offsets || !ctx->have_bits) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int bpm = ctx->ratio ? 4 : 3;
+    const long long nb = ctx->n[1] * bpm, nc = n_chunks(ctx->n);
+    std::vector<uint32_t> loc((size_t)nb);
+    std::vector<unsigned long long> base((size_t)nc);
+    EncState st;
+    CK(cudaMemcpyAsync(loc.data(), ctx->d_local_off, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(base.data(), ctx->d_cta_base, (size_t)nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&st, ctx->d_state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    const long long per = (long long)EC_MCUS * bpm;
+    for (long long s = 0; s < nb; s++) offsets[s] = base[(size_t)(s / per)] + loc[(size_t)s];
+    offsets[nb] = st.total_bits;
+    return JPGB200_OK;
+}
+
+/* ---- staged FP64 block API ------------------------------------------------------------------------ */
+
+static int stage_buf(jpgb200_ctx *ctx, size_t bytes, void **p)
+{
+    cudaError_t e = cudaMalloc(p, bytes ? bytes : 8);
+    if (e != cudaSuccess) {
+        snprintf(ctx->err, sizeof ctx->err, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return JPGB200_ERR_NOMEM;
+    }
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_stage_dct(jpgb200_ctx *ctx, double *blocks, long long n)
+{
+    if (!ctx || !blocks || n <= 0) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    void *d = NULL;
+    int rc = stage_buf(ctx, (size_t)n * 512, &d);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(d, blocks, (size_t)n * 512, cudaMemcpyHostToDevice, ctx->stream));
+    kf_dct_blocks<<<(unsigned)n, 64, 0, ctx->stream>>>((double *)d, n);
+    ctx->launch_total++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(blocks, d, (size_t)n * 512, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(d));
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_stage_quantise(jpgb200_ctx *ctx, double *blocks, long long n, const int table[64])
+{
+    if (!ctx || !blocks || !table || n <= 0) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    void *d = NULL, *t = NULL;
+    int rc = stage_buf(ctx, (size_t)n * 512, &d);
+    if (rc) return rc;
+    if ((rc = stage_buf(ctx, 256, &t))) return rc;
+    CK(cudaMemcpyAsync(d, blocks, (size_t)n * 512, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(t, table, 256, cudaMemcpyHostToDevice, ctx->stream));
+    kf_quantise_blocks<<<(unsigned)n, 64, 0, ctx->stream>>>((double *)d, n, (const int *)t);
+    ctx->launch_total++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(blocks, d, (size_t)n * 512, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(d));
+    CK(cudaFree(t));
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_stage_zigzag(jpgb200_ctx *ctx, const double *blocks, long long n, int *zz)
+{
+    if (!ctx || !blocks || !zz || n <= 0) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    void *d = NULL, *z = NULL;
+    int rc = stage_buf(ctx, (size_t)n * 512, &d);
+    if (rc) return rc;
+    if ((rc = stage_buf(ctx, (size_t)n * 256, &z))) return rc;
+    CK(cudaMemcpyAsync(d, blocks, (size_t)n * 512, cudaMemcpyHostToDevice, ctx->stream));
+    kf_zigzag_blocks<<<(unsigned)n, 64, 0, ctx->stream>>>((const double *)d, n, ctx->d_scan_order, (int *)z);
+    ctx->launch_total++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(zz, z, (size_t)n * 256, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(d));
+    CK(cudaFree(z));
+    return JPGB200_OK;
+}
+
+/* ---- device helpers -------------------------------------------------------------------------------- */
+
+extern "C" int jpgb200_malloc(jpgb200_ctx *ctx, void **dptr, size_t bytes)
+{
+    if (!ctx || !dptr) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    cudaError_t e = cudaMalloc(dptr, bytes);
+    if (e != cudaSuccess) {
+        snprintf(ctx->err, sizeof ctx->err, "cudaMalloc(%zu) failed: %s", bytes, cudaGetErrorString(e));
+        return JPGB200_ERR_NOMEM;
+    }
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_free(jpgb200_ctx *ctx, void *dptr)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaFree(dptr));
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_host_alloc(void **hptr, size_t bytes)
+{
+    if (!hptr) return JPGB200_ERR_BAD_ARG;
+    return cudaHostAlloc(hptr, bytes, cudaHostAllocDefault) == cudaSuccess ? JPGB200_OK : JPGB200_ERR_NOMEM;
+}
+
+extern "C" int jpgb200_host_free(void *hptr) { return cudaFreeHost(hptr) == cudaSuccess ? JPGB200_OK : JPGB200_ERR_CUDA; }
+
+extern "C" int jpgb200_memcpy_h2d(jpgb200_ctx *ctx, void *dptr, const void *hptr, size_t bytes)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(dptr, hptr, bytes, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_memcpy_d2h(jpgb200_ctx *ctx, void *hptr, const void *dptr, size_t bytes)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(hptr, dptr, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_synth_device(jpgb200_ctx *ctx, uint8_t *d_planes, int w, int h, uint64_t seed, uint32_t frame,
+                                    int kind)
+{
+    if (!ctx || !d_planes || w <= 0 || h <= 0 || (w % 8)) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    dim3 grid((unsigned)ctx->sm_count * 8, 1, 3);
+    ks_synth<<<grid, 256, 0, ctx->stream>>>(d_planes, w, h, (unsigned long long)seed, frame, kind);
+    ctx->launch_total++;
+    CK(cudaGetLastError());
+    return JPGB200_OK;
+}
