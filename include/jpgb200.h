@@ -45,7 +45,7 @@ extern "C" {
 #define JPGB200_SYM_REF 0           /* AC histogram index run|size (src/huffman.c:218)          */
 #define JPGB200_SYM_SPEC 1          /* (run<<4)|size                                            */
 
-#define JPGB200_NUM_KERNELS 8 /* K1 transform, K3 bits, K4 scan, zero, K5 pack, K6 count, K6 scan, K6 scatter */
+#define JPGB200_NUM_KERNELS 5 /* K1 transform, K3 block bits, K4 scan, K5 pack, K6 stuff */
 
 typedef struct jpgb200_ctx jpgb200_ctx;
 

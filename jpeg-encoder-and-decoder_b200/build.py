@@ -22,7 +22,7 @@ DRIVER = os.path.join(HERE, "jpg")
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-    "-shared", "-Xcompiler", "-fPIC", "-cudart", "static",
+    "-shared", "-Xcompiler", "-fPIC", "-cudart", "static", "--extended-lambda",
 ]
 
 

@@ -6,11 +6,12 @@
  * Launch sequence of one encode (one stream, no host synchronisation in between):
  *   K1 k1_transform   pixels -> int16 zig-zag coefficients           (HBM-bound, 9 B/px)
  *   K3 k3_block_bits  per-block code length, per-chunk offsets + totals
- *   K4 k4_scan_chunks device-wide exclusive scan of chunk totals (uint64)
- *   KZ k_zero_ubuf    clear the words the packer ORs into
- *   K5 k5_pack        every block writes its codes at its global bit offset
- *   K6 k6_count / k6_scan / k6_scatter  0xFF00 stuffing by a second length/offset scan,
- *      header and EOI written by k6_scan
+ *   K4 k4_scan_chunks device-wide exclusive scan of chunk totals (uint64); clears the few
+ *                     words K5 ORs into and K6's scan state
+ *   K5 k5_pack        every block writes its codes at its global bit offset (chunk streams
+ *                     assembled in shared memory, copied out coalesced)
+ *   K6 k6_stuff       0xFF00 stuffing by a second length/offset scan (single pass, chained),
+ *                     JFIF header, EOI and length word
  * There is no CPU arithmetic path in this library.
  */
 #include <cuda_runtime.h>
@@ -31,9 +32,8 @@
 
 using namespace jpgb200;
 
-enum { KI_K1 = 0, KI_K3, KI_K4, KI_ZERO, KI_K5, KI_K6COUNT, KI_K6SCAN, KI_K6SCATTER };
-static const char *kKernelNames[JPGB200_NUM_KERNELS] = {"k1_transform", "k3_block_bits", "k4_scan_chunks", "k_zero_ubuf",
-                                                        "k5_pack",      "k6_count",      "k6_scan",        "k6_scatter"};
+enum { KI_K1 = 0, KI_K3, KI_K4, KI_K5, KI_K6 };
+static const char *kKernelNames[JPGB200_NUM_KERNELS] = {"k1_transform", "k3_block_bits", "k4_scan_chunks", "k5_pack", "k6_stuff"};
 
 struct EvPair {
     int k;
@@ -61,7 +61,7 @@ struct jpgb200_ctx {
     size_t ubuf_cap;
     uint32_t *d_tile_ff;
     unsigned long long *d_tile_base;
-    size_t tile_cap;
+    size_t tile_cap, tile_bytes;
     EncState *d_state;
     uint8_t *d_header;
     int hdr_w, hdr_h, hdr_q, hdr_ratio, hdr_len;
@@ -88,6 +88,7 @@ struct jpgb200_ctx {
     double ms[JPGB200_NUM_KERNELS];
     long long launches[JPGB200_NUM_KERNELS];
     long long launch_total;
+    unsigned long long epoch; /* K6 chained-scan generation */
     char err[256];
 };
 
@@ -475,7 +476,13 @@ static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_
     }
     /* worst case 1658 bits per block (20-bit DC + 63 x 26-bit AC) */
     const size_t ub = (size_t)nb * 208 + 65536;
-    if ((rc = grow(ctx, &ctx->d_ubuf, &ctx->ubuf_cap, ub))) return rc;
+    {
+        const uint32_t *before = ctx->d_ubuf;
+        const size_t cap_before = ctx->ubuf_cap;
+        if ((rc = grow(ctx, &ctx->d_ubuf, &ctx->ubuf_cap, ub))) return rc;
+        if (ctx->d_ubuf != before || ctx->ubuf_cap != cap_before) /* K5's invariant: all-zero on entry */
+            CK(cudaMemsetAsync(ctx->d_ubuf, 0, ctx->ubuf_cap, ctx->stream));
+    }
     const size_t nt = ctx->ubuf_cap / K6_TILE + 2;
     if (ctx->tile_cap < nt || !ctx->d_tile_ff) {
         size_t c1 = 0, c2 = 0;
@@ -488,6 +495,8 @@ static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_
         }
         if ((rc = grow(ctx, &ctx->d_tile_ff, &c1, nt * 4))) return rc;
         if ((rc = grow(ctx, &ctx->d_tile_base, &c2, nt * 8))) return rc;
+        CK(cudaMemsetAsync(ctx->d_tile_base, 0, c2, ctx->stream));
+        ctx->tile_bytes = c2;
         ctx->tile_cap = nt;
     }
     return JPGB200_OK;
@@ -584,7 +593,7 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     {
         LaunchScope ls(ctx, KI_K4);
         k4_scan_chunks<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->d_cta_bits, ctx->d_cta_base, (long long)nc, ctx->d_state,
-                                                           K6_TILE, (unsigned long long)ctx->ubuf_cap);
+                                                           K6_TILE, (unsigned long long)ctx->ubuf_cap, 0ull);
     }
     CK(cudaGetLastError());
     ctx->have_bits = true;
@@ -598,12 +607,7 @@ static int launch_pack(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     EcParams e;
     fill_ec(ctx, e, zz, n);
     const unsigned nc = (unsigned)n_chunks(n);
-    const unsigned pgrid = (unsigned)ctx->sm_count * 8;
-    {
-        LaunchScope ls(ctx, KI_ZERO);
-        k_zero_ubuf<<<pgrid, 256, 0, ctx->stream>>>(reinterpret_cast<uint4 *>(ctx->d_ubuf), ctx->d_state);
-    }
-    CK(cudaGetLastError());
+    const unsigned pgrid = (unsigned)ctx->sm_count * 4;
     {
         LaunchScope ls(ctx, KI_K5);
         if (ratio == 0)
@@ -612,22 +616,15 @@ static int launch_pack(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
             k5_pack<1><<<nc, EcCfg<1>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
     }
     CK(cudaGetLastError());
-    {
-        LaunchScope ls(ctx, KI_K6COUNT);
-        k6_count<<<pgrid, K6_THREADS, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(ctx->d_ubuf), ctx->d_state,
-                                                        ctx->d_tile_ff);
+    if (((ctx->epoch + 1) & ((1ull << K6_EPOCH_BITS) - 1ull)) == 0ull) { /* epoch wrap: forget old states */
+        CK(cudaMemsetAsync(ctx->d_tile_base, 0, ctx->tile_bytes, ctx->stream));
+        ctx->epoch++;
     }
-    CK(cudaGetLastError());
     {
-        LaunchScope ls(ctx, KI_K6SCAN);
-        k6_scan<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->d_tile_ff, ctx->d_tile_base, ctx->d_state, ctx->d_header,
-                                                    ctx->hdr_len, d_out, (unsigned long long)cap, len_out);
-    }
-    CK(cudaGetLastError());
-    {
-        LaunchScope ls(ctx, KI_K6SCATTER);
-        k6_scatter<<<pgrid, K6_THREADS, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(ctx->d_ubuf), ctx->d_state,
-                                                          ctx->d_tile_base, d_out, ctx->hdr_len);
+        LaunchScope ls(ctx, KI_K6);
+        k6_stuff<<<pgrid, K6_THREADS, 0, ctx->stream>>>(reinterpret_cast<uint4 *>(ctx->d_ubuf), ctx->d_state,
+                                                        ctx->d_tile_base, ctx->d_header, ctx->hdr_len, d_out,
+                                                        (unsigned long long)cap, len_out, ++ctx->epoch);
     }
     CK(cudaGetLastError());
     return JPGB200_OK;
