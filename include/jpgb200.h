@@ -45,7 +45,7 @@ extern "C" {
 #define JPGB200_SYM_REF 0           /* AC histogram index run|size (src/huffman.c:218)          */
 #define JPGB200_SYM_SPEC 1          /* (run<<4)|size                                            */
 
-#define JPGB200_NUM_KERNELS 5 /* K1 transform, K3 block bits, K4 scan, K5 pack, K6 stuff */
+#define JPGB200_NUM_KERNELS 6 /* K1 transform, K35 fused entropy; staged: K3 block bits, K4 scan, K5 pack, K6 stuff */
 
 typedef struct jpgb200_ctx jpgb200_ctx;
 
@@ -60,6 +60,13 @@ const char *jpgb200_last_error(const jpgb200_ctx *ctx);
 /* Run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = context's own. */
 int jpgb200_set_stream(jpgb200_ctx *ctx, void *cuda_stream);
 int jpgb200_sync(jpgb200_ctx *ctx);
+/* Entropy stage selection: 0 (default) = the fused single-launch kernel K35; 1 = the staged
+ * K3 (bit lengths) / K4 (scan) / K5 (pack) / K6 (stuffing) pipeline, kept for the MCU-row
+ * partition and as a cross-check -- both produce identical bytes. */
+int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on);
+/* K1 selection: 0 (default) = persistent kernel fed by TMA bulk copies whenever width % 16 == 0;
+ * 1 = always the direct-load kernel (the only one for width % 16 == 8).  Identical results. */
+int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on);
 /* The 8 bytes the reference reads in front of each plane buffer for block W/8-1
  * (src/preprocess.c:159,206-210): oob[0..7]=r, [8..15]=g, [16..23]=b.
  * Default: zeros. */

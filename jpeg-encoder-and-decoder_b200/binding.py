@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libjpgb200.so")
 
 DC_REF, DC_SPEC = 0, 1
 SYM_REF, SYM_SPEC = 0, 1
-NUM_KERNELS = 5
+NUM_KERNELS = 6
 
 ERR_NO_DEVICE, ERR_BAD_DIMS, ERR_BAD_QUALITY, ERR_CUDA, ERR_OUT_TOO_SMALL, ERR_BAD_ARG, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
 
@@ -31,6 +31,8 @@ _SIGS = {
     "jpgb200_set_stream": (C.c_int, [_vp, _vp]),
     "jpgb200_sync": (C.c_int, [_vp]),
     "jpgb200_set_oob_bytes": (C.c_int, [_vp, _vp]),
+    "jpgb200_set_staged_entropy": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_set_plain_transform": (C.c_int, [_vp, C.c_int]),
     "jpgb200_encode_planar": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "jpgb200_encode_rgb": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "jpgb200_encode_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
@@ -147,6 +149,12 @@ class Encoder:
 
     def sync(self):
         self._ck(lib().jpgb200_sync(self._h))
+
+    def set_staged_entropy(self, on):
+        self._ck(lib().jpgb200_set_staged_entropy(self._h, 1 if on else 0))
+
+    def set_plain_transform(self, on):
+        self._ck(lib().jpgb200_set_plain_transform(self._h, 1 if on else 0))
 
     def set_oob_bytes(self, oob):
         oob = _c(oob)

@@ -1,5 +1,5 @@
 /*
- * Entropy stage: K3 (per-block bit lengths + per-CTA offsets), K4 (device-wide exclusive
+ * Entropy stage: K3 (per-block bit lengths + per-chunk offsets), K4 (device-wide exclusive
  * scan), K5 (parallel bit pack).  The reference has no bit writer at all (SURVEY.md F1,
  * F2): what it pins is the symbol alphabet -- categories = bit length of |v|, EOB 0x00
  * when zeros trail the last non-zero coefficient, ZRL 0xF0 per 16 zeros
@@ -7,23 +7,33 @@
  * emitted stream follows T.81 F.1.2: true DC differences and (run<<4)|size symbols.
  *
  * Scan order is the interleaved MCU order (T.81 A.2): 4:4:4 -> Y Cb Cr per MCU,
- * 4:2:2 -> Y(2m) Y(2m+1) Cb(m) Cr(m).  One thread encodes one 8x8 block; a CTA owns
- * EC_MCUS consecutive MCUs, whose coefficients are contiguous per component in HBM and are
- * staged through shared memory with coalesced 16-byte loads (rows of 128 B, XOR-swizzled so
- * that the per-thread row reads are conflict-free).
+ * 4:2:2 -> Y(2m) Y(2m+1) Cb(m) Cr(m).  One thread encodes one 8x8 block; a CTA owns a chunk
+ * of EC_MCUS consecutive MCUs, whose coefficients are contiguous per component in HBM and
+ * are staged into shared memory with asynchronous coalesced 16-byte copies (rows of 128 B
+ * padded to 144 B, so that per-thread 16-byte row reads are bank-conflict free and a
+ * coefficient's address is linear in its zig-zag index).
  */
 #ifndef JPGB200_ENTROPY_CUH
 #define JPGB200_ENTROPY_CUH
 
+#include <cuda_fp16.h>
 #include <stdint.h>
 
 namespace jpgb200 {
 
 #define EC_MCUS 64
+#define EC_ROW_CHUNKS 9 /* 8 data chunks of 16 B + 1 pad */
 
+/* pack tables */
 struct HuffDev {
     uint32_t ac[2][256]; /* (code << 8) | code_length ; [lum|chr][(run<<4)|size] */
     uint32_t dc[2][16];  /* (code << 8) | code_length ; [lum|chr][category]     */
+};
+/* count tables: total bits of one symbol incl. its additional bits; the AC table is
+ * extended to runs of up to 62 zeros, folding in the ZRL codes a long run needs */
+struct HuffBits {
+    uint8_t ac[2][1024]; /* [lum|chr][(run<<4)|size], run 0..62 */
+    uint8_t dc[2][16];
 };
 
 /* per-encode device state, written by the scan kernels and read by later kernels */
@@ -36,18 +46,20 @@ struct EncState {
     int error;                     /* 1: output capacity too small                     */
     int pad;
     unsigned long long ticket;     /* K6 tile dispenser                                 */
+    unsigned long long ticket35;   /* K35 chunk dispenser (reset by K35 itself)         */
 };
 
 struct EcParams {
-    const int16_t *zz_y, *zz_cb, *zz_cr;
+    const int16_t *zz; /* [Y blocks | Cb blocks | Cr blocks][64] */
+    long long coff1, coff2; /* first Cb / Cr block inside zz */
     long long n_mcu;
     int dc_pred[3];        /* predictor of the first block per component (0 for a whole image) */
     int is_last_band;      /* pad the final byte after the last block                         */
-    uint32_t *local_off;   /* [n_mcu*BPM] bit offset of each block inside its CTA chunk        */
-    uint32_t *cta_bits;    /* [n_cta] bits per CTA chunk                                       */
-    const unsigned long long *cta_base; /* [n_cta] exclusive scan of cta_bits (K5)            */
+    uint32_t *local_off;   /* [n_mcu*BPM] bit offset of each block inside its chunk            */
+    uint32_t *cta_bits;    /* [n_chunks] bits per chunk                                        */
+    const unsigned long long *cta_base; /* [n_chunks] exclusive scan of cta_bits (K5)         */
     unsigned long long bit_base;        /* global bit offset of this band (multi-GPU)         */
-    uint32_t *ubuf;        /* un-stuffed big-endian bit stream, zero-initialised (K5)          */
+    uint32_t *ubuf;        /* un-stuffed big-endian bit stream, all-zero on entry (K5)         */
     const EncState *st;    /* error flag set by K4 when the stream would not fit ubuf          */
 };
 
@@ -55,39 +67,40 @@ template <int RATIO>
 struct EcCfg {
     static const int BPM = (RATIO == 0) ? 3 : 4;
     static const int NT = EC_MCUS * BPM;
+    static const int STAGE_WORDS = (RATIO == 0) ? 3072 : 2048; /* K5 staging buffer */
 };
 
-/* Thread <-> block mapping inside a CTA.  Threads (= shared-memory rows) are grouped by
- * COMPONENT, not by MCU: luma blocks carry ~3x the non-zero coefficients of chroma blocks,
- * and the per-block loops run as long as the busiest lane of a warp, so component-pure warps
- * execute far fewer divergent iterations.  s_local is the block's position in scan (MCU
- * interleaved) order inside the CTA's chunk. */
+/* Row (= thread) <-> block mapping inside a chunk.  Rows are grouped by COMPONENT, not by
+ * MCU: luma blocks carry ~3x the non-zero coefficients of chroma blocks, and the per-block
+ * loops run as long as the busiest lane of a warp, so component-pure warps execute far fewer
+ * divergent iterations.  s_local is the block's position in scan (MCU interleaved) order
+ * inside the chunk; gabs its block index inside zz. */
 template <int RATIO>
 struct EcMap {
     int comp, s_local;
-    long long gblk; /* block index inside its component's coefficient array */
+    long long gabs;
     bool valid, first_of_comp;
-    __device__ __forceinline__ EcMap(const EcParams &p, long long m0, int tid)
+    __device__ __forceinline__ EcMap(const EcParams &p, long long m0, int row)
     {
         if (RATIO == 0) {
-            comp = tid >> 6;
-            const int m = tid & 63;
+            comp = row >> 6;
+            const int m = row & 63;
             s_local = m * 3 + comp;
-            gblk = m0 + m;
+            gabs = m0 + m + (comp == 0 ? 0ll : (comp == 1 ? p.coff1 : p.coff2));
             valid = (m0 + m) < p.n_mcu;
             first_of_comp = (m == 0);
         } else {
-            if (tid < 128) {
+            if (row < 128) {
                 comp = 0;
-                s_local = (tid >> 1) * 4 + (tid & 1);
-                gblk = 2 * m0 + tid;
-                valid = (m0 + (tid >> 1)) < p.n_mcu;
-                first_of_comp = (tid == 0);
+                s_local = (row >> 1) * 4 + (row & 1);
+                gabs = 2 * m0 + row;
+                valid = (m0 + (row >> 1)) < p.n_mcu;
+                first_of_comp = (row == 0);
             } else {
-                comp = 1 + ((tid - 128) >> 6);
-                const int m = tid & 63;
+                comp = 1 + ((row - 128) >> 6);
+                const int m = row & 63;
                 s_local = m * 4 + 1 + comp;
-                gblk = m0 + m;
+                gabs = m0 + m + (comp == 1 ? p.coff1 : p.coff2);
                 valid = (m0 + m) < p.n_mcu;
                 first_of_comp = (m == 0);
             }
@@ -108,63 +121,111 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
-/* coalesced asynchronous fill of the CTA's coefficient rows (row == thread index,
- * component-major); 16-byte chunk q of a row lives at chunk (q ^ (row & 7)) */
+/* asynchronous fill of the chunk's coefficient rows: 8 chunks of 16 B per thread, a warp's
+ * 32 copies cover 512 contiguous bytes of one component */
 template <int RATIO>
-__device__ __forceinline__ void ec_fill(uint4 (*sC)[8], const EcParams &p, long long m0, int tid)
+__device__ __forceinline__ void ec_fill(uint4 (*sC)[EC_ROW_CHUNKS], const EcParams &p, long long m0, int tid)
 {
     constexpr int NT = EcCfg<RATIO>::NT;
-    long long left = p.n_mcu - m0;
-    const int nv = left < EC_MCUS ? (int)left : EC_MCUS; /* valid MCUs in this CTA */
-    if (RATIO == 0) {
+    const uint4 *z = reinterpret_cast<const uint4 *>(p.zz);
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-            const int16_t *z = (c == 0) ? p.zz_y : (c == 1 ? p.zz_cb : p.zz_cr);
-            const uint4 *src = reinterpret_cast<const uint4 *>(z) + m0 * 8;
-            for (int i = tid; i < nv * 8; i += NT) {
-                const int row = c * 64 + (i >> 3), q = i & 7;
-                cp_async16(&sC[row][q ^ (row & 7)], src + i);
-            }
-        }
-    } else {
-        {
-            const uint4 *src = reinterpret_cast<const uint4 *>(p.zz_y) + m0 * 16;
-            for (int i = tid; i < nv * 16; i += NT) {
-                const int row = i >> 3, q = i & 7;
-                cp_async16(&sC[row][q ^ (row & 7)], src + i);
-            }
-        }
-#pragma unroll
-        for (int c = 1; c < 3; c++) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(c == 1 ? p.zz_cb : p.zz_cr) + m0 * 8;
-            for (int i = tid; i < nv * 8; i += NT) {
-                const int row = 64 + c * 64 + (i >> 3), q = i & 7;
-                cp_async16(&sC[row][q ^ (row & 7)], src + i);
-            }
-        }
+    for (int k = 0; k < 8; k++) {
+        const int i = k * NT + tid, row = i >> 3, q = i & 7;
+        const EcMap<RATIO> mp(p, m0, row);
+        if (mp.valid) cp_async16(&sC[row][q], z + mp.gabs * 8 + q);
     }
+}
+
+/* tables -> shared memory, 16 bytes per thread */
+template <class T>
+__device__ __forceinline__ void ec_load_table(T *sT, const T *g, int tid)
+{
+    static_assert(sizeof(T) % 16 == 0, "table size");
+    if (tid < (int)(sizeof(T) / 16))
+        cp_async16(reinterpret_cast<uint4 *>(sT) + tid, reinterpret_cast<const uint4 *>(g) + tid);
 }
 
 /* DC predictor: the previous block of the same component (raster == scan order per
  * component) -- the row above in shared memory, the caller's predictor for the first block
  * of the image/band, or the last block of the previous chunk read from HBM */
 template <int RATIO>
-__device__ __forceinline__ int ec_dc_pred(const uint4 (*sC)[8], const EcParams &p, long long m0, int tid,
+__device__ __forceinline__ int ec_dc_pred(const uint4 (*sC)[EC_ROW_CHUNKS], const EcParams &p, long long m0, int tid,
                                           const EcMap<RATIO> &mp)
 {
-    if (!mp.first_of_comp) return (int)(short)(sC[tid - 1][(tid - 1) & 7].x & 0xffffu);
+    if (!mp.first_of_comp) return (int)(short)(sC[tid - 1][0].x & 0xffffu);
     if (m0 == 0) return p.dc_pred[mp.comp];
-    const int16_t *z = (mp.comp == 0) ? p.zz_y : (mp.comp == 1 ? p.zz_cb : p.zz_cr);
-    return (int)z[(mp.gblk - 1) * 64];
+    return (int)p.zz[(mp.gabs - 1) * 64];
 }
 
-struct CountSink {
-    uint32_t bits;
-    __device__ __forceinline__ void put(uint32_t, int n) { bits += (uint32_t)n; }
-};
+/* 0xFFFF per non-zero int16 half.  The pair is compared as two fp16 numbers with an
+ * unordered != 0: every non-zero bit pattern except 0x8000 (-32768, which a quantised
+ * coefficient never reaches) is a non-zero number, a denormal or a NaN, and "unordered"
+ * makes NaN patterns (small negative integers) compare true.  One HSET2 per two coefficients. */
+__device__ __forceinline__ uint32_t nz_halves(uint32_t w)
+{
+    __half2 h;
+    *reinterpret_cast<uint32_t *>(&h) = w;
+    __half2 zero;
+    *reinterpret_cast<uint32_t *>(&zero) = 0u;
+    return __hneu2_mask(h, zero);
+}
 
-/* Bit writer: big-endian 32-bit words.  SHARED selects shared-memory atomics for the two
- * words a block can share with its neighbours; interior words are owned exclusively. */
+/* bit i = (coefficient i of these 16 != 0) */
+__device__ __forceinline__ uint32_t nz_mask16(const uint4 a, const uint4 b)
+{
+    const uint32_t w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+    uint32_t x = 0;
+#pragma unroll
+    for (int i = 0; i < 8; i++) x |= nz_halves(w[i]) & ((1u << (2 * i)) | (1u << (17 + 2 * i)));
+    return (x | (x >> 16)) & 0xffffu;
+}
+
+/* masks of the non-zero AC coefficients of a row: m[0] = positions 1..31, m[1] = 32..63 */
+__device__ __forceinline__ void ec_nz_masks(const uint4 *row, uint32_t &m0, uint32_t &m1)
+{
+    m0 = (nz_mask16(row[0], row[1]) | (nz_mask16(row[2], row[3]) << 16)) & ~1u; /* bit 0 is the DC */
+    m1 = nz_mask16(row[4], row[5]) | (nz_mask16(row[6], row[7]) << 16);
+}
+
+__device__ __forceinline__ int ec_coef(const uint4 *row, int k) { return (int)reinterpret_cast<const short *>(row)[k]; }
+
+/* index of the most significant set bit (v != 0): category - 1 */
+__device__ __forceinline__ int msb_index(uint32_t v)
+{
+    int r;
+    asm("bfind.u32 %0, %1;" : "=r"(r) : "r"(v));
+    return r;
+}
+
+/* ---- block coder, counting form (K3) ------------------------------------------------------
+ * The symbol loop visits only the set bits of the non-zero mask: its trip count is the
+ * block's number of non-zero AC coefficients (in a warp: the maximum over 32 blocks of one
+ * component), not 63.  One table lookup per symbol returns code length + additional bits +
+ * any ZRL codes of a long run. */
+__device__ __forceinline__ uint32_t ec_count_block(const uint4 *row, int diff, const uint8_t *bAc, const uint8_t *bDc)
+{
+    uint32_t bits = bDc[diff == 0 ? 0 : msb_index((uint32_t)abs(diff)) + 1];
+    uint32_t mm[2];
+    ec_nz_masks(row, mm[0], mm[1]);
+    int prev = 0;
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        uint32_t m = mm[half];
+        while (m) {
+            const int k = half * 32 + (__ffs((int)m) - 1);
+            m &= m - 1u;
+            const int v = ec_coef(row, k);
+            const int idx = ((k - prev - 1) << 4) + msb_index((uint32_t)abs(v)) + 1;
+            prev = k;
+            bits += bAc[idx];
+        }
+    }
+    if (prev != 63) bits += bAc[0]; /* EOB */
+    return bits;
+}
+
+/* ---- bit writer: big-endian 32-bit words; the first and last word a block touches can be
+ * shared with its neighbours and are OR-ed, interior words are owned exclusively */
 template <bool SHARED>
 struct PackSink {
     unsigned long long acc;
@@ -173,16 +234,18 @@ struct PackSink {
     bool first;
     __device__ __forceinline__ void or_word(uint32_t be)
     {
-        if (SHARED)
+        if (SHARED) {
+            const unsigned sa = (unsigned)__cvta_generic_to_shared(wp);
+            asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(sa), "r"(be) : "memory");
+        } else {
             atomicOr(wp, be);
-        else
-            atomicOr(wp, be);
+        }
     }
     __device__ __forceinline__ void emit(uint32_t word)
     {
         const uint32_t be = __byte_perm(word, 0, 0x0123);
         if (first) {
-            or_word(be); /* word shared with the preceding block */
+            or_word(be);
             first = false;
         } else {
             *wp = be;
@@ -200,79 +263,50 @@ struct PackSink {
     }
     __device__ __forceinline__ void finish()
     {
-        if (nacc > 0) {
-            const uint32_t word = (uint32_t)(acc << (32 - nacc));
-            or_word(__byte_perm(word, 0, 0x0123)); /* word shared with the following block */
-        }
+        if (nacc > 0) or_word(__byte_perm((uint32_t)(acc << (32 - nacc)), 0, 0x0123));
     }
 };
 
-/* int16 coefficient k of a swizzled 128-byte row */
-__device__ __forceinline__ int ec_coef(const uint4 *row, int key, int k)
-{
-    const char *base = reinterpret_cast<const char *>(row);
-    return (int)*reinterpret_cast<const short *>(base + ((((k >> 3) ^ key) << 4) | ((k & 7) << 1)));
-}
-
-/* One block: DC difference + AC run/size symbols (T.81 F.1.2.1-F.1.2.2).
- * row = this block's 128-byte shared-memory row (8 swizzled 16-byte chunks, key = row & 7);
- * sAc/sDc = (code<<8)|len tables of this component.
- * The 63 AC positions are first reduced to a bit mask of non-zero coefficients (2 predicated
- * instructions per coefficient, no branches); the symbol loop then visits only set bits, so
- * its trip count is the block's number of non-zero coefficients rather than 63 -- in a warp,
- * the maximum over 32 blocks of the same component. */
+/* ---- block coder, packing form (K5) ------------------------------------------------------- */
 template <class Sink>
-__device__ __forceinline__ void ec_encode_block(const uint4 *row, int key, int diff, const uint32_t *sAc,
-                                                const uint32_t *sDc, Sink &s)
+__device__ __forceinline__ void ec_pack_block(const uint4 *row, int diff, const uint32_t *sAc, const uint32_t *sDc,
+                                              Sink &s)
 {
     {
-        const int cat = 32 - __clz(abs(diff));
+        const int cat = diff == 0 ? 0 : msb_index((uint32_t)abs(diff)) + 1;
         const uint32_t e = sDc[cat];
         const uint32_t extra = (uint32_t)(diff - (diff < 0 ? 1 : 0)) & ((1u << cat) - 1u);
         s.put(((e >> 8) << cat) | extra, (int)(e & 0xffu) + cat);
     }
-    uint32_t m[2] = {0u, 0u};
-#pragma unroll
-    for (int j = 0; j < 8; j++) {
-        const uint4 q = row[j ^ key];
-        const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (int i = 0; i < 4; i++) {
-            const int k = 8 * j + 2 * i;
-            if (ws[i] & 0x0000ffffu) m[k >> 5] |= 1u << (k & 31);
-            if (ws[i] & 0xffff0000u) m[(k + 1) >> 5] |= 1u << ((k + 1) & 31);
-        }
-    }
-    m[0] &= ~1u; /* position 0 is the DC */
-    const uint32_t zrl = sAc[0xF0], eob = sAc[0x00];
+    uint32_t mm[2];
+    ec_nz_masks(row, mm[0], mm[1]);
     int prev = 0;
 #pragma unroll
     for (int half = 0; half < 2; half++) {
-        uint32_t mm = m[half];
-        while (mm) {
-            const int k = half * 32 + (__ffs((int)mm) - 1);
-            mm &= mm - 1u;
+        uint32_t m = mm[half];
+        while (m) {
+            const int k = half * 32 + (__ffs((int)m) - 1);
+            m &= m - 1u;
+            const int v = ec_coef(row, k);
             int run = k - prev - 1;
             prev = k;
-            const int v = ec_coef(row, key, k);
-            while (run > 15) {
-                s.put(zrl >> 8, (int)(zrl & 0xffu));
-                run -= 16;
+            if (run > 15) { /* rare: one ZRL code per 16 zeros */
+                const uint32_t zrl = sAc[0xF0];
+                do {
+                    s.put(zrl >> 8, (int)(zrl & 0xffu));
+                    run -= 16;
+                } while (run > 15);
             }
-            const int cat = 32 - __clz(abs(v));
+            const int cat = msb_index((uint32_t)abs(v)) + 1;
             const uint32_t e = sAc[(run << 4) | cat];
             const uint32_t extra = (uint32_t)(v - (v < 0 ? 1 : 0)) & ((1u << cat) - 1u);
             s.put(((e >> 8) << cat) | extra, (int)(e & 0xffu) + cat);
         }
     }
-    if (prev != 63) s.put(eob >> 8, (int)(eob & 0xffu));
-}
-
-/* Huffman tables -> shared memory (same layout as HuffDev: 2176 bytes = 136 x 16) */
-__device__ __forceinline__ void ec_load_tables(HuffDev *sH, const HuffDev *h, int tid)
-{
-    if (tid < (int)(sizeof(HuffDev) / 16))
-        cp_async16(reinterpret_cast<uint4 *>(sH) + tid, reinterpret_cast<const uint4 *>(h) + tid);
+    if (prev != 63) {
+        const uint32_t eob = sAc[0x00];
+        s.put(eob >> 8, (int)(eob & 0xffu));
+    }
 }
 
 /* exclusive scan of one uint32 per thread over the CTA; returns this thread's offset and
@@ -301,31 +335,29 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t *sWa
     return base + inc - v;
 }
 
-/* ---- K3: bit length of every block, exclusive offsets inside the CTA chunk, chunk total -- */
+/* ---- K3: bit length of every block, exclusive offsets inside the chunk, chunk total ------- */
 template <int RATIO>
-__global__ void __launch_bounds__(EcCfg<RATIO>::NT) k3_block_bits(const EcParams p, const HuffDev *huff)
+__global__ void __launch_bounds__(EcCfg<RATIO>::NT) k3_block_bits(const EcParams p, const HuffBits *hbits)
 {
     constexpr int BPM = EcCfg<RATIO>::BPM, NT = EcCfg<RATIO>::NT;
-    __shared__ uint4 sC[NT][8];
-    __shared__ __align__(16) HuffDev sH;
+    __shared__ uint4 sC[NT][EC_ROW_CHUNKS];
+    __shared__ __align__(16) HuffBits sB;
     __shared__ uint32_t sBits[NT];
     __shared__ uint32_t sWarp[NT / 32];
     const int tid = threadIdx.x;
     const long long m0 = (long long)blockIdx.x * EC_MCUS;
 
     ec_fill<RATIO>(sC, p, m0, tid);
-    ec_load_tables(&sH, huff, tid);
+    ec_load_table(&sB, hbits, tid);
+    const EcMap<RATIO> mp(p, m0, tid);
     cp_async_wait_all();
     __syncthreads();
 
-    const EcMap<RATIO> mp(p, m0, tid);
     uint32_t nbits = 0;
     if (mp.valid) {
         const int pred = ec_dc_pred<RATIO>(sC, p, m0, tid, mp);
-        const int diff = (int)(short)(sC[tid][tid & 7].x & 0xffffu) - pred;
-        CountSink s{0};
-        ec_encode_block(sC[tid], tid & 7, diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
-        nbits = s.bits;
+        const int diff = (int)(short)(sC[tid][0].x & 0xffffu) - pred;
+        nbits = ec_count_block(sC[tid], diff, sB.ac[mp.comp ? 1 : 0], sB.dc[mp.comp ? 1 : 0]);
     }
     sBits[mp.s_local] = nbits; /* scan (MCU-interleaved) order */
     __syncthreads();
@@ -342,21 +374,19 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k3_block_bits(const EcParams
  * word as its destination) and copied out with coalesced stores; only the chunk's first and
  * last word, which neighbouring chunks also write, are OR-ed into HBM.  A chunk too long for
  * the staging buffer packs straight into HBM with atomics on block-boundary words. */
-#define K5_STAGE_WORDS 3072 /* 12 KB = 98304 bits: ~4x the typical chunk at q75 */
-
 template <int RATIO>
 __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k5_pack(const EcParams p, const HuffDev *huff)
 {
-    constexpr int BPM = EcCfg<RATIO>::BPM, NT = EcCfg<RATIO>::NT;
-    __shared__ uint4 sC[NT][8];
+    constexpr int BPM = EcCfg<RATIO>::BPM, NT = EcCfg<RATIO>::NT, STAGE = EcCfg<RATIO>::STAGE_WORDS;
+    __shared__ uint4 sC[NT][EC_ROW_CHUNKS];
     __shared__ __align__(16) HuffDev sH;
-    __shared__ uint32_t sS[K5_STAGE_WORDS];
+    __shared__ uint32_t sS[STAGE];
     const int tid = threadIdx.x;
     const long long m0 = (long long)blockIdx.x * EC_MCUS;
 
     /* all global reads of the prologue are issued back to back, none depends on another */
     ec_fill<RATIO>(sC, p, m0, tid);
-    ec_load_tables(&sH, huff, tid);
+    ec_load_table(&sH, huff, tid);
     const EcMap<RATIO> mp(p, m0, tid);
     const int err = p.st->error;
     const unsigned long long g0 = p.bit_base + p.cta_base[blockIdx.x];
@@ -369,7 +399,7 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k5_pack(const EcParams p, co
     const uint32_t b0 = (uint32_t)(g0 & 31ull);
     const uint32_t nwords = (b0 + tbits + 31u) >> 5;
     uint32_t *gw = p.ubuf + (g0 >> 5);
-    const bool staged = nwords <= K5_STAGE_WORDS;
+    const bool staged = nwords <= (uint32_t)STAGE;
     if (staged)
         for (uint32_t i = tid; i < nwords; i += NT) sS[i] = 0u;
     cp_async_wait_all();
@@ -377,7 +407,7 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k5_pack(const EcParams p, co
 
     if (mp.valid) {
         const int pred = ec_dc_pred<RATIO>(sC, p, m0, tid, mp);
-        const int diff = (int)(short)(sC[tid][tid & 7].x & 0xffffu) - pred;
+        const int diff = (int)(short)(sC[tid][0].x & 0xffffu) - pred;
         const uint32_t loff = b0 + my_off;
         const bool very_last = p.is_last_band && (m0 * BPM + mp.s_local == p.n_mcu * BPM - 1);
         if (staged) {
@@ -386,7 +416,7 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k5_pack(const EcParams p, co
             s.nacc = (int)(loff & 31u);
             s.wp = sS + (loff >> 5);
             s.first = true;
-            ec_encode_block(sC[tid], tid & 7, diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
+            ec_pack_block(sC[tid], diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
             if (very_last) {
                 const int rem = s.nacc & 7; /* complete the final byte with 1-bits (T.81 F.1.2.3) */
                 if (rem) s.put((1u << (8 - rem)) - 1u, 8 - rem);
@@ -398,7 +428,7 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k5_pack(const EcParams p, co
             s.nacc = (int)(loff & 31u);
             s.wp = gw + (loff >> 5);
             s.first = true;
-            ec_encode_block(sC[tid], tid & 7, diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
+            ec_pack_block(sC[tid], diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
             if (very_last) {
                 const int rem = s.nacc & 7;
                 if (rem) s.put((1u << (8 - rem)) - 1u, 8 - rem);
@@ -419,13 +449,11 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k5_pack(const EcParams p, co
 }
 
 /* ---- K4: single-CTA exclusive scan of per-chunk totals (uint32 -> uint64) ----------------
- * 8 items per thread: 8192 chunks (one 8K 4:4:4 frame) per pass.  `each(i, base, v)` sees
- * every element with its exclusive prefix while both are still in registers. */
+ * 8 items per thread: 8192 chunks (one 8K 4:4:4 frame) per pass. */
 #define SCAN_THREADS 1024
 #define SCAN_ITEMS 8
-template <class F>
 __device__ __forceinline__ unsigned long long scan_u32_to_u64(const uint32_t *in, unsigned long long *out,
-                                                              long long n, uint32_t *sWarp, F each)
+                                                              long long n, uint32_t *sWarp)
 {
     const int tid = threadIdx.x;
     unsigned long long carry = 0;
@@ -441,10 +469,7 @@ __device__ __forceinline__ unsigned long long scan_u32_to_u64(const uint32_t *in
         uint32_t ex = cta_exclusive_scan<SCAN_THREADS>(sum, sWarp, tid, total);
 #pragma unroll
         for (int k = 0; k < SCAN_ITEMS; k++) {
-            if (i0 + k < n) {
-                if (out) out[i0 + k] = carry + ex;
-                each(i0 + k, carry + ex, v[k]);
-            }
+            if (i0 + k < n) out[i0 + k] = carry + ex;
             ex += v[k];
         }
         carry += total;
@@ -460,8 +485,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) k4_scan_chunks(const uint32_t *c
                                                                unsigned long long bit_base)
 {
     __shared__ uint32_t sWarp[SCAN_THREADS / 32];
-    const unsigned long long total =
-        scan_u32_to_u64(cta_bits, cta_base, n, sWarp, [](long long, unsigned long long, uint32_t) {});
+    const unsigned long long total = scan_u32_to_u64(cta_bits, cta_base, n, sWarp);
     if (threadIdx.x == 0) {
         /* the workspace is sized for the worst case, so this only trips on corrupted lengths;
          * it keeps every later kernel inside its buffers */

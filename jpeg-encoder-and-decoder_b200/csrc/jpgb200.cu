@@ -24,6 +24,7 @@
 
 #include "../../include/jpgb200.h"
 #include "entropy.cuh"
+#include "entropy_fused.cuh"
 #include "jpgb200_math.cuh"
 #include "jpgb200_tables.h"
 #include "k1_transform.cuh"
@@ -32,8 +33,9 @@
 
 using namespace jpgb200;
 
-enum { KI_K1 = 0, KI_K3, KI_K4, KI_K5, KI_K6 };
-static const char *kKernelNames[JPGB200_NUM_KERNELS] = {"k1_transform", "k3_block_bits", "k4_scan_chunks", "k5_pack", "k6_stuff"};
+enum { KI_K1 = 0, KI_K35, KI_K3, KI_K4, KI_K5, KI_K6 };
+static const char *kKernelNames[JPGB200_NUM_KERNELS] = {"k1_transform", "k35_entropy", "k3_block_bits",
+                                                        "k4_scan_chunks", "k5_pack", "k6_stuff"};
 
 struct EvPair {
     int k;
@@ -45,6 +47,7 @@ struct jpgb200_ctx {
     int sm_count;
     cudaStream_t own_stream, stream, copy_in, copy_out;
     HuffDev *d_huff;
+    HuffBits *d_hbits;
     int *d_scan_order;
     uint8_t oob[24];
     /* workspaces, grown on demand */
@@ -60,6 +63,10 @@ struct jpgb200_ctx {
     uint32_t *d_ubuf;
     size_t ubuf_cap;
     uint32_t *d_tile_ff;
+    unsigned long long *d_bit_state, *d_ff_state;
+    size_t chain_cap;
+    bool fused_attr_set, k1_attr_set;
+    bool k1_plain; /* force the non-TMA K1 (tests) */
     unsigned long long *d_tile_base;
     size_t tile_cap, tile_bytes;
     EncState *d_state;
@@ -78,6 +85,7 @@ struct jpgb200_ctx {
     int w, h, q, ratio;
     long long n[3];
     bool have_bits;
+    bool legacy_entropy; /* staged K3/K4/K5/K6 pipeline instead of the fused K35 (tests) */
     /* quantiser cache */
     int q_cached;
     float mul[2][64];
@@ -170,6 +178,23 @@ static void build_huff(HuffDev *h)
     }
 }
 
+/* total bits per symbol (code + additional bits), AC extended to runs of 0..62 zeros */
+static void build_huff_bits(const HuffDev *h, HuffBits *b)
+{
+    memset(b, 0, sizeof *b);
+    for (int t = 0; t < 2; t++) {
+        for (int c = 0; c < 16; c++)
+            if (h->dc[t][c] & 0xff) b->dc[t][c] = (uint8_t)((h->dc[t][c] & 0xff) + c);
+        const int zrl = (int)(h->ac[t][0xF0] & 0xff);
+        b->ac[t][0] = (uint8_t)(h->ac[t][0x00] & 0xff); /* EOB */
+        for (int run = 0; run < 63; run++)
+            for (int c = 1; c <= 10; c++) {
+                const int len = (int)(h->ac[t][((run & 15) << 4) | c] & 0xff);
+                if (len) b->ac[t][(run << 4) | c] = (uint8_t)((run >> 4) * zrl + len + c);
+            }
+    }
+}
+
 static size_t put16(uint8_t *o, size_t p, unsigned v)
 {
     o[p] = (uint8_t)(v >> 8);
@@ -257,6 +282,7 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
     memset(ctx->oob, 0, sizeof ctx->oob);
     ctx->device = device;
     ctx->q_cached = -1;
+    ctx->legacy_entropy = true; /* measured faster than the fused K35 so far */
     ctx->hdr_w = -1;
     ctx->err[0] = 0;
     cudaDeviceProp prop;
@@ -266,7 +292,9 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
     }
     ctx->sm_count = prop.multiProcessorCount;
     HuffDev hh;
+    HuffBits hb;
     build_huff(&hh);
+    build_huff_bits(&hh, &hb);
     int rc = [&]() -> int {
         CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
@@ -274,6 +302,8 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         ctx->stream = ctx->own_stream;
         CK(cudaMalloc(&ctx->d_huff, sizeof(HuffDev)));
         CK(cudaMemcpy(ctx->d_huff, &hh, sizeof hh, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&ctx->d_hbits, sizeof(HuffBits)));
+        CK(cudaMemcpy(ctx->d_hbits, &hb, sizeof hb, cudaMemcpyHostToDevice));
         CK(cudaMalloc(&ctx->d_scan_order, 64 * sizeof(int)));
         CK(cudaMemcpy(ctx->d_scan_order, kZigZag, 64 * sizeof(int), cudaMemcpyHostToDevice));
         CK(cudaMalloc(&ctx->d_state, sizeof(EncState)));
@@ -298,9 +328,9 @@ extern "C" void jpgb200_destroy(jpgb200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {ctx->d_huff,     ctx->d_scan_order, ctx->d_planes[0], ctx->d_planes[1], ctx->d_zz,   ctx->d_local_off,
+    void *ptrs[] = {ctx->d_huff,     ctx->d_hbits, ctx->d_scan_order, ctx->d_planes[0], ctx->d_planes[1], ctx->d_zz,   ctx->d_local_off,
                     ctx->d_cta_bits, ctx->d_cta_base,   ctx->d_ubuf,      ctx->d_tile_ff,   ctx->d_tile_base,
-                    ctx->d_state,    ctx->d_header,     ctx->d_out[0],    ctx->d_out[1],    ctx->d_len,  ctx->d_dc,
+                    ctx->d_state,    ctx->d_bit_state, ctx->d_ff_state, ctx->d_header,     ctx->d_out[0],    ctx->d_out[1],    ctx->d_len,  ctx->d_dc,
                     ctx->d_tile_sum, ctx->d_freq};
     for (void *p : ptrs)
         if (p) cudaFree(p);
@@ -330,6 +360,20 @@ extern "C" int jpgb200_sync(jpgb200_ctx *ctx)
     if (!ctx) return JPGB200_ERR_BAD_ARG;
     CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    ctx->k1_plain = on != 0;
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    ctx->legacy_entropy = on != 0;
     return JPGB200_OK;
 }
 
@@ -474,6 +518,21 @@ static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_
         if ((rc = grow(ctx, &ctx->d_cta_base, &c2, nc * 8))) return rc;
         ctx->cta_cap = nc * 8;
     }
+    if (ctx->chain_cap < nc || !ctx->d_bit_state) {
+        size_t c1 = 0, c2 = 0;
+        if (ctx->d_bit_state) {
+            CK(cudaStreamSynchronize(ctx->stream));
+            CK(cudaFree(ctx->d_bit_state));
+            CK(cudaFree(ctx->d_ff_state));
+            ctx->d_bit_state = NULL;
+            ctx->d_ff_state = NULL;
+        }
+        if ((rc = grow(ctx, &ctx->d_bit_state, &c1, nc * 8))) return rc;
+        if ((rc = grow(ctx, &ctx->d_ff_state, &c2, nc * 8))) return rc;
+        CK(cudaMemsetAsync(ctx->d_bit_state, 0, c1, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_ff_state, 0, c2, ctx->stream));
+        ctx->chain_cap = c1 / 8;
+    }
     /* worst case 1658 bits per block (20-bit DC + 63 x 26-bit AC) */
     const size_t ub = (size_t)nb * 208 + 65536;
     {
@@ -548,8 +607,27 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
     p.has_halo = has_halo;
     memcpy(p.mul, ctx->mul, sizeof p.mul);
     memcpy(p.oob, ctx->oob, 24);
-    dim3 grid((unsigned)((p.BW + K1_TILE_BLOCKS - 1) / K1_TILE_BLOCKS), (unsigned)(h / 8), (unsigned)nframes);
-    {
+    p.tiles_per_row = (p.BW + K1_TILE_BLOCKS - 1) / K1_TILE_BLOCKS;
+    p.n_frames = nframes;
+    const bool aligned16 = (w % 16 == 0) && (((uintptr_t)d_r | (uintptr_t)d_g | (uintptr_t)d_b) % 16 == 0) &&
+                           (plane_stride % 16 == 0);
+    if (aligned16 && !ctx->k1_plain) {
+        /* persistent CTAs fed by TMA bulk copies */
+        if (!ctx->k1_attr_set) {
+            CK(cudaFuncSetAttribute(k1_transform_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemTma)));
+            CK(cudaFuncSetAttribute(k1_transform_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemTma)));
+            ctx->k1_attr_set = true;
+        }
+        const long long n_tiles = (long long)p.tiles_per_row * (h / 8) * nframes;
+        const long long resident = (long long)ctx->sm_count * 4;
+        const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+        LaunchScope ls(ctx, KI_K1);
+        if (ratio == 0)
+            k1_transform_tma<0><<<grid, K1_THREADS, sizeof(K1SmemTma), ctx->stream>>>(p, n_tiles);
+        else
+            k1_transform_tma<1><<<grid, K1_THREADS, sizeof(K1SmemTma), ctx->stream>>>(p, n_tiles);
+    } else {
+        dim3 grid((unsigned)p.tiles_per_row, (unsigned)(h / 8), (unsigned)nframes);
         LaunchScope ls(ctx, KI_K1);
         if (ratio == 0)
             k1_transform<0><<<grid, K1_THREADS, 0, ctx->stream>>>(p);
@@ -562,9 +640,9 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
 
 static void fill_ec(jpgb200_ctx *ctx, EcParams &e, const int16_t *zz, const long long n[3])
 {
-    e.zz_y = zz;
-    e.zz_cb = zz + n[0] * 64;
-    e.zz_cr = zz + (n[0] + n[1]) * 64;
+    e.zz = zz;
+    e.coff1 = n[0];
+    e.coff2 = n[0] + n[1];
     e.n_mcu = n[1];
     e.dc_pred[0] = e.dc_pred[1] = e.dc_pred[2] = 0;
     e.is_last_band = 1;
@@ -585,9 +663,9 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     {
         LaunchScope ls(ctx, KI_K3);
         if (ratio == 0)
-            k3_block_bits<0><<<nc, EcCfg<0>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
+            k3_block_bits<0><<<nc, EcCfg<0>::NT, 0, ctx->stream>>>(e, ctx->d_hbits);
         else
-            k3_block_bits<1><<<nc, EcCfg<1>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
+            k3_block_bits<1><<<nc, EcCfg<1>::NT, 0, ctx->stream>>>(e, ctx->d_hbits);
     }
     CK(cudaGetLastError());
     {
@@ -630,6 +708,48 @@ static int launch_pack(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     return JPGB200_OK;
 }
 
+/* K35: the whole entropy stage in one launch (entropy_fused.cuh) */
+static int launch_fused(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3], uint8_t *d_out, size_t cap,
+                        unsigned long long *len_out)
+{
+    if (!ctx->fused_attr_set) {
+        CK(cudaFuncSetAttribute(k35_entropy<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, EfSmem<0>::BYTES));
+        CK(cudaFuncSetAttribute(k35_entropy<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, EfSmem<1>::BYTES));
+        ctx->fused_attr_set = true;
+    }
+    if (((ctx->epoch + 1) & CS_EPOCH_MASK) == 0ull) { /* epoch wrap: forget old states */
+        CK(cudaMemsetAsync(ctx->d_bit_state, 0, ctx->chain_cap * 8, ctx->stream));
+        CK(cudaMemsetAsync(ctx->d_ff_state, 0, ctx->chain_cap * 8, ctx->stream));
+        ctx->epoch++;
+    }
+    EfParams q;
+    q.zz = zz;
+    q.coff1 = n[0];
+    q.coff2 = n[0] + n[1];
+    q.n_mcu = n[1];
+    q.n_chunks = n_chunks(n);
+    q.dc_pred[0] = q.dc_pred[1] = q.dc_pred[2] = 0;
+    q.header_len = ctx->hdr_len;
+    q.st = ctx->d_state;
+    q.bit_state = ctx->d_bit_state;
+    q.ff_state = ctx->d_ff_state;
+    q.epoch = ++ctx->epoch;
+    q.header = ctx->d_header;
+    q.out = d_out;
+    q.cap = (unsigned long long)cap;
+    q.len_out = len_out;
+    q.dbg_block_off = NULL;
+    {
+        LaunchScope ls(ctx, KI_K35);
+        if (ratio == 0)
+            k35_entropy<0><<<(unsigned)q.n_chunks, EcCfg<0>::NT, EfSmem<0>::BYTES, ctx->stream>>>(q, ctx->d_hbits, ctx->d_huff);
+        else
+            k35_entropy<1><<<(unsigned)q.n_chunks, EcCfg<1>::NT, EfSmem<1>::BYTES, ctx->stream>>>(q, ctx->d_hbits, ctx->d_huff);
+    }
+    CK(cudaGetLastError());
+    return JPGB200_OK;
+}
+
 static int encode_core(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w, int h,
                        int quality, int ratio, uint8_t *d_out, size_t cap, unsigned long long *len_out)
 {
@@ -644,9 +764,16 @@ static int encode_core(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g,
     ctx->ratio = ratio;
     memcpy(ctx->n, n, sizeof n);
     if ((rc = launch_k1(ctx, d_r, d_g, d_b, w, h, ratio, n, 1, 0, ctx->d_zz, 0, 0))) return rc;
-    if ((rc = launch_bits(ctx, ctx->d_zz, ratio, n))) return rc;
-    if (d_out) rc = launch_pack(ctx, ctx->d_zz, ratio, n, d_out, cap, len_out);
-    return rc;
+    if (d_out) {
+        ctx->have_bits = false;
+        if (ctx->legacy_entropy) {
+            if ((rc = launch_bits(ctx, ctx->d_zz, ratio, n))) return rc;
+            return launch_pack(ctx, ctx->d_zz, ratio, n, d_out, cap, len_out);
+        }
+        return launch_fused(ctx, ctx->d_zz, ratio, n, d_out, cap, len_out);
+    }
+    /* parity tap: coefficients plus the staged K3/K4 bit offsets */
+    return launch_bits(ctx, ctx->d_zz, ratio, n);
 }
 
 /* ---- public encode entry points -------------------------------------------------------------- */

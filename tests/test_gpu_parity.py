@@ -356,3 +356,48 @@ def test_full_size_8k_properties(enc):
         enc.free(d_pl)
         enc.free(d_out)
         enc.free(d_len)
+
+
+@pytest.mark.parametrize("w,h,q,ratio,kind,seed", [(520, 72, 24, 0, 0, 16), (1024, 1032, 97, 1, 1, 17),
+                                                   (1024, 512, 97, 0, 1, 21), (640, 480, 75, 0, 0, 18),
+                                                   (3840, 2160, 90, 1, 0, 1002)])
+def test_staged_and_fused_entropy_agree(enc, w, h, q, ratio, kind, seed):
+    """The fused single-launch entropy kernel (K35) and the staged K3/K4/K5/K6 pipeline emit
+    the same bytes; the q97 noise cases overflow K35's staging buffer and exercise its
+    multi-batch path and K5's direct-to-HBM path."""
+    r, g, b = O.synth_planes(w, h, seed, 0, kind)
+    try:
+        enc.set_staged_entropy(False)
+        fused = enc.encode_planar(r, g, b, w, h, q, ratio)
+        enc.set_staged_entropy(True)
+        staged = enc.encode_planar(r, g, b, w, h, q, ratio)
+        enc.set_staged_entropy(False)
+        fused2 = enc.encode_planar(r, g, b, w, h, q, ratio)  # fused right after staged: separate ticket counters
+    finally:
+        enc.set_staged_entropy(True)
+    assert fused.shape == staged.shape and (fused == staged).all()
+    assert fused2.shape == staged.shape and (fused2 == staged).all()
+    zz = enc.coefficients(r, g, b, w, h, q, ratio)
+    scan, _ = O.encode_scan(zz, w, h, ratio)
+    want = np.concatenate([O.jfif_header(w, h, q, ratio), scan, np.array([0xFF, 0xD9], np.uint8)])
+    assert staged.shape == want.shape and (staged == want).all()
+
+
+@pytest.mark.parametrize("w,h,q,ratio,seed", [(272, 24, 75, 0, 31), (528, 40, 50, 0, 32), (544, 32, 90, 1, 33),
+                                              (1920, 1080, 75, 0, 34), (256, 8, 75, 1, 35), (16, 16, 75, 0, 36)])
+def test_tma_and_plain_transform_agree(enc, w, h, q, ratio, seed):
+    """K1 has two loaders (persistent + TMA bulk copies; one CTA per tile + direct loads):
+    bit-identical coefficients, including the shifted last block column and ragged tiles."""
+    r, g, b = O.synth_planes(w, h, seed, 0, 0)
+    oob = np.arange(24, dtype=np.uint8) * 7 + 3
+    enc.set_oob_bytes(oob)
+    try:
+        enc.set_plain_transform(False)
+        a = enc.coefficients(r, g, b, w, h, q, ratio)
+        enc.set_plain_transform(True)
+        p = enc.coefficients(r, g, b, w, h, q, ratio)
+    finally:
+        enc.set_plain_transform(False)
+        enc.set_oob_bytes(np.zeros(24, np.uint8))
+    assert (a == p).all()
+    assert_coeff_close(a, O.coefficients(r, g, b, w, h, q, ratio, oob=oob), "tma")
