@@ -97,6 +97,29 @@ int jpgb200_encode_batch_device(jpgb200_ctx *ctx, const uint8_t *d_planes, int n
 int jpgb200_encode_batch_host(jpgb200_ctx *ctx, const uint8_t *const *frames, int n_frames, int width, int height,
                               int quality, int sample_ratio, uint8_t *const *outs, size_t cap, size_t *lens);
 
+/* ---- MCU-row partition of one large image across GPUs ---------------------
+ * The reference has no counterpart (it cannot even load such an image: int fileSize,
+ * src/bitmap.c:27).  Rank k holds a band of `band_height` rows (multiple of 8) on its GPU and
+ * calls, in order, with four small exchanges in between (INTEGRATION.md shows them as NCCL
+ * allgathers; jpeg-encoder-and-decoder_b200/mgpu.py is the reference orchestration):
+ *   band_transform: K1.  d_r/g/b point at the band's first row; when has_halo != 0 the image
+ *                row above it must be valid memory in front of the band (the 1-row halo of the
+ *                reference's last-block-column quirk).  -> last_dc[3]          [exchange 0]
+ *   band_bits    : K3+K4 with pred_dc = previous band's last_dc (zeros for band 0): the DC
+ *                predictor changes the length of the band's first blocks.  -> band_bits [exchange 1]
+ *   band_pack    : K5 at bit_phase = (sum of earlier bands' bits) & 7; is_last for the final
+ *                band.  -> owned_bytes (stream bytes whose last bit lies in this band) and
+ *                tail_byte (its trailing partial byte, which the NEXT band owns)  [exchange 2]
+ *   band_finish  : K6.  carry_byte = previous band's tail_byte; stuffs the owned bytes into
+ *                d_segment.  -> segment_len                                    [exchange 3]
+ * Segments are byte-aligned: header, then the segments in band order, then EOI. */
+int jpgb200_band_transform(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int width,
+                           int band_height, int has_halo, int quality, int sample_ratio, int last_dc[3]);
+int jpgb200_band_bits(jpgb200_ctx *ctx, const int pred_dc[3], unsigned long long *band_bits);
+int jpgb200_band_pack(jpgb200_ctx *ctx, int bit_phase, int is_last, unsigned long long *owned_bytes,
+                      uint8_t *tail_byte);
+int jpgb200_band_finish(jpgb200_ctx *ctx, int carry_byte, uint8_t *d_segment, size_t cap,
+                        unsigned long long *segment_len);
 /* JFIF header bytes for (w,h,q,ratio): SOI..SOS, 623 bytes. */
 int jpgb200_jfif_header(int width, int height, int quality, int sample_ratio, uint8_t *out, size_t cap, size_t *len);
 
@@ -122,6 +145,24 @@ long long jpgb200_num_blocks(int width, int height, int sample_ratio, long long 
 int jpgb200_stage_dct(jpgb200_ctx *ctx, double *blocks, long long n);                        /* dct_block */
 int jpgb200_stage_quantise(jpgb200_ctx *ctx, double *blocks, long long n, const int table[64]); /* quantise_lum|chr */
 int jpgb200_stage_zigzag(jpgb200_ctx *ctx, const double *blocks, long long n, int *zz);       /* zig_zag_block */
+/* The remaining per-stage functions of the reference, GPU-backed, so that a caller of its
+ * stage-level API (void f(JpgData), src/jpg_encode.c:32-50) gets reference-shaped results:
+ *   preprocess_jpeg's block fill + level shift (src/preprocess.c:155-169,176-196), FP64, same
+ *   operation order, including the last-block-column shift; blocks are [N][64] doubles */
+int jpgb200_stage_preprocess(jpgb200_ctx *ctx, const uint8_t *r, const uint8_t *g, const uint8_t *b, int width,
+                             int height, double *Y, double *Cb, double *Cr);
+/*   subsample_422 (a stub in src/downsample.c:24; semantics SURVEY.md A.3): in = full-resolution
+ *   chroma blocks [bh][bw][64], out = [bh][bw/2][64] */
+int jpgb200_stage_subsample422(jpgb200_ctx *ctx, const double *in, double *out, int width_blocks, int height_blocks);
+/*   dpcm() (src/dpcm.c:6-21) on one component's DC sequence, in place: d[i] = dc[i] - d[i-1] */
+int jpgb200_stage_dpcm(jpgb200_ctx *ctx, int *dc, long long n);
+/*   calculate_freq_block_DC/AC (src/huffman.c:182-222) over n int[64] blocks, accumulated into
+ *   freq_dc[257] / freq_ac[257]; sym_mode JPGB200_SYM_REF reproduces run|size */
+int jpgb200_stage_histograms(jpgb200_ctx *ctx, const int *zz, long long n, int sym_mode, int *freq_dc, int *freq_ac);
+/* Entropy-code caller-supplied quantised zig-zag coefficients (layout of jpgb200_coefficients)
+ * into a complete JFIF stream: what huffman_encode (src/huffman.c:23) was meant to end in. */
+int jpgb200_encode_coefficients(jpgb200_ctx *ctx, const int16_t *zz, int width, int height, int quality,
+                                int sample_ratio, uint8_t *out, size_t cap, size_t *len);
 /* scaled tables as the reference's first scale_table call leaves them (src/quantise.c:74-86) */
 int jpgb200_quant_tables(int quality, int lum[64], int chr[64]);
 

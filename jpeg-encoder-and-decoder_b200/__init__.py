@@ -6,5 +6,5 @@ The product is csrc/ (CUDA kernels + the extern "C" boundary of include/jpgb200.
 for tests/ and bench.py.  The directory name contains hyphens, so load it through
 `__graft_entry__.load_package()` (importlib) under the module name `jpgb200`.
 """
-from . import binding, build  # noqa: F401
+from . import binding, build, mgpu  # noqa: F401
 from .binding import Encoder, Jpgb200Error  # noqa: F401

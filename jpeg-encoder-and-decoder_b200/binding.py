@@ -38,6 +38,10 @@ _SIGS = {
     "jpgb200_encode_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
     "jpgb200_encode_batch_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
     "jpgb200_encode_batch_host": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
+    "jpgb200_band_transform": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_int)]),
+    "jpgb200_band_bits": (C.c_int, [_vp, C.POINTER(C.c_int), C.POINTER(C.c_ulonglong)]),
+    "jpgb200_band_pack": (C.c_int, [_vp, C.c_int, C.c_int, C.POINTER(C.c_ulonglong), C.POINTER(C.c_uint8)]),
+    "jpgb200_band_finish": (C.c_int, [_vp, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_ulonglong)]),
     "jpgb200_jfif_header": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "jpgb200_coefficients": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp]),
     "jpgb200_dc_sequence": (C.c_int, [_vp, C.c_int, _vp]),
@@ -48,6 +52,11 @@ _SIGS = {
     "jpgb200_stage_quantise": (C.c_int, [_vp, _vp, C.c_longlong, _vp]),
     "jpgb200_stage_zigzag": (C.c_int, [_vp, _vp, C.c_longlong, _vp]),
     "jpgb200_quant_tables": (C.c_int, [C.c_int, _vp, _vp]),
+    "jpgb200_stage_preprocess": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, _vp, _vp, _vp]),
+    "jpgb200_stage_subsample422": (C.c_int, [_vp, _vp, _vp, C.c_int, C.c_int]),
+    "jpgb200_stage_dpcm": (C.c_int, [_vp, _vp, C.c_longlong]),
+    "jpgb200_stage_histograms": (C.c_int, [_vp, _vp, C.c_longlong, C.c_int, _vp, _vp]),
+    "jpgb200_encode_coefficients": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "jpgb200_device_count": (C.c_int, []),
     "jpgb200_malloc": (C.c_int, [_vp, C.POINTER(_vp), C.c_size_t]),
     "jpgb200_free": (C.c_int, [_vp, _vp]),
@@ -193,6 +202,29 @@ class Encoder:
         self._ck(lib().jpgb200_encode_batch_host(self._h, fa, n, w, h, quality, ratio, oa, cap, lens))
         return [int(x) for x in lens]
 
+    # ---- MCU-row bands (one band per rank; see mgpu.py)
+    def band_transform(self, d_r, d_g, d_b, w, band_h, has_halo, quality, ratio):
+        dc = (C.c_int * 3)()
+        self._ck(lib().jpgb200_band_transform(self._h, d_r, d_g, d_b, w, band_h, 1 if has_halo else 0, quality, ratio, dc))
+        return [int(dc[0]), int(dc[1]), int(dc[2])]
+
+    def band_bits(self, pred_dc):
+        bits = C.c_ulonglong(0)
+        pd = (C.c_int * 3)(*pred_dc)
+        self._ck(lib().jpgb200_band_bits(self._h, pd, C.byref(bits)))
+        return int(bits.value)
+
+    def band_pack(self, bit_phase, is_last):
+        own = C.c_ulonglong(0)
+        tail = C.c_uint8(0)
+        self._ck(lib().jpgb200_band_pack(self._h, bit_phase, 1 if is_last else 0, C.byref(own), C.byref(tail)))
+        return int(own.value), int(tail.value)
+
+    def band_finish(self, carry_byte, d_segment, cap):
+        n = C.c_ulonglong(0)
+        self._ck(lib().jpgb200_band_finish(self._h, carry_byte, d_segment, cap, C.byref(n)))
+        return int(n.value)
+
     # ---- parity taps
     def coefficients(self, r, g, b, w, h, quality, ratio=0):
         r, g, b = _c(r), _c(g), _c(b)
@@ -234,6 +266,40 @@ class Encoder:
         zz = np.zeros((b.shape[0], 64), np.int32)
         self._ck(lib().jpgb200_stage_zigzag(self._h, b.ctypes.data, b.shape[0], zz.ctypes.data))
         return zz
+
+    def stage_preprocess(self, r, g, b, w, h):
+        r, g, b = _c(r), _c(g), _c(b)
+        n = (w // 8) * (h // 8)
+        Y, Cb, Cr = (np.zeros((n, 64), np.float64) for _ in range(3))
+        self._ck(lib().jpgb200_stage_preprocess(self._h, r.ctypes.data, g.ctypes.data, b.ctypes.data, w, h,
+                                               Y.ctypes.data, Cb.ctypes.data, Cr.ctypes.data))
+        return Y, Cb, Cr
+
+    def stage_subsample422(self, blocks, bw, bh):
+        blk = np.ascontiguousarray(blocks, np.float64).reshape(-1, 64)
+        out = np.zeros((blk.shape[0] // 2, 64), np.float64)
+        self._ck(lib().jpgb200_stage_subsample422(self._h, blk.ctypes.data, out.ctypes.data, bw, bh))
+        return out
+
+    def stage_dpcm(self, dc):
+        d = np.ascontiguousarray(dc, np.int32).copy()
+        self._ck(lib().jpgb200_stage_dpcm(self._h, d.ctypes.data, d.size))
+        return d
+
+    def stage_histograms(self, zz, sym_mode, freq_dc=None, freq_ac=None):
+        z = np.ascontiguousarray(zz, np.int32).reshape(-1, 64)
+        fd = np.zeros(257, np.int32) if freq_dc is None else np.ascontiguousarray(freq_dc, np.int32).copy()
+        fa = np.zeros(257, np.int32) if freq_ac is None else np.ascontiguousarray(freq_ac, np.int32).copy()
+        self._ck(lib().jpgb200_stage_histograms(self._h, z.ctypes.data, z.shape[0], sym_mode, fd.ctypes.data, fa.ctypes.data))
+        return fd, fa
+
+    def encode_coefficients(self, zz, w, h, quality, ratio=0, cap=None):
+        z = np.ascontiguousarray(zz, np.int16)
+        cap = cap or (w * h * 3 + 65536)
+        out = np.empty(cap, np.uint8)
+        n = C.c_size_t(0)
+        self._ck(lib().jpgb200_encode_coefficients(self._h, z.ctypes.data, w, h, quality, ratio, out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value].copy()
 
     # ---- device helpers
     def malloc(self, nbytes):

@@ -85,6 +85,10 @@ struct jpgb200_ctx {
     int w, h, q, ratio;
     long long n[3];
     bool have_bits;
+    /* MCU-row band in progress (jpgb200_band_*) */
+    unsigned long long band_bits;
+    int band_phase, band_last, band_ratio, band_pred[3];
+    long long band_n[3];
     bool legacy_entropy; /* staged K3/K4/K5/K6 pipeline instead of the fused K35 (tests) */
     /* quantiser cache */
     int q_cached;
@@ -283,6 +287,12 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
     ctx->device = device;
     ctx->q_cached = -1;
     ctx->legacy_entropy = true; /* measured faster than the fused K35 so far */
+    {
+        const char *e = getenv("JPGB200_ENTROPY"); /* "fused" | "staged": experiment switch for bench runs */
+        if (e && !strcmp(e, "fused")) ctx->legacy_entropy = false;
+        const char *k = getenv("JPGB200_K1"); /* "plain" | "tma" */
+        if (k && !strcmp(k, "plain")) ctx->k1_plain = true;
+    }
     ctx->hdr_w = -1;
     ctx->err[0] = 0;
     cudaDeviceProp prop;
@@ -655,10 +665,12 @@ static void fill_ec(jpgb200_ctx *ctx, EcParams &e, const int16_t *zz, const long
 }
 
 /* K3 + K4: bit lengths and their device-wide exclusive scan */
-static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3])
+static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3], const int *pred = NULL)
 {
     EcParams e;
     fill_ec(ctx, e, zz, n);
+    if (pred)
+        for (int c = 0; c < 3; c++) e.dc_pred[c] = pred[c];
     const unsigned nc = (unsigned)n_chunks(n);
     {
         LaunchScope ls(ctx, KI_K3);
@@ -702,7 +714,7 @@ static int launch_pack(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
         LaunchScope ls(ctx, KI_K6);
         k6_stuff<<<pgrid, K6_THREADS, 0, ctx->stream>>>(reinterpret_cast<uint4 *>(ctx->d_ubuf), ctx->d_state,
                                                         ctx->d_tile_base, ctx->d_header, ctx->hdr_len, d_out,
-                                                        (unsigned long long)cap, len_out, ++ctx->epoch);
+                                                        (unsigned long long)cap, len_out, ++ctx->epoch, -1ll, 1);
     }
     CK(cudaGetLastError());
     return JPGB200_OK;
@@ -938,6 +950,130 @@ extern "C" int jpgb200_encode_batch_host(jpgb200_ctx *ctx, const uint8_t *const 
     return rc;
 }
 
+/* ---- MCU-row partition of one large image across GPUs -----------------------------
+ * Each rank runs the staged pipeline on its band; three tiny host-side exchanges (done by the
+ * caller with NCCL allgathers) carry {band bits, last DCs}, {trailing partial byte} and
+ * {stuffed length} between ranks.  A band OWNS the stream bytes whose last bit lies in its bit
+ * range, so every stuffed segment is byte-aligned and segments simply concatenate. */
+extern "C" int jpgb200_band_transform(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b,
+                                      int w, int band_h, int has_halo, int quality, int ratio, int last_dc[3])
+{
+    if (!ctx || !d_r || !d_g || !d_b || !last_dc) return JPGB200_ERR_BAD_ARG;
+    long long n[3];
+    int rc = validate(w, band_h, quality, ratio, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = ensure_workspace(ctx, n, 1))) return rc;
+    if (ctx->q_cached != quality) {
+        int lum[64], chr[64];
+        if (jpgb200_quant_tables(quality, lum, chr)) return JPGB200_ERR_BAD_QUALITY;
+        make_quant_multipliers(lum, ctx->mul[0]);
+        make_quant_multipliers(chr, ctx->mul[1]);
+        ctx->q_cached = quality;
+    }
+    ctx->w = w;
+    ctx->h = band_h;
+    ctx->q = quality;
+    ctx->ratio = ratio;
+    memcpy(ctx->n, n, sizeof n);
+    memcpy(ctx->band_n, n, sizeof n);
+    ctx->band_ratio = ratio;
+    ctx->have_bits = false;
+    if ((rc = launch_k1(ctx, d_r, d_g, d_b, w, band_h, ratio, n, 1, 0, ctx->d_zz, 0, has_halo ? 1 : 0))) return rc;
+    int16_t dc[3];
+    CK(cudaMemcpyAsync(&dc[0], ctx->d_zz + (n[0] - 1) * 64, 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&dc[1], ctx->d_zz + (n[0] + n[1] - 1) * 64, 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(&dc[2], ctx->d_zz + (n[0] + n[1] + n[2] - 1) * 64, 2, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int c = 0; c < 3; c++) last_dc[c] = dc[c];
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_band_bits(jpgb200_ctx *ctx, const int pred_dc[3], unsigned long long *band_bits)
+{
+    if (!ctx || !pred_dc || !band_bits) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    for (int c = 0; c < 3; c++) ctx->band_pred[c] = pred_dc[c];
+    int rc = launch_bits(ctx, ctx->d_zz, ctx->band_ratio, ctx->band_n, ctx->band_pred);
+    if (rc) return rc;
+    EncState st;
+    CK(cudaMemcpyAsync(&st, ctx->d_state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (st.error) return JPGB200_ERR_OUT_TOO_SMALL;
+    ctx->band_bits = st.total_bits;
+    *band_bits = st.total_bits;
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_band_pack(jpgb200_ctx *ctx, int bit_phase, int is_last, unsigned long long *owned_bytes,
+                                 uint8_t *tail_byte)
+{
+    if (!ctx || !owned_bytes || !tail_byte || bit_phase < 0 || bit_phase > 7) return JPGB200_ERR_BAD_ARG;
+    const int *pred_dc = ctx->band_pred;
+    CK(cudaSetDevice(ctx->device));
+    EcParams e;
+    fill_ec(ctx, e, ctx->d_zz, ctx->band_n);
+    e.dc_pred[0] = pred_dc[0];
+    e.dc_pred[1] = pred_dc[1];
+    e.dc_pred[2] = pred_dc[2];
+    e.bit_base = (unsigned long long)bit_phase;
+    e.is_last_band = is_last ? 1 : 0;
+    const unsigned nc = (unsigned)n_chunks(ctx->band_n);
+    {
+        LaunchScope ls(ctx, KI_K5);
+        if (ctx->band_ratio == 0)
+            k5_pack<0><<<nc, EcCfg<0>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
+        else
+            k5_pack<1><<<nc, EcCfg<1>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
+    }
+    CK(cudaGetLastError());
+    const unsigned long long end = (unsigned long long)bit_phase + ctx->band_bits;
+    unsigned long long own = end >> 3;
+    if (is_last && (end & 7ull)) own += 1; /* the 1-padded final byte */
+    *tail_byte = 0;
+    if (!is_last && (end & 7ull))
+        CK(cudaMemcpyAsync(tail_byte, reinterpret_cast<const uint8_t *>(ctx->d_ubuf) + (end >> 3), 1, cudaMemcpyDeviceToHost,
+                           ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->band_phase = bit_phase;
+    ctx->band_last = is_last ? 1 : 0;
+    *owned_bytes = own;
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_band_finish(jpgb200_ctx *ctx, int carry_byte, uint8_t *d_segment, size_t cap,
+                                   unsigned long long *segment_len)
+{
+    if (!ctx || !d_segment || !segment_len) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const unsigned long long end = (unsigned long long)ctx->band_phase + ctx->band_bits;
+    unsigned long long own = end >> 3;
+    if (ctx->band_last && (end & 7ull)) own += 1;
+    if (ctx->band_phase) {
+        k_or_first_byte<<<1, 1, 0, ctx->stream>>>(ctx->d_ubuf, (uint32_t)carry_byte);
+        ctx->launch_total++;
+    }
+    if (((ctx->epoch + 1) & ((1ull << K6_EPOCH_BITS) - 1ull)) == 0ull) {
+        CK(cudaMemsetAsync(ctx->d_tile_base, 0, ctx->tile_bytes, ctx->stream));
+        ctx->epoch++;
+    }
+    {
+        LaunchScope ls(ctx, KI_K6);
+        k6_stuff<<<(unsigned)ctx->sm_count * 4, K6_THREADS, 0, ctx->stream>>>(
+            reinterpret_cast<uint4 *>(ctx->d_ubuf), ctx->d_state, ctx->d_tile_base, ctx->d_header, 0, d_segment,
+            (unsigned long long)cap, ctx->d_len, ++ctx->epoch, (long long)own, 0);
+    }
+    CK(cudaGetLastError());
+    /* the trailing partial byte belongs to the next band: clear its line for the next encode's K5 */
+    CK(cudaMemsetAsync(reinterpret_cast<uint8_t *>(ctx->d_ubuf) + ((end >> 3) & ~15ull), 0, 32, ctx->stream));
+    unsigned long long l = 0;
+    CK(cudaMemcpyAsync(&l, ctx->d_len, sizeof l, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (own && l == 0) return JPGB200_ERR_OUT_TOO_SMALL;
+    *segment_len = l;
+    return JPGB200_OK;
+}
+
 /* ---- parity taps -------------------------------------------------------------------------------- */
 
 extern "C" int jpgb200_coefficients(jpgb200_ctx *ctx, const uint8_t *r, const uint8_t *g, const uint8_t *b, int w, int h,
@@ -1107,6 +1243,145 @@ extern "C" int jpgb200_stage_zigzag(jpgb200_ctx *ctx, const double *blocks, long
     CK(cudaFree(d));
     CK(cudaFree(z));
     return JPGB200_OK;
+}
+
+/* RAII-free scratch helper for the staged entry points (they are not on the hot path) */
+struct Scratch {
+    jpgb200_ctx *ctx;
+    std::vector<void *> ptrs;
+    explicit Scratch(jpgb200_ctx *c) : ctx(c) {}
+    ~Scratch()
+    {
+        for (void *p : ptrs) cudaFree(p);
+    }
+    int get(size_t bytes, void **p)
+    {
+        int rc = stage_buf(ctx, bytes, p);
+        if (rc == JPGB200_OK) ptrs.push_back(*p);
+        return rc;
+    }
+};
+
+extern "C" int jpgb200_stage_preprocess(jpgb200_ctx *ctx, const uint8_t *r, const uint8_t *g, const uint8_t *b, int w,
+                                        int h, double *Y, double *Cb, double *Cr)
+{
+    if (!ctx || !r || !g || !b || !Y || !Cb || !Cr) return JPGB200_ERR_BAD_ARG;
+    if (w <= 0 || h <= 0 || (w % 8) || (h % 8)) return JPGB200_ERR_BAD_DIMS;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)w * h;
+    Scratch sc(ctx);
+    void *dp = NULL, *dd = NULL, *doob = NULL;
+    int rc;
+    if ((rc = sc.get(3 * npx, &dp)) || (rc = sc.get(3 * npx * 8, &dd)) || (rc = sc.get(32, &doob))) return rc;
+    uint8_t *pl = (uint8_t *)dp;
+    double *blk = (double *)dd;
+    CK(cudaMemcpyAsync(pl, r, npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(pl + npx, g, npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(pl + 2 * npx, b, npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(doob, ctx->oob, 24, cudaMemcpyHostToDevice, ctx->stream));
+    kf_preprocess_blocks<<<(unsigned)((npx + 255) / 256), 256, 0, ctx->stream>>>(pl, pl + npx, pl + 2 * npx, w, h,
+                                                                               (const uint8_t *)doob, blk, blk + npx,
+                                                                               blk + 2 * npx);
+    ctx->launch_total++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(Y, blk, npx * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(Cb, blk + npx, npx * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(Cr, blk + 2 * npx, npx * 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_stage_subsample422(jpgb200_ctx *ctx, const double *in, double *out, int width_blocks,
+                                          int height_blocks)
+{
+    if (!ctx || !in || !out || width_blocks <= 0 || height_blocks <= 0 || (width_blocks & 1)) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t nin = (size_t)width_blocks * height_blocks, nout = nin / 2;
+    Scratch sc(ctx);
+    void *di = NULL, *dout = NULL;
+    int rc;
+    if ((rc = sc.get(nin * 512, &di)) || (rc = sc.get(nout * 512, &dout))) return rc;
+    CK(cudaMemcpyAsync(di, in, nin * 512, cudaMemcpyHostToDevice, ctx->stream));
+    kf_subsample422_blocks<<<(unsigned)nout, 64, 0, ctx->stream>>>((const double *)di, (double *)dout, width_blocks);
+    ctx->launch_total++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(out, dout, nout * 512, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_stage_dpcm(jpgb200_ctx *ctx, int *dc, long long n)
+{
+    if (!ctx || !dc || n <= 0) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const unsigned tiles = (unsigned)((n + K2_TILE - 1) / K2_TILE);
+    Scratch sc(ctx);
+    void *din = NULL, *dout = NULL, *dts = NULL;
+    int rc;
+    if ((rc = sc.get((size_t)n * 4, &din)) || (rc = sc.get((size_t)n * 4, &dout)) || (rc = sc.get((size_t)tiles * 4, &dts)))
+        return rc;
+    CK(cudaMemcpyAsync(din, dc, (size_t)n * 4, cudaMemcpyHostToDevice, ctx->stream));
+    k2s_tile_sums<<<tiles, K2_THREADS, 0, ctx->stream>>>((const int *)din, n, (int *)dts);
+    k2_scan_tiles<<<1, 1024, 0, ctx->stream>>>((int *)dts, (long long)tiles);
+    k2s_apply<<<tiles, K2_THREADS, 0, ctx->stream>>>((const int *)din, n, (const int *)dts, (int *)dout);
+    ctx->launch_total += 3;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(dc, dout, (size_t)n * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_stage_histograms(jpgb200_ctx *ctx, const int *zz, long long n, int sym_mode, int *freq_dc,
+                                        int *freq_ac)
+{
+    if (!ctx || !zz || !freq_dc || !freq_ac || n <= 0) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    Scratch sc(ctx);
+    void *dz = NULL, *df = NULL;
+    int rc;
+    if ((rc = sc.get((size_t)n * 256, &dz)) || (rc = sc.get(2 * 257 * 4, &df))) return rc;
+    int *f = (int *)df;
+    CK(cudaMemcpyAsync(dz, zz, (size_t)n * 256, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f, freq_dc, 257 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(f + 257, freq_ac, 257 * 4, cudaMemcpyHostToDevice, ctx->stream));
+    khs_histograms<<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((const int *)dz, n, sym_mode, f, f + 257);
+    ctx->launch_total++;
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(freq_dc, f, 257 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(freq_ac, f + 257, 257 * 4, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JPGB200_OK;
+}
+
+/* Entropy-code caller-supplied quantised coefficients (host, int16 [Y|Cb|Cr][block][64]) into a
+ * complete JFIF stream: K3..K6 (or K35) only.  "Given identical coefficients the bytes are
+ * identical" is checked through this entry point. */
+extern "C" int jpgb200_encode_coefficients(jpgb200_ctx *ctx, const int16_t *zz, int w, int h, int quality, int ratio,
+                                           uint8_t *out, size_t cap, size_t *len)
+{
+    if (!ctx || !zz || !out) return JPGB200_ERR_BAD_ARG;
+    long long n[3];
+    int rc = validate(w, h, quality, ratio, n);
+    if (rc) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = ensure_workspace(ctx, n, 1))) return rc;
+    if ((rc = ensure_tables(ctx, w, h, quality, ratio))) return rc;
+    if (ctx->out_cap < cap || !ctx->d_out[1] || !ctx->d_planes[1]) {
+        if ((rc = ensure_io(ctx, ctx->planes_cap ? ctx->planes_cap / 3 : 64, cap, 2))) return rc;
+    }
+    ctx->w = w;
+    ctx->h = h;
+    ctx->q = quality;
+    ctx->ratio = ratio;
+    memcpy(ctx->n, n, sizeof n);
+    CK(cudaMemcpyAsync(ctx->d_zz, zz, (size_t)(n[0] + n[1] + n[2]) * 128, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->legacy_entropy) {
+        if ((rc = launch_bits(ctx, ctx->d_zz, ratio, n))) return rc;
+        if ((rc = launch_pack(ctx, ctx->d_zz, ratio, n, ctx->d_out[0], cap, ctx->d_len))) return rc;
+    } else {
+        if ((rc = launch_fused(ctx, ctx->d_zz, ratio, n, ctx->d_out[0], cap, ctx->d_len))) return rc;
+    }
+    return finish_host(ctx, ctx->d_out[0], out, cap, len);
 }
 
 /* ---- device helpers -------------------------------------------------------------------------------- */

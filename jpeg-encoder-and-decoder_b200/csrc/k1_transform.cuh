@@ -319,12 +319,12 @@ struct K1Tile {
 __device__ __forceinline__ K1Tile k1_tile(const K1Params &p, long long t)
 {
     K1Tile o;
-    const int bh = p.H >> 3;
-    const long long per_frame = (long long)p.tiles_per_row * bh;
-    o.frame = (int)(t / per_frame);
-    const int rem = (int)(t - (long long)o.frame * per_frame);
-    o.by = rem / p.tiles_per_row;
-    o.tb0 = (rem - o.by * p.tiles_per_row) * K1_TILE_BLOCKS;
+    const unsigned tpr = (unsigned)p.tiles_per_row, per_frame = tpr * (unsigned)(p.H >> 3);
+    const unsigned tt = (unsigned)t; /* tile counts stay far below 2^32 */
+    o.frame = (int)(tt / per_frame);
+    const unsigned rem = tt - (unsigned)o.frame * per_frame;
+    o.by = (int)(rem / tpr);
+    o.tb0 = (int)(rem - (unsigned)o.by * tpr) * K1_TILE_BLOCKS;
     return o;
 }
 
@@ -420,8 +420,10 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform_tma(const K1Params
             k1_convert<RATIO>(S.sF, y, seg, vr, vg, vb);
         }
         __syncthreads();
-        /* the stage's raw bytes are consumed: refill it with the tile K1_STAGES iterations ahead */
-        if (tid < 32) {
+        /* the stage's raw bytes are consumed: refill it with the tile K1_STAGES iterations ahead.
+         * Issued by warp 3, which has no 8x8 blocks to transform in phase 2 (4:4:4: 3 component
+         * warps, 4:2:2: 2), so the TMA descriptors cost nothing on the critical path. */
+        if (tid >= 96) {
             const long long tn = t + (long long)K1_STAGES * gridDim.x;
             if (tn < n_tiles) {
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");

@@ -97,7 +97,8 @@ __device__ __forceinline__ unsigned long long k6_lookback(volatile unsigned long
 __global__ void __launch_bounds__(K6_THREADS) k6_stuff(uint4 *ubuf, EncState *st, unsigned long long *tile_state,
                                                        const uint8_t *header, int header_len, uint8_t *out,
                                                        unsigned long long cap, unsigned long long *len_out,
-                                                       unsigned long long epoch)
+                                                       unsigned long long epoch, long long nbytes_override,
+                                                       int write_eoi)
 {
     __shared__ uint32_t sWarp[K6_THREADS / 32];
     __shared__ __align__(16) uint8_t sT[2 * K6_TILE + 32];
@@ -107,7 +108,10 @@ __global__ void __launch_bounds__(K6_THREADS) k6_stuff(uint4 *ubuf, EncState *st
         if (blockIdx.x == 0 && tid == 0 && len_out) *len_out = 0ull;
         return;
     }
-    const unsigned long long nbytes = st->nbytes, ntiles = st->n_tiles;
+    /* an MCU-row band stuffs only the bytes it owns (jpgb200_band_finish) */
+    const unsigned long long nbytes = nbytes_override >= 0 ? (unsigned long long)nbytes_override : st->nbytes;
+    const unsigned long long ntiles = (nbytes + K6_TILE - 1) / K6_TILE;
+    const unsigned long long trailer = write_eoi ? 2ull : 0ull;
     while (true) {
         if (tid == 0) sTicket = atomicAdd(&st->ticket, 1ull);
         __syncthreads();
@@ -143,7 +147,7 @@ __global__ void __launch_bounds__(K6_THREADS) k6_stuff(uint4 *ubuf, EncState *st
         const unsigned long long g0 = (unsigned long long)header_len + t * K6_TILE + excl;
         const unsigned long long tile_in = (nbytes - t * K6_TILE) >= K6_TILE ? K6_TILE : (nbytes - t * K6_TILE);
         const int n_out = (int)tile_in + (int)tile_ffs;
-        const bool fits = g0 + (unsigned long long)n_out + 2ull <= cap;
+        const bool fits = g0 + (unsigned long long)n_out + trailer <= cap;
         if (fits) {
             const unsigned long long gaddr = (unsigned long long)(uintptr_t)out + g0;
             const int phase = (int)(gaddr & 15ull);
@@ -180,9 +184,9 @@ __global__ void __launch_bounds__(K6_THREADS) k6_stuff(uint4 *ubuf, EncState *st
         }
         if (t == ntiles - 1 && tid == 0) {
             const unsigned long long total_ff = excl + (unsigned long long)tile_ffs;
-            const unsigned long long out_len = (unsigned long long)header_len + nbytes + total_ff + 2ull;
+            const unsigned long long out_len = (unsigned long long)header_len + nbytes + total_ff + trailer;
             const bool ok = out_len <= cap;
-            if (ok) {
+            if (ok && write_eoi) {
                 out[out_len - 2] = 0xFF;
                 out[out_len - 1] = 0xD9; /* EOI */
             }
@@ -194,6 +198,9 @@ __global__ void __launch_bounds__(K6_THREADS) k6_stuff(uint4 *ubuf, EncState *st
         __syncthreads();
     }
 }
+
+/* OR the previous band's trailing bits into the first byte of this band's stream */
+__global__ void k_or_first_byte(uint32_t *ubuf, uint32_t carry) { ubuf[0] |= (carry & 0xffu); }
 
 }  // namespace jpgb200
 #endif

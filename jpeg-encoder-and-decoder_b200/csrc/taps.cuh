@@ -206,6 +206,149 @@ __global__ void __launch_bounds__(64) kf_zigzag_blocks(const double *blocks, lon
     zz[(long long)blockIdx.x * 64 + scan_order[threadIdx.x]] = (int)b[threadIdx.x];
 }
 
+/* preprocess_jpeg's block fill (src/preprocess.c:155-169,186-188) in FP64 with the reference's
+ * operation order (no FMA contraction), including blockToCoords' last-column shift.
+ * One thread per sample; blocks[comp][block][y*8+x]. */
+__global__ void __launch_bounds__(256) kf_preprocess_blocks(const uint8_t *r, const uint8_t *g, const uint8_t *b, int w,
+                                                            int h, const uint8_t *oob, double *Y, double *Cb, double *Cr)
+{
+    const long long n = (long long)w * h;
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const int bw = w >> 3;
+    const long long blk = i >> 6;
+    const int s = (int)(i & 63), x = s & 7, y = s >> 3;
+    const int bx = (int)(blk % bw), by = (int)(blk / bw);
+    long long row = (long long)by * 8 + y - (bx == bw - 1 ? 1 : 0);
+    double rv, gv, bv;
+    if (row < 0) {
+        rv = oob[x];
+        gv = oob[8 + x];
+        bv = oob[16 + x];
+    } else {
+        const long long o = row * w + (long long)bx * 8 + x;
+        rv = r[o];
+        gv = g[o];
+        bv = b[o];
+    }
+    const double yv = __dadd_rn(__dadd_rn(__dmul_rn(0.299, rv), __dmul_rn(0.587, gv)), __dmul_rn(0.114, bv));
+    const double cb = 128.0 - __dadd_rn(__dadd_rn(__dmul_rn(0.168736, rv), -__dmul_rn(0.331264, gv)), __dmul_rn(0.5, bv));
+    const double cr = 128.0 + __dadd_rn(__dadd_rn(__dmul_rn(0.5, rv), -__dmul_rn(0.418688, gv)), -__dmul_rn(0.081312, bv));
+    Y[i] = yv - 128.0;
+    Cb[i] = cb - 128.0;
+    Cr[i] = cr - 128.0;
+}
+
+/* 4:2:2: mean of horizontally adjacent samples of two neighbouring
+ * full-resolution chroma blocks -> one half-resolution block */
+__global__ void __launch_bounds__(64) kf_subsample422_blocks(const double *in, double *out, int bw)
+{
+    const long long ob = blockIdx.x; /* output block: row-major over (bw/2) x bh */
+    const int cbw = bw >> 1;
+    const long long by = ob / cbw, cx = ob % cbw;
+    const int x = threadIdx.x & 7, y = threadIdx.x >> 3;
+    const double *src = in + ((by * bw + 2 * cx + (x >> 2)) * 64) + y * 8 + (x & 3) * 2;
+    out[ob * 64 + y * 8 + x] = 0.5 * (src[0] + src[1]);
+}
+
+/* dpcm() on a contiguous int32 DC array (staged API): REF recurrence via the same 3-kernel
+ * scan as K2 */
+__global__ void __launch_bounds__(K2_THREADS) k2s_tile_sums(const int *dc, long long n, int *tile_sum)
+{
+    __shared__ int sW[K2_THREADS / 32];
+    const int tid = threadIdx.x;
+    const long long i0 = (long long)blockIdx.x * K2_TILE + (long long)tid * K2_ITEMS;
+    int s = 0;
+#pragma unroll
+    for (int k = 0; k < K2_ITEMS; k++) {
+        const long long i = i0 + k;
+        if (i < n) s += (i & 1) ? -dc[i] : dc[i];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) s += __shfl_xor_sync(0xffffffffu, s, d);
+    if ((tid & 31) == 0) sW[tid >> 5] = s;
+    __syncthreads();
+    if (tid == 0) {
+        int t = 0;
+        for (int w = 0; w < K2_THREADS / 32; w++) t += sW[w];
+        tile_sum[blockIdx.x] = t;
+    }
+}
+
+__global__ void __launch_bounds__(K2_THREADS) k2s_apply(const int *dc, long long n, const int *tile_base, int *d)
+{
+    __shared__ int sW[K2_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long i0 = (long long)blockIdx.x * K2_TILE + (long long)tid * K2_ITEMS;
+    int v[K2_ITEMS], s = 0;
+#pragma unroll
+    for (int k = 0; k < K2_ITEMS; k++) {
+        const long long i = i0 + k;
+        const int x = (i < n) ? dc[i] : 0;
+        s += (i & 1) ? -x : x;
+        v[k] = s;
+    }
+    const int inc = warp_inclusive_scan_i32(s, lane);
+    if (lane == 31) sW[wid] = inc;
+    __syncthreads();
+    int wbase = 0;
+    for (int w = 0; w < wid; w++) wbase += sW[w];
+    const int base = tile_base[blockIdx.x] + wbase + inc - s;
+#pragma unroll
+    for (int k = 0; k < K2_ITEMS; k++) {
+        const long long i = i0 + k;
+        if (i < n) {
+            const int t = base + v[k];
+            d[i] = (i & 1) ? -t : t;
+        }
+    }
+}
+
+/* calculate_freq_block_DC/AC on int32 zig-zag blocks whose [0] already holds the dpcm output */
+__global__ void __launch_bounds__(256) khs_histograms(const int *zz, long long n, int sym_mode, int *fdc, int *fac)
+{
+    __shared__ int sH[2][257];
+    const int tid = threadIdx.x;
+    for (int i = tid; i < 2 * 257; i += 256) (&sH[0][0])[i] = 0;
+    __syncthreads();
+    const long long b = (long long)blockIdx.x * 256 + tid;
+    if (b < n) {
+        const int *z = zz + b * 64;
+        int cls = 32 - __clz(abs(z[0]));
+        if (cls > 256) cls = 256;
+        atomicAdd(&sH[0][cls], 1);
+        int last = 0;
+        for (int i = 63; i > 0; i--)
+            if (z[i] != 0) {
+                last = i;
+                break;
+            }
+        int run = 0;
+        for (int i = 1; i < 64; i++) {
+            if (i == last + 1) {
+                atomicAdd(&sH[1][0x00], 1);
+                break;
+            }
+            const int v = z[i];
+            if (v == 0) {
+                if (++run == 16) {
+                    atomicAdd(&sH[1][0xF0], 1);
+                    run = 0;
+                }
+            } else {
+                const int c = 32 - __clz(abs(v));
+                atomicAdd(&sH[1][(sym_mode ? ((run << 4) | c) : (run | c)) & 0xff], 1);
+                run = 0;
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = tid; i < 257; i += 256) {
+        if (sH[0][i]) atomicAdd(&fdc[i], sH[0][i]);
+        if (sH[1][i]) atomicAdd(&fac[i], sH[1][i]);
+    }
+}
+
 /* ---- KS: synthetic planes ------------------------------------------------------------- */
 __global__ void __launch_bounds__(256) ks_synth(uint8_t *planes, int w, int h, unsigned long long seed,
                                                 unsigned frame, int kind)

@@ -393,6 +393,7 @@ typedef struct {
     int nacc;
     uint64_t total_bits;
     int overflow;
+    int raw; /* 1: no byte stuffing (orc_encode_scan_raw) */
 } BitW;
 
 static void bw_byte(BitW *w, uint8_t v)
@@ -402,7 +403,7 @@ static void bw_byte(BitW *w, uint8_t v)
         return;
     }
     w->out[w->pos++] = v;
-    if (v == 0xFF) w->out[w->pos++] = 0x00;
+    if (v == 0xFF && !w->raw) w->out[w->pos++] = 0x00;
 }
 
 static void bw_put(BitW *w, uint32_t bits, int n)
@@ -527,9 +528,24 @@ static uint64_t walk_scan(BitW *w, const int16_t *zz, int wpx, int hpx, int samp
 size_t orc_encode_scan(const int16_t *zz, int w, int h, int sample_ratio, uint8_t *out, size_t cap,
                        uint64_t *total_bits)
 {
-    BitW bw = {out, cap, 0, 0, 0, 0, 0};
+    BitW bw = {out, cap, 0, 0, 0, 0, 0, 0};
     uint64_t t = walk_scan(&bw, zz, w, h, sample_ratio, NULL);
     bw_flush(&bw);
+    if (total_bits) *total_bits = t;
+    return bw.overflow ? 0 : bw.pos;
+}
+
+/* The same bit string without byte stuffing and without 1-padding (a trailing partial byte
+ * is zero-filled): what the GPU's un-stuffed buffer holds; used by the band-partition tests. */
+size_t orc_encode_scan_raw(const int16_t *zz, int w, int h, int sample_ratio, uint8_t *out, size_t cap,
+                           uint64_t *total_bits)
+{
+    BitW bw = {out, cap, 0, 0, 0, 0, 0, 1};
+    uint64_t t = walk_scan(&bw, zz, w, h, sample_ratio, NULL);
+    if (bw.nacc > 0) {
+        bw_byte(&bw, (uint8_t)((bw.acc << (8 - bw.nacc)) & 0xFF));
+        bw.nacc = 0;
+    }
     if (total_bits) *total_bits = t;
     return bw.overflow ? 0 : bw.pos;
 }

@@ -74,6 +74,10 @@ void orc_huffman_table(int table, uint16_t code[256], uint8_t len[256]);
 size_t orc_encode_scan(const int16_t *zz, int w, int h, int sample_ratio, uint8_t *out, size_t cap,
                        uint64_t *total_bits);
 
+/* Same bit string, neither stuffed nor 1-padded (trailing partial byte zero-filled). */
+size_t orc_encode_scan_raw(const int16_t *zz, int w, int h, int sample_ratio, uint8_t *out, size_t cap,
+                           uint64_t *total_bits);
+
 /* Per-block code lengths in bits, scan (MCU-interleaved) order. */
 void orc_block_bits(const int16_t *zz, int w, int h, int sample_ratio, uint32_t *bits);
 

@@ -47,6 +47,8 @@ def lib():
         L.orc_huffman_table.argtypes = [C.c_int, C.c_void_p, C.c_void_p]
         L.orc_encode_scan.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
         L.orc_encode_scan.restype = C.c_size_t
+        L.orc_encode_scan_raw.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t, C.POINTER(C.c_uint64)]
+        L.orc_encode_scan_raw.restype = C.c_size_t
         L.orc_block_bits.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_jfif_header.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.orc_jfif_header.restype = C.c_size_t
@@ -131,6 +133,16 @@ def encode_scan(zz, w, h, ratio):
     out = np.zeros(cap, dtype=np.uint8)
     tb = C.c_uint64(0)
     n = lib().orc_encode_scan(zz.ctypes.data, w, h, ratio, out.ctypes.data, cap, C.byref(tb))
+    assert n > 0
+    return out[:n].copy(), int(tb.value)
+
+
+def encode_scan_raw(zz, w, h, ratio):
+    zz = np.ascontiguousarray(zz, dtype=np.int16)
+    cap = zz.size * 4 + 1024
+    out = np.zeros(cap, dtype=np.uint8)
+    tb = C.c_uint64(0)
+    n = lib().orc_encode_scan_raw(zz.ctypes.data, w, h, ratio, out.ctypes.data, cap, C.byref(tb))
     assert n > 0
     return out[:n].copy(), int(tb.value)
 
