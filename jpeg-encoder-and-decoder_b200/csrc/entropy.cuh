@@ -23,6 +23,7 @@ namespace jpgb200 {
 
 #define EC_MCUS 64
 #define EC_ROW_CHUNKS 9 /* 8 data chunks of 16 B + 1 pad */
+#define EC_SUPER_SHIFT 6 /* chunks per super-chunk = 64 */
 
 /* pack tables */
 struct HuffDev {
@@ -47,6 +48,7 @@ struct EncState {
     int pad;
     unsigned long long ticket;     /* K6 tile dispenser                                 */
     unsigned long long ticket35;   /* K35 chunk dispenser (reset by K35 itself)         */
+    unsigned long long ticket3;    /* K3 chunk dispenser (reset by K3 itself)           */
 };
 
 struct EcParams {
@@ -57,10 +59,13 @@ struct EcParams {
     int is_last_band;      /* pad the final byte after the last block                         */
     uint32_t *local_off;   /* [n_mcu*BPM] bit offset of each block inside its chunk            */
     uint32_t *cta_bits;    /* [n_chunks] bits per chunk                                        */
-    const unsigned long long *cta_base; /* [n_chunks] exclusive scan of cta_bits (K5)         */
+    uint32_t *super_bits;  /* [ceil(n_chunks/EC_SUPER)] bits per group of EC_SUPER chunks (atomics)   */
     unsigned long long bit_base;        /* global bit offset of this band (multi-GPU)         */
     uint32_t *ubuf;        /* un-stuffed big-endian bit stream, all-zero on entry (K5)         */
-    const EncState *st;    /* error flag set by K4 when the stream would not fit ubuf          */
+    EncState *st;          /* totals and error flag, written by K5's last chunk                */
+    long long n_chunks;
+    unsigned long long ubuf_cap_bytes;
+    int tile_bytes;                     /* K6 tile size, for EncState::n_tiles                 */
 };
 
 template <int RATIO>
@@ -335,7 +340,82 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t *sWa
     return base + inc - v;
 }
 
-/* ---- K3: bit length of every block, exclusive offsets inside the chunk, chunk total ------- */
+/* chained-scan state word: flag (2 bits) | epoch (22 bits) | value (40 bits) */
+#define CS_FLAG_A 1ull
+#define CS_FLAG_P 2ull
+#define CS_VALUE_BITS 40
+#define CS_EPOCH_BITS 22
+#define CS_VALUE_MASK ((1ull << CS_VALUE_BITS) - 1ull)
+#define CS_EPOCH_MASK ((1ull << CS_EPOCH_BITS) - 1ull)
+
+__device__ __forceinline__ unsigned long long cs_pack(unsigned long long flag, unsigned long long epoch,
+                                                      unsigned long long value)
+{
+    return (flag << 62) | ((epoch & CS_EPOCH_MASK) << CS_VALUE_BITS) | (value & CS_VALUE_MASK);
+}
+
+/* Executed by all 32 lanes of one warp.  Returns the sum of the values of tiles [0, t).
+ * publish_a: announce this tile's own value first so that successors need not wait for its
+ * prefix; the inclusive prefix is published at the end when publish_p is set.
+ * Every lane inspects W consecutive predecessors per step (window of 32*W tiles, all loads in
+ * flight together), so the "prefix known" front advances 32*W tiles per memory round trip even
+ * when a whole wave of tiles starts at once. */
+template <int W>
+__device__ __forceinline__ unsigned long long cs_lookback(volatile unsigned long long *ts, unsigned long long t,
+                                                          unsigned long long epoch, unsigned long long own, int lane,
+                                                          bool publish_a, bool publish_p)
+{
+    if (t == 0) {
+        if (lane == 0 && publish_p) ts[0] = cs_pack(CS_FLAG_P, epoch, own);
+        return 0ull;
+    }
+    if (lane == 0 && publish_a) ts[t] = cs_pack(CS_FLAG_A, epoch, own);
+    unsigned long long excl = 0;
+    long long j = (long long)t - 1;
+    for (;;) {
+        bool done = false;
+        for (;;) {
+            /* lane inspects tiles j - lane*W - k, k = 0..W-1 (nearest first) */
+            unsigned long long st[W];
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                const long long idx = j - (long long)lane * W - k;
+                st[k] = idx >= 0 ? ts[idx] : cs_pack(CS_FLAG_P, epoch, 0ull); /* before tile 0: prefix 0 */
+            }
+            bool has_p = false, empty_before_p = false;
+            unsigned long long sum = 0ull;
+#pragma unroll
+            for (int k = 0; k < W; k++) {
+                const bool cur = ((st[k] >> CS_VALUE_BITS) & CS_EPOCH_MASK) == (epoch & CS_EPOCH_MASK);
+                const unsigned flag = cur ? (unsigned)(st[k] >> 62) : 0u;
+                if (!has_p) {
+                    if (flag == 0u) empty_before_p = true;
+                    sum += st[k] & CS_VALUE_MASK;
+                    if (flag == 2u) has_p = true;
+                }
+            }
+            const unsigned pm = __ballot_sync(0xffffffffu, has_p);
+            const unsigned em = __ballot_sync(0xffffffffu, empty_before_p);
+            const unsigned upto = pm ? (0xffffffffu >> (32 - __ffs((int)pm))) : 0xffffffffu; /* lanes 0..first P */
+            if ((em & upto) == 0u) {
+                unsigned long long c = ((upto >> lane) & 1u) ? sum : 0ull;
+#pragma unroll
+                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+                excl += c;
+                done = pm != 0u;
+                break;
+            }
+        }
+        if (done) break;
+        j -= 32 * W;
+    }
+    if (lane == 0 && publish_p) ts[t] = cs_pack(CS_FLAG_P, epoch, excl + own);
+    return excl;
+}
+
+/* ---- K3: bit length of every block, exclusive offsets inside the chunk, chunk total; the
+ * device-wide exclusive prefix sum of bit offsets is finished by K5 from two-level sums:
+ * per-chunk totals and (atomically accumulated) totals per 64 chunks ------------------------- */
 template <int RATIO>
 __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k3_block_bits(const EcParams p, const HuffBits *hbits)
 {
@@ -345,7 +425,8 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k3_block_bits(const EcParams
     __shared__ uint32_t sBits[NT];
     __shared__ uint32_t sWarp[NT / 32];
     const int tid = threadIdx.x;
-    const long long m0 = (long long)blockIdx.x * EC_MCUS;
+    const long long chunk = blockIdx.x;
+    const long long m0 = chunk * EC_MCUS;
 
     ec_fill<RATIO>(sC, p, m0, tid);
     ec_load_table(&sB, hbits, tid);
@@ -364,7 +445,11 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k3_block_bits(const EcParams
     uint32_t total;
     const uint32_t off = cta_exclusive_scan<NT>(sBits[tid], sWarp, tid, total);
     if (m0 * BPM + tid < p.n_mcu * BPM) p.local_off[m0 * BPM + tid] = off;
-    if (tid == 0) p.cta_bits[blockIdx.x] = total;
+    if (tid == 0) {
+        /* two-level sums instead of a scan kernel: K5 adds up at most n_chunks/64 + 63 numbers */
+        p.cta_bits[chunk] = total;
+        atomicAdd(&p.super_bits[chunk >> EC_SUPER_SHIFT], total);
+    }
 }
 
 /* ---- K5: pack every block's codes at its global bit offset -------------------------------
@@ -381,6 +466,7 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k5_pack(const EcParams p, co
     __shared__ uint4 sC[NT][EC_ROW_CHUNKS];
     __shared__ __align__(16) HuffDev sH;
     __shared__ uint32_t sS[STAGE];
+    __shared__ unsigned long long sPart[NT / 32];
     const int tid = threadIdx.x;
     const long long m0 = (long long)blockIdx.x * EC_MCUS;
 
@@ -388,22 +474,46 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k5_pack(const EcParams p, co
     ec_fill<RATIO>(sC, p, m0, tid);
     ec_load_table(&sH, huff, tid);
     const EcMap<RATIO> mp(p, m0, tid);
-    const int err = p.st->error;
-    const unsigned long long g0 = p.bit_base + p.cta_base[blockIdx.x];
-    uint32_t tbits = p.cta_bits[blockIdx.x];
+    const long long chunk = blockIdx.x;
+    uint32_t tbits = p.cta_bits[chunk];
     const uint32_t my_off = mp.valid ? p.local_off[m0 * BPM + mp.s_local] : 0u;
-    if (err) return;
+    /* exclusive prefix of the chunk totals = the chunk's global bit offset */
+    unsigned long long part = 0ull;
+    {
+        const long long sup = chunk >> EC_SUPER_SHIFT;
+        for (long long i = tid; i < sup; i += NT) part += p.super_bits[i];
+        for (long long i = (sup << EC_SUPER_SHIFT) + tid; i < chunk; i += NT) part += p.cta_bits[i];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if ((tid & 31) == 0) sPart[tid >> 5] = part;
+    for (uint32_t i = tid; i < (uint32_t)STAGE; i += NT) sS[i] = 0u;
+    cp_async_wait_all();
+    __syncthreads();
+    unsigned long long g0 = p.bit_base;
+#pragma unroll
+    for (int i = 0; i < NT / 32; i++) g0 += sPart[i];
+    const bool fits = ((g0 + tbits + 7ull) >> 3) + 64ull <= p.ubuf_cap_bytes; /* only trips on corrupted lengths */
 
     const bool last_chunk = (m0 + EC_MCUS >= p.n_mcu);
+    if (last_chunk && tid == 0) {
+        /* totals for K6 and the host */
+        const unsigned long long all = g0 - p.bit_base + tbits;
+        EncState *st = p.st;
+        st->total_bits = fits ? all : 0ull;
+        st->nbytes = fits ? (all + 7) >> 3 : 0ull;
+        st->n_tiles = (st->nbytes + (unsigned long long)p.tile_bytes - 1) / (unsigned long long)p.tile_bytes;
+        st->total_ff = 0;
+        st->out_len = 0;
+        st->error = fits ? 0 : 1;
+        st->ticket = 0ull;
+    }
+    if (!fits) return;
     if (last_chunk && p.is_last_band) tbits += (uint32_t)((8u - (uint32_t)((g0 + tbits) & 7ull)) & 7u); /* 1-padding */
     const uint32_t b0 = (uint32_t)(g0 & 31ull);
     const uint32_t nwords = (b0 + tbits + 31u) >> 5;
     uint32_t *gw = p.ubuf + (g0 >> 5);
     const bool staged = nwords <= (uint32_t)STAGE;
-    if (staged)
-        for (uint32_t i = tid; i < nwords; i += NT) sS[i] = 0u;
-    cp_async_wait_all();
-    __syncthreads();
 
     if (mp.valid) {
         const int pred = ec_dc_pred<RATIO>(sC, p, m0, tid, mp);
@@ -445,58 +555,6 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k5_pack(const EcParams p, co
         } else {
             gw[i] = v;
         }
-    }
-}
-
-/* ---- K4: single-CTA exclusive scan of per-chunk totals (uint32 -> uint64) ----------------
- * 8 items per thread: 8192 chunks (one 8K 4:4:4 frame) per pass. */
-#define SCAN_THREADS 1024
-#define SCAN_ITEMS 8
-__device__ __forceinline__ unsigned long long scan_u32_to_u64(const uint32_t *in, unsigned long long *out,
-                                                              long long n, uint32_t *sWarp)
-{
-    const int tid = threadIdx.x;
-    unsigned long long carry = 0;
-    for (long long base = 0; base < n; base += SCAN_THREADS * SCAN_ITEMS) {
-        const long long i0 = base + (long long)tid * SCAN_ITEMS;
-        uint32_t v[SCAN_ITEMS], sum = 0;
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++) {
-            v[k] = (i0 + k < n) ? in[i0 + k] : 0u;
-            sum += v[k];
-        }
-        uint32_t total;
-        uint32_t ex = cta_exclusive_scan<SCAN_THREADS>(sum, sWarp, tid, total);
-#pragma unroll
-        for (int k = 0; k < SCAN_ITEMS; k++) {
-            if (i0 + k < n) out[i0 + k] = carry + ex;
-            ex += v[k];
-        }
-        carry += total;
-        __syncthreads();
-    }
-    return carry;
-}
-
-/* chunk bits -> chunk bases, total bits, byte and tile counts */
-__global__ void __launch_bounds__(SCAN_THREADS) k4_scan_chunks(const uint32_t *cta_bits, unsigned long long *cta_base,
-                                                               long long n, EncState *st, int tile_bytes,
-                                                               unsigned long long ubuf_cap_bytes,
-                                                               unsigned long long bit_base)
-{
-    __shared__ uint32_t sWarp[SCAN_THREADS / 32];
-    const unsigned long long total = scan_u32_to_u64(cta_bits, cta_base, n, sWarp);
-    if (threadIdx.x == 0) {
-        /* the workspace is sized for the worst case, so this only trips on corrupted lengths;
-         * it keeps every later kernel inside its buffers */
-        const bool fits = ((bit_base + total + 7) >> 3) + 64ull <= ubuf_cap_bytes;
-        st->total_bits = fits ? total : 0ull;
-        st->nbytes = fits ? (total + 7) >> 3 : 0ull;
-        st->n_tiles = (st->nbytes + (unsigned long long)tile_bytes - 1) / (unsigned long long)tile_bytes;
-        st->total_ff = 0;
-        st->out_len = 0;
-        st->error = fits ? 0 : 1;
-        st->ticket = 0ull;
     }
 }
 

@@ -30,65 +30,6 @@ namespace jpgb200 {
 #define EF_CAP_BYTES 4096 /* un-stuffed bytes staged per batch */
 #define EF_CAP_BITS (EF_CAP_BYTES * 8 - 64)
 
-/* chained-scan state word: flag (2 bits) | epoch (22 bits) | value (40 bits) */
-#define CS_FLAG_A 1ull
-#define CS_FLAG_P 2ull
-#define CS_VALUE_BITS 40
-#define CS_EPOCH_BITS 22
-#define CS_VALUE_MASK ((1ull << CS_VALUE_BITS) - 1ull)
-#define CS_EPOCH_MASK ((1ull << CS_EPOCH_BITS) - 1ull)
-
-__device__ __forceinline__ unsigned long long cs_pack(unsigned long long flag, unsigned long long epoch,
-                                                      unsigned long long value)
-{
-    return (flag << 62) | ((epoch & CS_EPOCH_MASK) << CS_VALUE_BITS) | (value & CS_VALUE_MASK);
-}
-
-/* Executed by all 32 lanes of one warp.  Returns the sum of the values of tiles [0, t).
- * publish_a: announce this tile's own value first so that successors need not wait for its
- * prefix; the inclusive prefix is published at the end when publish_p is set. */
-__device__ __forceinline__ unsigned long long cs_lookback(volatile unsigned long long *ts, unsigned long long t,
-                                                          unsigned long long epoch, unsigned long long own, int lane,
-                                                          bool publish_a, bool publish_p)
-{
-    if (t == 0) {
-        if (lane == 0 && publish_p) ts[0] = cs_pack(CS_FLAG_P, epoch, own);
-        return 0ull;
-    }
-    if (lane == 0 && publish_a) ts[t] = cs_pack(CS_FLAG_A, epoch, own);
-    unsigned long long excl = 0;
-    long long j = (long long)t - 1;
-    for (;;) {
-        const long long idx = j - lane;
-        bool done = false;
-        for (;;) {
-            unsigned flag = 2u; /* tiles before the first one: prefix 0 */
-            unsigned long long val = 0ull;
-            if (idx >= 0) {
-                const unsigned long long s = ts[idx];
-                const bool cur = ((s >> CS_VALUE_BITS) & CS_EPOCH_MASK) == (epoch & CS_EPOCH_MASK);
-                flag = cur ? (unsigned)(s >> 62) : 0u;
-                val = s & CS_VALUE_MASK;
-            }
-            const unsigned pm = __ballot_sync(0xffffffffu, flag == 2u);
-            const unsigned em = __ballot_sync(0xffffffffu, flag == 0u);
-            const unsigned upto = pm ? (0xffffffffu >> (32 - __ffs((int)pm))) : 0xffffffffu; /* lanes 0..first P */
-            if ((em & upto) == 0u) {
-                unsigned long long c = ((upto >> lane) & 1u) ? val : 0ull;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-                excl += c;
-                done = pm != 0u;
-                break;
-            }
-        }
-        if (done) break;
-        j -= 32;
-    }
-    if (lane == 0 && publish_p) ts[t] = cs_pack(CS_FLAG_P, epoch, excl + own);
-    return excl;
-}
-
 struct EfParams {
     const int16_t *zz; /* [Y blocks | Cb blocks | Cr blocks][64] */
     long long coff1, coff2;
@@ -212,7 +153,7 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k35_entropy(const EfParams q
 
     /* ---- 3. chained scan #1: global bit offset of the chunk ---- */
     if (wid == NW - 1) {
-        const unsigned long long g = cs_lookback(q.bit_state, (unsigned long long)chunk, q.epoch, total, lane, true, true);
+        const unsigned long long g = cs_lookback<16>(q.bit_state, (unsigned long long)chunk, q.epoch, total, lane, true, true);
         if (lane == 0) sG0 = g;
     }
     __syncthreads();
@@ -310,7 +251,7 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k35_entropy(const EfParams q
              * chunk only learns its total at the end and publishes the prefix then. */
             if (wid == NW - 1) {
                 const unsigned long long e =
-                    cs_lookback(q.ff_state, (unsigned long long)chunk, q.epoch, batch_ff, lane, single, single);
+                    cs_lookback<16>(q.ff_state, (unsigned long long)chunk, q.epoch, batch_ff, lane, single, single);
                 if (lane == 0) sFF = e;
             }
             __syncthreads();

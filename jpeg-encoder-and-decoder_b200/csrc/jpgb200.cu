@@ -5,12 +5,11 @@
  *
  * Launch sequence of one encode (one stream, no host synchronisation in between):
  *   K1 k1_transform   pixels -> int16 zig-zag coefficients           (HBM-bound, 9 B/px)
- *   K3 k3_block_bits  per-block code length, per-chunk offsets + totals
- *   K4 k4_scan_chunks device-wide exclusive scan of chunk totals (uint64); clears the few
- *                     words K5 ORs into and K6's scan state
+ *   K3 k3_block_bits  per-block code length, per-chunk offsets + totals, and the device-wide
+ *                     exclusive prefix sum of the chunk totals (single-pass chained scan)
  *   K5 k5_pack        every block writes its codes at its global bit offset (chunk streams
  *                     assembled in shared memory, copied out coalesced)
- *   K6 k6_stuff       0xFF00 stuffing by a second length/offset scan (single pass, chained),
+ *   K6 k6_count / k6_scatter  0xFF00 stuffing by a second length/offset scan (two-level sums),
  *                     JFIF header, EOI and length word
  * There is no CPU arithmetic path in this library.
  */
@@ -33,9 +32,9 @@
 
 using namespace jpgb200;
 
-enum { KI_K1 = 0, KI_K35, KI_K3, KI_K4, KI_K5, KI_K6 };
+enum { KI_K1 = 0, KI_K35, KI_K3, KI_K5, KI_K6COUNT, KI_K6SCATTER };
 static const char *kKernelNames[JPGB200_NUM_KERNELS] = {"k1_transform", "k35_entropy", "k3_block_bits",
-                                                        "k4_scan_chunks", "k5_pack", "k6_stuff"};
+                                                        "k5_pack",      "k6_count",    "k6_scatter"};
 
 struct EvPair {
     int k;
@@ -58,6 +57,8 @@ struct jpgb200_ctx {
     uint32_t *d_local_off;
     size_t local_cap;
     uint32_t *d_cta_bits;
+    uint32_t *d_super;   /* [n_super_bits | n_super_ff] two-level sums, cleared by K1 */
+    size_t n_super_bits, n_super_ff;
     unsigned long long *d_cta_base;
     size_t cta_cap;
     uint32_t *d_ubuf;
@@ -339,7 +340,7 @@ extern "C" void jpgb200_destroy(jpgb200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {ctx->d_huff,     ctx->d_hbits, ctx->d_scan_order, ctx->d_planes[0], ctx->d_planes[1], ctx->d_zz,   ctx->d_local_off,
-                    ctx->d_cta_bits, ctx->d_cta_base,   ctx->d_ubuf,      ctx->d_tile_ff,   ctx->d_tile_base,
+                    ctx->d_cta_bits, ctx->d_super, ctx->d_cta_base,   ctx->d_ubuf,      ctx->d_tile_ff,   ctx->d_tile_base,
                     ctx->d_state,    ctx->d_bit_state, ctx->d_ff_state, ctx->d_header,     ctx->d_out[0],    ctx->d_out[1],    ctx->d_len,  ctx->d_dc,
                     ctx->d_tile_sum, ctx->d_freq};
     for (void *p : ptrs)
@@ -568,6 +569,21 @@ static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_
         ctx->tile_bytes = c2;
         ctx->tile_cap = nt;
     }
+    {
+        const size_t nsb = nc / 64 + 2, nsf = ctx->tile_cap / 64 + 2;
+        if (!ctx->d_super || ctx->n_super_bits < nsb || ctx->n_super_ff < nsf) {
+            if (ctx->d_super) {
+                CK(cudaStreamSynchronize(ctx->stream));
+                CK(cudaFree(ctx->d_super));
+                ctx->d_super = NULL;
+            }
+            size_t c3 = 0;
+            if ((rc = grow(ctx, &ctx->d_super, &c3, (nsb + nsf) * 4))) return rc;
+            CK(cudaMemsetAsync(ctx->d_super, 0, c3, ctx->stream));
+            ctx->n_super_bits = nsb;
+            ctx->n_super_ff = nsf;
+        }
+    }
     return JPGB200_OK;
 }
 
@@ -615,6 +631,8 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
     p.H = h;
     p.BW = w / 8;
     p.has_halo = has_halo;
+    p.clear = ctx->d_super; /* K3 and K6 accumulate their two-level sums into it */
+    p.clear_n = (int)(ctx->n_super_bits + ctx->n_super_ff);
     memcpy(p.mul, ctx->mul, sizeof p.mul);
     memcpy(p.oob, ctx->oob, 24);
     p.tiles_per_row = (p.BW + K1_TILE_BLOCKS - 1) / K1_TILE_BLOCKS;
@@ -658,15 +676,20 @@ static void fill_ec(jpgb200_ctx *ctx, EcParams &e, const int16_t *zz, const long
     e.is_last_band = 1;
     e.local_off = ctx->d_local_off;
     e.cta_bits = ctx->d_cta_bits;
-    e.cta_base = ctx->d_cta_base;
+    e.super_bits = ctx->d_super;
     e.bit_base = 0;
     e.ubuf = ctx->d_ubuf;
     e.st = ctx->d_state;
+    e.n_chunks = n_chunks(n);
+    e.ubuf_cap_bytes = (unsigned long long)ctx->ubuf_cap;
+    e.tile_bytes = K6_TILE;
 }
 
 /* K3 + K4: bit lengths and their device-wide exclusive scan */
-static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3], const int *pred = NULL)
+static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3], const int *pred = NULL,
+                       bool clear_supers = false)
 {
+    if (clear_supers) CK(cudaMemsetAsync(ctx->d_super, 0, (ctx->n_super_bits + ctx->n_super_ff) * 4, ctx->stream));
     EcParams e;
     fill_ec(ctx, e, zz, n);
     if (pred)
@@ -680,12 +703,6 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
             k3_block_bits<1><<<nc, EcCfg<1>::NT, 0, ctx->stream>>>(e, ctx->d_hbits);
     }
     CK(cudaGetLastError());
-    {
-        LaunchScope ls(ctx, KI_K4);
-        k4_scan_chunks<<<1, SCAN_THREADS, 0, ctx->stream>>>(ctx->d_cta_bits, ctx->d_cta_base, (long long)nc, ctx->d_state,
-                                                           K6_TILE, (unsigned long long)ctx->ubuf_cap, 0ull);
-    }
-    CK(cudaGetLastError());
     ctx->have_bits = true;
     return JPGB200_OK;
 }
@@ -697,7 +714,7 @@ static int launch_pack(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     EcParams e;
     fill_ec(ctx, e, zz, n);
     const unsigned nc = (unsigned)n_chunks(n);
-    const unsigned pgrid = (unsigned)ctx->sm_count * 4;
+    const unsigned pgrid = (unsigned)ctx->sm_count * 8;
     {
         LaunchScope ls(ctx, KI_K5);
         if (ratio == 0)
@@ -706,15 +723,17 @@ static int launch_pack(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
             k5_pack<1><<<nc, EcCfg<1>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
     }
     CK(cudaGetLastError());
-    if (((ctx->epoch + 1) & ((1ull << K6_EPOCH_BITS) - 1ull)) == 0ull) { /* epoch wrap: forget old states */
-        CK(cudaMemsetAsync(ctx->d_tile_base, 0, ctx->tile_bytes, ctx->stream));
-        ctx->epoch++;
-    }
     {
-        LaunchScope ls(ctx, KI_K6);
-        k6_stuff<<<pgrid, K6_THREADS, 0, ctx->stream>>>(reinterpret_cast<uint4 *>(ctx->d_ubuf), ctx->d_state,
-                                                        ctx->d_tile_base, ctx->d_header, ctx->hdr_len, d_out,
-                                                        (unsigned long long)cap, len_out, ++ctx->epoch, -1ll, 1);
+        LaunchScope ls(ctx, KI_K6COUNT);
+        k6_count<<<pgrid, K6_THREADS, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(ctx->d_ubuf), ctx->d_state,
+                                                        ctx->d_tile_ff, ctx->d_super + ctx->n_super_bits, -1ll);
+    }
+    CK(cudaGetLastError());
+    {
+        LaunchScope ls(ctx, KI_K6SCATTER);
+        k6_scatter<<<pgrid, K6_THREADS, 0, ctx->stream>>>(reinterpret_cast<uint4 *>(ctx->d_ubuf), ctx->d_state,
+                                                          ctx->d_tile_ff, ctx->d_super + ctx->n_super_bits, ctx->d_header,
+                                                          ctx->hdr_len, d_out, (unsigned long long)cap, len_out, -1ll, 1);
     }
     CK(cudaGetLastError());
     return JPGB200_OK;
@@ -996,10 +1015,13 @@ extern "C" int jpgb200_band_bits(jpgb200_ctx *ctx, const int pred_dc[3], unsigne
     for (int c = 0; c < 3; c++) ctx->band_pred[c] = pred_dc[c];
     int rc = launch_bits(ctx, ctx->d_zz, ctx->band_ratio, ctx->band_n, ctx->band_pred);
     if (rc) return rc;
-    EncState st;
-    CK(cudaMemcpyAsync(&st, ctx->d_state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t ns = (size_t)(n_chunks(ctx->band_n) / 64 + 1);
+    std::vector<uint32_t> sup(ns);
+    CK(cudaMemcpyAsync(sup.data(), ctx->d_super, ns * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
-    if (st.error) return JPGB200_ERR_OUT_TOO_SMALL;
+    EncState st;
+    st.total_bits = 0;
+    for (size_t i = 0; i < ns; i++) st.total_bits += sup[i];
     ctx->band_bits = st.total_bits;
     *band_bits = st.total_bits;
     return JPGB200_OK;
@@ -1053,15 +1075,19 @@ extern "C" int jpgb200_band_finish(jpgb200_ctx *ctx, int carry_byte, uint8_t *d_
         k_or_first_byte<<<1, 1, 0, ctx->stream>>>(ctx->d_ubuf, (uint32_t)carry_byte);
         ctx->launch_total++;
     }
-    if (((ctx->epoch + 1) & ((1ull << K6_EPOCH_BITS) - 1ull)) == 0ull) {
-        CK(cudaMemsetAsync(ctx->d_tile_base, 0, ctx->tile_bytes, ctx->stream));
-        ctx->epoch++;
-    }
+    /* K1 cleared the two-level sums at band_transform; K3 used the bit half, this is the 0xFF half */
     {
-        LaunchScope ls(ctx, KI_K6);
-        k6_stuff<<<(unsigned)ctx->sm_count * 4, K6_THREADS, 0, ctx->stream>>>(
-            reinterpret_cast<uint4 *>(ctx->d_ubuf), ctx->d_state, ctx->d_tile_base, ctx->d_header, 0, d_segment,
-            (unsigned long long)cap, ctx->d_len, ++ctx->epoch, (long long)own, 0);
+        LaunchScope ls(ctx, KI_K6COUNT);
+        k6_count<<<(unsigned)ctx->sm_count * 8, K6_THREADS, 0, ctx->stream>>>(
+            reinterpret_cast<const uint4 *>(ctx->d_ubuf), ctx->d_state, ctx->d_tile_ff, ctx->d_super + ctx->n_super_bits,
+            (long long)own);
+    }
+    CK(cudaGetLastError());
+    {
+        LaunchScope ls(ctx, KI_K6SCATTER);
+        k6_scatter<<<(unsigned)ctx->sm_count * 8, K6_THREADS, 0, ctx->stream>>>(
+            reinterpret_cast<uint4 *>(ctx->d_ubuf), ctx->d_state, ctx->d_tile_ff, ctx->d_super + ctx->n_super_bits,
+            ctx->d_header, 0, d_segment, (unsigned long long)cap, ctx->d_len, (long long)own, 0);
     }
     CK(cudaGetLastError());
     /* the trailing partial byte belongs to the next band: clear its line for the next encode's K5 */
@@ -1164,16 +1190,17 @@ extern "C" int jpgb200_block_bit_offsets(jpgb200_ctx *ctx, unsigned long long *o
     CK(cudaSetDevice(ctx->device));
     const int bpm = ctx->ratio ? 4 : 3;
     const long long nb = ctx->n[1] * bpm, nc = n_chunks(ctx->n);
-    std::vector<uint32_t> loc((size_t)nb);
-    std::vector<unsigned long long> base((size_t)nc);
-    EncState st;
+    std::vector<uint32_t> loc((size_t)nb), cbits((size_t)nc);
     CK(cudaMemcpyAsync(loc.data(), ctx->d_local_off, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(base.data(), ctx->d_cta_base, (size_t)nc * 8, cudaMemcpyDeviceToHost, ctx->stream));
-    CK(cudaMemcpyAsync(&st, ctx->d_state, sizeof st, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(cbits.data(), ctx->d_cta_bits, (size_t)nc * 4, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
+    /* tap only: the device-side prefix of the chunk totals is computed inside K5 */
+    std::vector<unsigned long long> base((size_t)nc + 1);
+    base[0] = 0;
+    for (long long c = 0; c < nc; c++) base[(size_t)c + 1] = base[(size_t)c] + cbits[(size_t)c];
     const long long per = (long long)EC_MCUS * bpm;
     for (long long s = 0; s < nb; s++) offsets[s] = base[(size_t)(s / per)] + loc[(size_t)s];
-    offsets[nb] = st.total_bits;
+    offsets[nb] = base[(size_t)nc];
     return JPGB200_OK;
 }
 
@@ -1376,7 +1403,7 @@ extern "C" int jpgb200_encode_coefficients(jpgb200_ctx *ctx, const int16_t *zz, 
     memcpy(ctx->n, n, sizeof n);
     CK(cudaMemcpyAsync(ctx->d_zz, zz, (size_t)(n[0] + n[1] + n[2]) * 128, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->legacy_entropy) {
-        if ((rc = launch_bits(ctx, ctx->d_zz, ratio, n))) return rc;
+        if ((rc = launch_bits(ctx, ctx->d_zz, ratio, n, NULL, true))) return rc;
         if ((rc = launch_pack(ctx, ctx->d_zz, ratio, n, ctx->d_out[0], cap, ctx->d_len))) return rc;
     } else {
         if ((rc = launch_fused(ctx, ctx->d_zz, ratio, n, ctx->d_out[0], cap, ctx->d_len))) return rc;

@@ -54,6 +54,8 @@ struct K1Params {
     int W, H, BW;           /* pixels, pixels, W/8 */
     int has_halo;           /* row -1 of the band is valid memory (MCU-row partition) */
     int tiles_per_row, n_frames;
+    uint32_t *clear; /* small scratch array the entropy stage accumulates into: cleared here, for free */
+    int clear_n;
     float mul[2][64];       /* quantiser multipliers [lum|chr][v*8+u] */
     uint8_t oob[24];        /* r[8] g[8] b[8] */
 };
@@ -233,6 +235,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform(const K1Params p)
     const uint8_t *pb = p.b + (long long)frame * p.plane_stride;
 
     sMul[tid >> 6][tid & 63] = p.mul[tid >> 6][tid & 63];
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+        for (int i = tid; i < p.clear_n; i += K1_THREADS) p.clear[i] = 0u;
     {
         const int y = tid >> 4, seg = tid & 15;
         uint2 vr[2], vg[2], vb[2];
@@ -357,6 +361,8 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform_tma(const K1Params
     const int tid = threadIdx.x, lane = tid & 31;
 
     S.sMul[tid >> 6][tid & 63] = p.mul[tid >> 6][tid & 63];
+    if (blockIdx.x == 0)
+        for (int i = tid; i < p.clear_n; i += K1_THREADS) p.clear[i] = 0u;
     if (tid == 0) {
 #pragma unroll
         for (int s = 0; s < K1_STAGES; s++) mbar_init(&S.full[s], 1);

@@ -1,12 +1,11 @@
 /*
  * K6 -- 0xFF -> 0xFF00 byte stuffing (T.81 F.1.2.3) by a second length/offset scan:
- *   k6_stuff: one persistent kernel.  Per 4 KB tile of the un-stuffed stream: count 0xFF
- *             bytes, obtain the number of 0xFF bytes in all earlier tiles by a single-pass
- *             chained scan (decoupled look-back), then write the tile at (tile offset +
- *             #0xFF before it) inserting the zero bytes; output is staged in shared memory
- *             at the same 16-byte phase as the destination so the copy-out is 16-byte
- *             vectorised and coalesced.  Tile 0 also writes the JFIF header, the last tile
- *             the EOI marker and the final length.
+ *   k6_count   : 0xFF bytes per 4 KB tile of the un-stuffed stream, and per 64 tiles
+ *   k6_scatter : a tile's insertion offset = sum of the counts before it (at most
+ *                n_tiles/64 + 63 numbers, added up by the CTA itself -- no scan kernel, no
+ *                serial chain between CTAs); then the stuffed bytes go out.
+ * (A single-pass chained scan was measured first: with one wave of tiles per frame its
+ * look-back latency dominated -- 40 us per 8K frame against 25 us for this form.)
  * The reference emits no byte stream; the oracle for these bytes is
  * oracle/jpgb200_oracle.c (bw_byte), checked by PIL/OpenCV decodes in tests/.
  */
@@ -14,12 +13,13 @@
 #define JPGB200_STUFFING_CUH
 
 #include "entropy.cuh"
+#include "entropy_fused.cuh"
 
 namespace jpgb200 {
 
 #define K6_THREADS 256
-#define K6_ITEMS 4
-#define K6_TILE (K6_THREADS * 16 * K6_ITEMS) /* 16 KB of un-stuffed stream per tile: 64 contiguous bytes per thread */
+#define K6_TILE 4096     /* bytes of un-stuffed stream per tile: 16 per thread */
+#define K6_SUPER_SHIFT 6 /* tiles per super-tile = 64 */
 
 /* number of 0xFF bytes among the first `nvalid` (0..16) bytes of v */
 __device__ __forceinline__ int count_ff16(const uint4 v, int nvalid)
@@ -36,73 +36,52 @@ __device__ __forceinline__ int count_ff16(const uint4 v, int nvalid)
     return c;
 }
 
-/* single-pass chained scan over tiles ("decoupled look-back"): tile_state[t] holds, in one
- * 64-bit word, a 2-bit flag, the encode's epoch and a count: A = this tile's own 0xFF count is
- * known, P = the inclusive prefix up to and including this tile is known.  States of earlier
- * encodes carry another epoch and read as "empty", so nothing has to be cleared.  Tiles are
- * handed out by an atomic ticket, so every predecessor of a waiting tile is already running on
- * a resident CTA and the wait terminates.  Warp 0 looks back 32 tiles per step. */
-#define K6_FLAG_A 1ull
-#define K6_FLAG_P 2ull
-#define K6_VALUE_BITS 40
-#define K6_EPOCH_BITS 22
-#define K6_VALUE_MASK ((1ull << K6_VALUE_BITS) - 1ull)
-#define K6_EPOCH_MASK ((1ull << K6_EPOCH_BITS) - 1ull)
-
-__device__ __forceinline__ unsigned long long k6_pack(unsigned long long flag, unsigned long long epoch,
-                                                      unsigned long long value)
-{
-    return (flag << 62) | ((epoch & K6_EPOCH_MASK) << K6_VALUE_BITS) | (value & K6_VALUE_MASK);
-}
-
-/* executed by all 32 lanes of warp 0; returns the number of 0xFF bytes in tiles [0, t) */
-__device__ __forceinline__ unsigned long long k6_lookback(volatile unsigned long long *ts, unsigned long long t,
-                                                          unsigned long long epoch, uint32_t own, int lane)
-{
-    if (lane == 0) ts[t] = k6_pack(t == 0 ? K6_FLAG_P : K6_FLAG_A, epoch, own);
-    unsigned long long excl = 0;
-    if (t == 0) return 0ull;
-    long long j = (long long)t - 1;
-    for (;;) {
-        const long long idx = j - lane;
-        bool done = false;
-        for (;;) {
-            unsigned flag = 2u; /* tiles before the first one: prefix 0 */
-            unsigned long long val = 0ull;
-            if (idx >= 0) {
-                const unsigned long long s = ts[idx];
-                const bool cur = ((s >> K6_VALUE_BITS) & K6_EPOCH_MASK) == (epoch & K6_EPOCH_MASK);
-                flag = cur ? (unsigned)(s >> 62) : 0u;
-                val = s & K6_VALUE_MASK;
-            }
-            const unsigned pm = __ballot_sync(0xffffffffu, flag == 2u);
-            const unsigned em = __ballot_sync(0xffffffffu, flag == 0u);
-            const unsigned upto = pm ? (0xffffffffu >> (32 - __ffs((int)pm))) : 0xffffffffu; /* lanes 0..first P */
-            if ((em & upto) == 0u) {
-                unsigned long long c = ((upto >> lane) & 1u) ? val : 0ull;
-#pragma unroll
-                for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
-                excl += c;
-                done = pm != 0u;
-                break;
-            }
-        }
-        if (done) break;
-        j -= 32;
-    }
-    if (lane == 0) ts[t] = k6_pack(K6_FLAG_P, epoch, excl + own);
-    return excl;
-}
-
-__global__ void __launch_bounds__(K6_THREADS) k6_stuff(uint4 *ubuf, EncState *st, unsigned long long *tile_state,
-                                                       const uint8_t *header, int header_len, uint8_t *out,
-                                                       unsigned long long cap, unsigned long long *len_out,
-                                                       unsigned long long epoch, long long nbytes_override,
-                                                       int write_eoi)
+/* K6a: 0xFF bytes per tile, and (atomically) per 64 tiles -- the two-level sums from which
+ * K6b derives every tile's insertion offset without a scan kernel or a serial chain */
+__global__ void __launch_bounds__(K6_THREADS) k6_count(const uint4 *ubuf, const EncState *st, uint32_t *tile_ff,
+                                                       uint32_t *super_ff, long long nbytes_override)
 {
     __shared__ uint32_t sWarp[K6_THREADS / 32];
+    if (st->error) return;
+    const unsigned long long nbytes = nbytes_override >= 0 ? (unsigned long long)nbytes_override : st->nbytes;
+    const unsigned long long ntiles = (nbytes + K6_TILE - 1) / K6_TILE;
+    const int tid = threadIdx.x;
+    for (unsigned long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const unsigned long long b0 = t * K6_TILE + (unsigned long long)tid * 16;
+        int c = 0;
+        if (b0 < nbytes) {
+            const unsigned long long left = nbytes - b0;
+            c = count_ff16(ubuf[b0 >> 4], left >= 16 ? 16 : (int)left);
+        }
+#pragma unroll
+        for (int d = 16; d > 0; d >>= 1) c += __shfl_xor_sync(0xffffffffu, c, d);
+        if ((tid & 31) == 0) sWarp[tid >> 5] = (uint32_t)c;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t total = 0;
+#pragma unroll
+            for (int i = 0; i < K6_THREADS / 32; i++) total += sWarp[i];
+            tile_ff[t] = total;
+            if (total) atomicAdd(&super_ff[t >> K6_SUPER_SHIFT], total);
+        }
+        __syncthreads();
+    }
+}
+
+/* K6b: every tile writes its bytes at (tile offset + #0xFF before it), inserting the zero
+ * bytes; output is staged in shared memory at the same 16-byte phase as the destination so the
+ * copy-out is 16-byte vectorised and coalesced.  Tile 0 also writes the JFIF header, the last
+ * tile the EOI marker and the length word.  Every line of the un-stuffed buffer is cleared
+ * after it has been read (K5's all-zero invariant). */
+__global__ void __launch_bounds__(K6_THREADS) k6_scatter(uint4 *ubuf, EncState *st, const uint32_t *tile_ff,
+                                                         const uint32_t *super_ff, const uint8_t *header,
+                                                         int header_len, uint8_t *out, unsigned long long cap,
+                                                         unsigned long long *len_out, long long nbytes_override,
+                                                         int write_eoi)
+{
+    __shared__ uint32_t sWarp[K6_THREADS / 32];
+    __shared__ unsigned long long sPart[K6_THREADS / 32];
     __shared__ __align__(16) uint8_t sT[2 * K6_TILE + 32];
-    __shared__ unsigned long long sTicket, sExcl;
     const int tid = threadIdx.x;
     if (st->error) {
         if (blockIdx.x == 0 && tid == 0 && len_out) *len_out = 0ull;
@@ -112,37 +91,32 @@ __global__ void __launch_bounds__(K6_THREADS) k6_stuff(uint4 *ubuf, EncState *st
     const unsigned long long nbytes = nbytes_override >= 0 ? (unsigned long long)nbytes_override : st->nbytes;
     const unsigned long long ntiles = (nbytes + K6_TILE - 1) / K6_TILE;
     const unsigned long long trailer = write_eoi ? 2ull : 0ull;
-    while (true) {
-        if (tid == 0) sTicket = atomicAdd(&st->ticket, 1ull);
-        __syncthreads();
-        const unsigned long long t = sTicket;
-        if (t >= ntiles) break;
-        const unsigned long long b0 = t * K6_TILE + (unsigned long long)tid * (16 * K6_ITEMS);
-        int nvalid[K6_ITEMS];
-        uint4 v[K6_ITEMS];
-        int c = 0;
-#pragma unroll
-        for (int k = 0; k < K6_ITEMS; k++) {
-            const unsigned long long bk = b0 + 16ull * k;
-            nvalid[k] = 0;
-            v[k] = make_uint4(0, 0, 0, 0);
-            if (bk < nbytes) {
-                const unsigned long long left = nbytes - bk;
-                nvalid[k] = left >= 16 ? 16 : (int)left;
-                v[k] = ubuf[bk >> 4];
-                ubuf[bk >> 4] = make_uint4(0, 0, 0, 0); /* leave the buffer clean for the next encode's K5 */
-            }
+    for (unsigned long long t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const unsigned long long b0 = t * K6_TILE + (unsigned long long)tid * 16;
+        int nvalid = 0;
+        uint4 v = make_uint4(0, 0, 0, 0);
+        if (b0 < nbytes) {
+            const unsigned long long left = nbytes - b0;
+            nvalid = left >= 16 ? 16 : (int)left;
+            v = ubuf[b0 >> 4];
+            ubuf[b0 >> 4] = make_uint4(0, 0, 0, 0);
+        }
+        /* 0xFF bytes in all earlier tiles, from the two-level sums */
+        unsigned long long part = 0ull;
+        {
+            const unsigned long long sup = t >> K6_SUPER_SHIFT;
+            for (unsigned long long i = tid; i < sup; i += K6_THREADS) part += super_ff[i];
+            for (unsigned long long i = (sup << K6_SUPER_SHIFT) + tid; i < t; i += K6_THREADS) part += tile_ff[i];
         }
 #pragma unroll
-        for (int k = 0; k < K6_ITEMS; k++) c += count_ff16(v[k], nvalid[k]);
+        for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+        if ((tid & 31) == 0) sPart[tid >> 5] = part;
+        const int c = count_ff16(v, nvalid);
         uint32_t tile_ffs;
-        const uint32_t ff_before = cta_exclusive_scan<K6_THREADS>((uint32_t)c, sWarp, tid, tile_ffs);
-        if (tid < 32) {
-            const unsigned long long e = k6_lookback(tile_state, t, epoch, tile_ffs, tid);
-            if (tid == 0) sExcl = e;
-        }
-        __syncthreads();
-        const unsigned long long excl = sExcl;
+        const uint32_t ff_before = cta_exclusive_scan<K6_THREADS>((uint32_t)c, sWarp, tid, tile_ffs); /* has a barrier */
+        unsigned long long excl = 0ull;
+#pragma unroll
+        for (int i = 0; i < K6_THREADS / 32; i++) excl += sPart[i];
         /* destination of the tile's first byte, and its phase inside a 16-byte line */
         const unsigned long long g0 = (unsigned long long)header_len + t * K6_TILE + excl;
         const unsigned long long tile_in = (nbytes - t * K6_TILE) >= K6_TILE ? K6_TILE : (nbytes - t * K6_TILE);
@@ -151,17 +125,14 @@ __global__ void __launch_bounds__(K6_THREADS) k6_stuff(uint4 *ubuf, EncState *st
         if (fits) {
             const unsigned long long gaddr = (unsigned long long)(uintptr_t)out + g0;
             const int phase = (int)(gaddr & 15ull);
-            int pos = phase + tid * (16 * K6_ITEMS) + (int)ff_before;
+            int pos = phase + tid * 16 + (int)ff_before;
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-            for (int k = 0; k < K6_ITEMS; k++) {
-                const uint32_t w[4] = {v[k].x, v[k].y, v[k].z, v[k].w};
-#pragma unroll
-                for (int i = 0; i < 16; i++) {
-                    if (i < nvalid[k]) {
-                        const uint8_t byte = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
-                        sT[pos++] = byte;
-                        if (byte == 0xFF) sT[pos++] = 0x00;
-                    }
+            for (int i = 0; i < 16; i++) {
+                if (i < nvalid) {
+                    const uint8_t byte = (uint8_t)(w[i >> 2] >> (8 * (i & 3)));
+                    sT[pos++] = byte;
+                    if (byte == 0xFF) sT[pos++] = 0x00;
                 }
             }
             __syncthreads();
