@@ -48,7 +48,6 @@ struct EncState {
     int pad;
     unsigned long long ticket;     /* K6 tile dispenser                                 */
     unsigned long long ticket35;   /* K35 chunk dispenser (reset by K35 itself)         */
-    unsigned long long ticket3;    /* K3 chunk dispenser (reset by K3 itself)           */
 };
 
 struct EcParams {
@@ -56,23 +55,13 @@ struct EcParams {
     long long coff1, coff2; /* first Cb / Cr block inside zz */
     long long n_mcu;
     int dc_pred[3];        /* predictor of the first block per component (0 for a whole image) */
-    int is_last_band;      /* pad the final byte after the last block                         */
-    uint32_t *local_off;   /* [n_mcu*BPM] bit offset of each block inside its chunk            */
-    uint32_t *cta_bits;    /* [n_chunks] bits per chunk                                        */
-    uint32_t *super_bits;  /* [ceil(n_chunks/EC_SUPER)] bits per group of EC_SUPER chunks (atomics)   */
-    unsigned long long bit_base;        /* global bit offset of this band (multi-GPU)         */
-    uint32_t *ubuf;        /* un-stuffed big-endian bit stream, all-zero on entry (K5)         */
-    EncState *st;          /* totals and error flag, written by K5's last chunk                */
-    long long n_chunks;
-    unsigned long long ubuf_cap_bytes;
-    int tile_bytes;                     /* K6 tile size, for EncState::n_tiles                 */
 };
 
 template <int RATIO>
 struct EcCfg {
     static const int BPM = (RATIO == 0) ? 3 : 4;
     static const int NT = EC_MCUS * BPM;
-    static const int STAGE_WORDS = (RATIO == 0) ? 3072 : 2048; /* K5 staging buffer */
+    static const int STAGE_WORDS = (RATIO == 0) ? 3072 : 1664; /* chunk stream staging (static smem <= 48 KB) */
 };
 
 /* Row (= thread) <-> block mapping inside a chunk.  Rows are grouped by COMPONENT, not by
@@ -413,113 +402,93 @@ __device__ __forceinline__ unsigned long long cs_lookback(volatile unsigned long
     return excl;
 }
 
-/* ---- K3: bit length of every block, exclusive offsets inside the chunk, chunk total; the
- * device-wide exclusive prefix sum of bit offsets is finished by K5 from two-level sums:
- * per-chunk totals and (atomically accumulated) totals per 64 chunks ------------------------- */
+/* ---- KE (k_encode_chunks): per-block bit lengths AND the bit pack, chunk-locally -------------
+ * One CTA per chunk of EC_MCUS MCUs, coefficients read from HBM once:
+ *   count pass  : bits per block (ec_count_block) -> CTA scan in scan order -> chunk total T
+ *   pack pass   : every block writes its codes at its offset inside the CHUNK's own stream
+ *                 (bit 0 = the chunk's first bit), assembled in shared memory and copied to the
+ *                 chunk's slot of a temporary buffer with coalesced stores -- a chunk owns its
+ *                 slot, so nothing in HBM is shared between CTAs
+ *   totals      : T per chunk and, atomically, per 64 chunks: the two-level sums from which KC
+ *                 derives every chunk's global bit offset (the device-wide exclusive prefix sum)
+ * A chunk whose stream exceeds the staging buffer clears its slot and packs straight into it
+ * (atomics on block-boundary words).  Slots need no initialisation between encodes. */
+struct KeParams {
+    const int16_t *zz;
+    long long coff1, coff2, n_mcu;
+    int dc_pred[3];
+    uint32_t *tmp;         /* [n_chunks][slot_words] chunk-local streams, big-endian words */
+    long long slot_words;
+    uint32_t *cta_bits;    /* [n_chunks] */
+    uint32_t *super_bits;  /* [n_chunks / 64 + 1], cleared by K1 */
+    uint32_t *local_off;   /* optional parity tap: [n_mcu*BPM] offset of every block in its chunk */
+};
+
 template <int RATIO>
-__global__ void __launch_bounds__(EcCfg<RATIO>::NT) k3_block_bits(const EcParams p, const HuffBits *hbits)
+__global__ void __launch_bounds__(EcCfg<RATIO>::NT) k_encode_chunks(const KeParams q, const HuffBits *hbits,
+                                                                    const HuffDev *huff)
 {
-    constexpr int BPM = EcCfg<RATIO>::BPM, NT = EcCfg<RATIO>::NT;
+    constexpr int BPM = EcCfg<RATIO>::BPM, NT = EcCfg<RATIO>::NT, STAGE = EcCfg<RATIO>::STAGE_WORDS;
     __shared__ uint4 sC[NT][EC_ROW_CHUNKS];
     __shared__ __align__(16) HuffBits sB;
-    __shared__ uint32_t sBits[NT];
+    __shared__ __align__(16) HuffDev sH;
+    __shared__ uint32_t sOff[NT];
     __shared__ uint32_t sWarp[NT / 32];
+    __shared__ __align__(16) uint32_t sS[STAGE];
     const int tid = threadIdx.x;
     const long long chunk = blockIdx.x;
     const long long m0 = chunk * EC_MCUS;
 
+    EcParams p;
+    p.zz = q.zz;
+    p.coff1 = q.coff1;
+    p.coff2 = q.coff2;
+    p.n_mcu = q.n_mcu;
+    p.dc_pred[0] = q.dc_pred[0];
+    p.dc_pred[1] = q.dc_pred[1];
+    p.dc_pred[2] = q.dc_pred[2];
+
     ec_fill<RATIO>(sC, p, m0, tid);
     ec_load_table(&sB, hbits, tid);
-    const EcMap<RATIO> mp(p, m0, tid);
-    cp_async_wait_all();
-    __syncthreads();
-
-    uint32_t nbits = 0;
-    if (mp.valid) {
-        const int pred = ec_dc_pred<RATIO>(sC, p, m0, tid, mp);
-        const int diff = (int)(short)(sC[tid][0].x & 0xffffu) - pred;
-        nbits = ec_count_block(sC[tid], diff, sB.ac[mp.comp ? 1 : 0], sB.dc[mp.comp ? 1 : 0]);
-    }
-    sBits[mp.s_local] = nbits; /* scan (MCU-interleaved) order */
-    __syncthreads();
-    uint32_t total;
-    const uint32_t off = cta_exclusive_scan<NT>(sBits[tid], sWarp, tid, total);
-    if (m0 * BPM + tid < p.n_mcu * BPM) p.local_off[m0 * BPM + tid] = off;
-    if (tid == 0) {
-        /* two-level sums instead of a scan kernel: K5 adds up at most n_chunks/64 + 63 numbers */
-        p.cta_bits[chunk] = total;
-        atomicAdd(&p.super_bits[chunk >> EC_SUPER_SHIFT], total);
-    }
-}
-
-/* ---- K5: pack every block's codes at its global bit offset -------------------------------
- * Invariant: the un-stuffed buffer is all-zero on entry -- it is cleared once at allocation
- * and K6 zeroes every 16-byte line right after consuming it.
- * The chunk's stream is assembled in shared memory (at the same bit phase inside a 32-bit
- * word as its destination) and copied out with coalesced stores; only the chunk's first and
- * last word, which neighbouring chunks also write, are OR-ed into HBM.  A chunk too long for
- * the staging buffer packs straight into HBM with atomics on block-boundary words. */
-template <int RATIO>
-__global__ void __launch_bounds__(EcCfg<RATIO>::NT) k5_pack(const EcParams p, const HuffDev *huff)
-{
-    constexpr int BPM = EcCfg<RATIO>::BPM, NT = EcCfg<RATIO>::NT, STAGE = EcCfg<RATIO>::STAGE_WORDS;
-    __shared__ uint4 sC[NT][EC_ROW_CHUNKS];
-    __shared__ __align__(16) HuffDev sH;
-    __shared__ uint32_t sS[STAGE];
-    __shared__ unsigned long long sPart[NT / 32];
-    const int tid = threadIdx.x;
-    const long long m0 = (long long)blockIdx.x * EC_MCUS;
-
-    /* all global reads of the prologue are issued back to back, none depends on another */
-    ec_fill<RATIO>(sC, p, m0, tid);
     ec_load_table(&sH, huff, tid);
     const EcMap<RATIO> mp(p, m0, tid);
-    const long long chunk = blockIdx.x;
-    uint32_t tbits = p.cta_bits[chunk];
-    const uint32_t my_off = mp.valid ? p.local_off[m0 * BPM + mp.s_local] : 0u;
-    /* exclusive prefix of the chunk totals = the chunk's global bit offset */
-    unsigned long long part = 0ull;
-    {
-        const long long sup = chunk >> EC_SUPER_SHIFT;
-        for (long long i = tid; i < sup; i += NT) part += p.super_bits[i];
-        for (long long i = (sup << EC_SUPER_SHIFT) + tid; i < chunk; i += NT) part += p.cta_bits[i];
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-    if ((tid & 31) == 0) sPart[tid >> 5] = part;
-    for (uint32_t i = tid; i < (uint32_t)STAGE; i += NT) sS[i] = 0u;
+    for (int i = tid; i < STAGE; i += NT) sS[i] = 0u;
     cp_async_wait_all();
     __syncthreads();
-    unsigned long long g0 = p.bit_base;
-#pragma unroll
-    for (int i = 0; i < NT / 32; i++) g0 += sPart[i];
-    const bool fits = ((g0 + tbits + 7ull) >> 3) + 64ull <= p.ubuf_cap_bytes; /* only trips on corrupted lengths */
 
-    const bool last_chunk = (m0 + EC_MCUS >= p.n_mcu);
-    if (last_chunk && tid == 0) {
-        /* totals for K6 and the host */
-        const unsigned long long all = g0 - p.bit_base + tbits;
-        EncState *st = p.st;
-        st->total_bits = fits ? all : 0ull;
-        st->nbytes = fits ? (all + 7) >> 3 : 0ull;
-        st->n_tiles = (st->nbytes + (unsigned long long)p.tile_bytes - 1) / (unsigned long long)p.tile_bytes;
-        st->total_ff = 0;
-        st->out_len = 0;
-        st->error = fits ? 0 : 1;
-        st->ticket = 0ull;
-    }
-    if (!fits) return;
-    if (last_chunk && p.is_last_band) tbits += (uint32_t)((8u - (uint32_t)((g0 + tbits) & 7ull)) & 7u); /* 1-padding */
-    const uint32_t b0 = (uint32_t)(g0 & 31ull);
-    const uint32_t nwords = (b0 + tbits + 31u) >> 5;
-    uint32_t *gw = p.ubuf + (g0 >> 5);
-    const bool staged = nwords <= (uint32_t)STAGE;
-
+    /* count pass */
+    uint32_t nbits = 0;
+    int diff = 0;
     if (mp.valid) {
         const int pred = ec_dc_pred<RATIO>(sC, p, m0, tid, mp);
-        const int diff = (int)(short)(sC[tid][0].x & 0xffffu) - pred;
-        const uint32_t loff = b0 + my_off;
-        const bool very_last = p.is_last_band && (m0 * BPM + mp.s_local == p.n_mcu * BPM - 1);
+        diff = (int)(short)(sC[tid][0].x & 0xffffu) - pred;
+        nbits = ec_count_block(sC[tid], diff, sB.ac[mp.comp ? 1 : 0], sB.dc[mp.comp ? 1 : 0]);
+    }
+    sOff[mp.s_local] = nbits; /* scan (MCU-interleaved) order */
+    __syncthreads();
+    uint32_t total;
+    {
+        const uint32_t ex = cta_exclusive_scan<NT>(sOff[tid], sWarp, tid, total);
+        __syncthreads();
+        sOff[tid] = ex;
+        if (q.local_off && m0 * BPM + tid < q.n_mcu * BPM) q.local_off[m0 * BPM + tid] = ex;
+    }
+    if (tid == 0) {
+        q.cta_bits[chunk] = total;
+        atomicAdd(&q.super_bits[chunk >> EC_SUPER_SHIFT], total);
+    }
+    __syncthreads();
+
+    /* pack pass */
+    const uint32_t nwords = (total + 31u) >> 5;
+    const bool staged = nwords <= (uint32_t)STAGE;
+    uint32_t *slot = q.tmp + chunk * q.slot_words;
+    if (!staged) {
+        for (uint32_t i = tid; i < nwords; i += NT) slot[i] = 0u;
+        __syncthreads();
+    }
+    if (mp.valid) {
+        const uint32_t loff = sOff[mp.s_local];
         if (staged) {
             PackSink<true> s;
             s.acc = 0;
@@ -527,33 +496,96 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k5_pack(const EcParams p, co
             s.wp = sS + (loff >> 5);
             s.first = true;
             ec_pack_block(sC[tid], diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
-            if (very_last) {
-                const int rem = s.nacc & 7; /* complete the final byte with 1-bits (T.81 F.1.2.3) */
-                if (rem) s.put((1u << (8 - rem)) - 1u, 8 - rem);
-            }
             s.finish();
         } else {
             PackSink<false> s;
             s.acc = 0;
             s.nacc = (int)(loff & 31u);
-            s.wp = gw + (loff >> 5);
+            s.wp = slot + (loff >> 5);
             s.first = true;
             ec_pack_block(sC[tid], diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
-            if (very_last) {
-                const int rem = s.nacc & 7;
-                if (rem) s.put((1u << (8 - rem)) - 1u, 8 - rem);
-            }
             s.finish();
         }
     }
     if (!staged) return;
     __syncthreads();
-    for (uint32_t i = tid; i < nwords; i += NT) {
-        const uint32_t v = sS[i];
-        if (i == 0 || i + 1 == nwords) {
-            if (v) atomicOr(gw + i, v);
+    for (uint32_t i = tid; i < nwords; i += NT) slot[i] = sS[i];
+}
+
+/* ---- KC (k_concat_chunks): place every chunk's stream at its global bit offset ---------------
+ * g0(chunk) = bit_base + sum of the totals of all earlier chunks, added up from the two-level
+ * sums (at most n_chunks/64 + 63 numbers per CTA: no scan kernel, no chain between CTAs).
+ * The chunk's words are funnel-shifted by g0 & 31 into the un-stuffed stream; only a chunk's
+ * first and last word, which its neighbours also write, are OR-ed (the stream buffer is
+ * all-zero on entry: K6 clears every line it consumes).  The last chunk completes the final
+ * byte with 1-bits (T.81 F.1.2.3) and publishes the totals. */
+struct KcParams {
+    const uint32_t *tmp;
+    long long slot_words, n_chunks;
+    const uint32_t *cta_bits, *super_bits;
+    unsigned long long bit_base; /* global bit offset of this band (multi-GPU) */
+    int is_last_band;
+    uint32_t *ubuf;
+    unsigned long long ubuf_cap_bytes;
+    EncState *st;
+    int tile_bytes;
+};
+
+#define KC_THREADS 256
+__global__ void __launch_bounds__(KC_THREADS) k_concat_chunks(const KcParams q)
+{
+    __shared__ unsigned long long sPart[KC_THREADS / 32];
+    const int tid = threadIdx.x;
+    const long long chunk = blockIdx.x;
+    const uint32_t tbits = q.cta_bits[chunk];
+    unsigned long long part = 0ull;
+    {
+        const long long sup = chunk >> EC_SUPER_SHIFT;
+        for (long long i = tid; i < sup; i += KC_THREADS) part += q.super_bits[i];
+        for (long long i = (sup << EC_SUPER_SHIFT) + tid; i < chunk; i += KC_THREADS) part += q.cta_bits[i];
+    }
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    if ((tid & 31) == 0) sPart[tid >> 5] = part;
+    __syncthreads();
+    unsigned long long g0 = q.bit_base;
+#pragma unroll
+    for (int i = 0; i < KC_THREADS / 32; i++) g0 += sPart[i];
+    const bool fits = ((g0 + tbits + 7ull) >> 3) + 64ull <= q.ubuf_cap_bytes; /* only trips on corrupted lengths */
+    const bool last_chunk = (chunk == q.n_chunks - 1);
+    if (last_chunk && tid == 0) {
+        const unsigned long long all = g0 - q.bit_base + tbits;
+        EncState *st = q.st;
+        st->total_bits = fits ? all : 0ull;
+        st->nbytes = fits ? (all + 7) >> 3 : 0ull;
+        st->n_tiles = (st->nbytes + (unsigned long long)q.tile_bytes - 1) / (unsigned long long)q.tile_bytes;
+        st->total_ff = 0;
+        st->out_len = 0;
+        st->error = fits ? 0 : 1;
+    }
+    const uint32_t *slot = q.tmp + chunk * q.slot_words;
+    const uint32_t nin = (tbits + 31u) >> 5;
+    if (!fits) return;
+    const uint32_t sh = (uint32_t)(g0 & 31ull);
+    uint32_t pad = 0;
+    if (last_chunk && q.is_last_band) pad = (8u - (uint32_t)((g0 + tbits) & 7ull)) & 7u;
+    const uint32_t nout = (sh + tbits + pad + 31u) >> 5;
+    uint32_t *gw = q.ubuf + (g0 >> 5);
+    /* output word i holds chunk bits [32 i - sh, 32 i - sh + 32): the low sh bits of input word
+     * i-1 and the high 32-sh bits of input word i (numeric big-endian values) */
+    for (uint32_t i = tid; i < nout; i += KC_THREADS) {
+        const uint32_t lo = (i < nin) ? __byte_perm(slot[i], 0, 0x0123) : 0u;
+        const uint32_t hi = (i >= 1 && i - 1 < nin) ? __byte_perm(slot[i - 1], 0, 0x0123) : 0u;
+        uint32_t v = sh ? ((hi << (32 - sh)) | (lo >> sh)) : lo;
+        if (pad && i == nout - 1) {
+            const uint32_t endbit = (sh + tbits) - 32u * i; /* valid bits of the last word, 1..32 */
+            v |= (pad >= 32u - 0u ? 0u : (((1u << pad) - 1u) << (32u - endbit - pad)));
+        }
+        const uint32_t be = __byte_perm(v, 0, 0x0123);
+        if (i == 0 || i == nout - 1) {
+            if (be) atomicOr(gw + i, be);
         } else {
-            gw[i] = v;
+            gw[i] = be;
         }
     }
 }

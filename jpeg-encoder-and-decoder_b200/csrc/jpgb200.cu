@@ -5,10 +5,10 @@
  *
  * Launch sequence of one encode (one stream, no host synchronisation in between):
  *   K1 k1_transform   pixels -> int16 zig-zag coefficients           (HBM-bound, 9 B/px)
- *   K3 k3_block_bits  per-block code length, per-chunk offsets + totals, and the device-wide
- *                     exclusive prefix sum of the chunk totals (single-pass chained scan)
- *   K5 k5_pack        every block writes its codes at its global bit offset (chunk streams
- *                     assembled in shared memory, copied out coalesced)
+ *   KE k_encode_chunks  per-block code lengths and the bit pack, chunk-locally: coefficients are
+ *                     read once; every chunk's stream goes to its own slot, its length into
+ *                     two-level sums (the device-wide exclusive prefix sum of bit offsets)
+ *   KC k_concat_chunks  chunk streams funnel-shifted to their global bit offsets
  *   K6 k6_count / k6_scatter  0xFF00 stuffing by a second length/offset scan (two-level sums),
  *                     JFIF header, EOI and length word
  * There is no CPU arithmetic path in this library.
@@ -32,9 +32,9 @@
 
 using namespace jpgb200;
 
-enum { KI_K1 = 0, KI_K35, KI_K3, KI_K5, KI_K6COUNT, KI_K6SCATTER };
-static const char *kKernelNames[JPGB200_NUM_KERNELS] = {"k1_transform", "k35_entropy", "k3_block_bits",
-                                                        "k5_pack",      "k6_count",    "k6_scatter"};
+enum { KI_K1 = 0, KI_K35, KI_KE, KI_KC, KI_K6COUNT, KI_K6SCATTER };
+static const char *kKernelNames[JPGB200_NUM_KERNELS] = {"k1_transform",    "k35_entropy", "k_encode_chunks",
+                                                        "k_concat_chunks", "k6_count",    "k6_scatter"};
 
 struct EvPair {
     int k;
@@ -63,6 +63,8 @@ struct jpgb200_ctx {
     size_t cta_cap;
     uint32_t *d_ubuf;
     size_t ubuf_cap;
+    uint32_t *d_tmp; /* chunk-local streams written by KE, one slot per chunk */
+    size_t tmp_cap;
     uint32_t *d_tile_ff;
     unsigned long long *d_bit_state, *d_ff_state;
     size_t chain_cap;
@@ -340,7 +342,7 @@ extern "C" void jpgb200_destroy(jpgb200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {ctx->d_huff,     ctx->d_hbits, ctx->d_scan_order, ctx->d_planes[0], ctx->d_planes[1], ctx->d_zz,   ctx->d_local_off,
-                    ctx->d_cta_bits, ctx->d_super, ctx->d_cta_base,   ctx->d_ubuf,      ctx->d_tile_ff,   ctx->d_tile_base,
+                    ctx->d_cta_bits, ctx->d_super, ctx->d_cta_base,   ctx->d_ubuf,      ctx->d_tmp,       ctx->d_tile_ff,   ctx->d_tile_base,
                     ctx->d_state,    ctx->d_bit_state, ctx->d_ff_state, ctx->d_header,     ctx->d_out[0],    ctx->d_out[1],    ctx->d_len,  ctx->d_dc,
                     ctx->d_tile_sum, ctx->d_freq};
     for (void *p : ptrs)
@@ -508,6 +510,12 @@ static int validate(int w, int h, int quality, int ratio, long long n[3])
 }
 
 static long long n_chunks(const long long n[3]) { return (n[1] + EC_MCUS - 1) / EC_MCUS; }
+/* words of one chunk's slot: worst case 1658 bits per block (20-bit DC + 63 x 26-bit AC), 16-byte multiple */
+static long long slot_words(const long long n[3])
+{
+    const long long bpm = (n[0] == n[1]) ? 3 : 4;
+    return (((long long)EC_MCUS * bpm * 1658 + 31) / 32 + 4) & ~3ll;
+}
 
 static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_zz)
 {
@@ -553,6 +561,7 @@ static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_
         if (ctx->d_ubuf != before || ctx->ubuf_cap != cap_before) /* K5's invariant: all-zero on entry */
             CK(cudaMemsetAsync(ctx->d_ubuf, 0, ctx->ubuf_cap, ctx->stream));
     }
+    if ((rc = grow(ctx, &ctx->d_tmp, &ctx->tmp_cap, nc * (size_t)slot_words(n) * 4))) return rc;
     const size_t nt = ctx->ubuf_cap / K6_TILE + 2;
     if (ctx->tile_cap < nt || !ctx->d_tile_ff) {
         size_t c1 = 0, c2 = 0;
@@ -666,63 +675,67 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
     return JPGB200_OK;
 }
 
-static void fill_ec(jpgb200_ctx *ctx, EcParams &e, const int16_t *zz, const long long n[3])
-{
-    e.zz = zz;
-    e.coff1 = n[0];
-    e.coff2 = n[0] + n[1];
-    e.n_mcu = n[1];
-    e.dc_pred[0] = e.dc_pred[1] = e.dc_pred[2] = 0;
-    e.is_last_band = 1;
-    e.local_off = ctx->d_local_off;
-    e.cta_bits = ctx->d_cta_bits;
-    e.super_bits = ctx->d_super;
-    e.bit_base = 0;
-    e.ubuf = ctx->d_ubuf;
-    e.st = ctx->d_state;
-    e.n_chunks = n_chunks(n);
-    e.ubuf_cap_bytes = (unsigned long long)ctx->ubuf_cap;
-    e.tile_bytes = K6_TILE;
-}
-
-/* K3 + K4: bit lengths and their device-wide exclusive scan */
+/* KE: every chunk's bit lengths and its packed, chunk-local stream; two-level sums of the lengths */
 static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3], const int *pred = NULL,
                        bool clear_supers = false)
 {
     if (clear_supers) CK(cudaMemsetAsync(ctx->d_super, 0, (ctx->n_super_bits + ctx->n_super_ff) * 4, ctx->stream));
-    EcParams e;
-    fill_ec(ctx, e, zz, n);
-    if (pred)
-        for (int c = 0; c < 3; c++) e.dc_pred[c] = pred[c];
+    KeParams e;
+    e.zz = zz;
+    e.coff1 = n[0];
+    e.coff2 = n[0] + n[1];
+    e.n_mcu = n[1];
+    for (int c = 0; c < 3; c++) e.dc_pred[c] = pred ? pred[c] : 0;
+    e.tmp = ctx->d_tmp;
+    e.slot_words = slot_words(n);
+    e.cta_bits = ctx->d_cta_bits;
+    e.super_bits = ctx->d_super;
+    e.local_off = ctx->d_local_off;
     const unsigned nc = (unsigned)n_chunks(n);
     {
-        LaunchScope ls(ctx, KI_K3);
+        LaunchScope ls(ctx, KI_KE);
         if (ratio == 0)
-            k3_block_bits<0><<<nc, EcCfg<0>::NT, 0, ctx->stream>>>(e, ctx->d_hbits);
+            k_encode_chunks<0><<<nc, EcCfg<0>::NT, 0, ctx->stream>>>(e, ctx->d_hbits, ctx->d_huff);
         else
-            k3_block_bits<1><<<nc, EcCfg<1>::NT, 0, ctx->stream>>>(e, ctx->d_hbits);
+            k_encode_chunks<1><<<nc, EcCfg<1>::NT, 0, ctx->stream>>>(e, ctx->d_hbits, ctx->d_huff);
     }
     CK(cudaGetLastError());
     ctx->have_bits = true;
     return JPGB200_OK;
 }
 
-/* KZ + K5 + K6: pack and stuff into d_out */
+/* KC: chunk streams -> the un-stuffed stream at their global bit offsets */
+static int launch_concat(jpgb200_ctx *ctx, const long long n[3], unsigned long long bit_base, int is_last_band)
+{
+    KcParams q;
+    q.tmp = ctx->d_tmp;
+    q.slot_words = slot_words(n);
+    q.n_chunks = n_chunks(n);
+    q.cta_bits = ctx->d_cta_bits;
+    q.super_bits = ctx->d_super;
+    q.bit_base = bit_base;
+    q.is_last_band = is_last_band;
+    q.ubuf = ctx->d_ubuf;
+    q.ubuf_cap_bytes = (unsigned long long)ctx->ubuf_cap;
+    q.st = ctx->d_state;
+    q.tile_bytes = K6_TILE;
+    {
+        LaunchScope ls(ctx, KI_KC);
+        k_concat_chunks<<<(unsigned)q.n_chunks, KC_THREADS, 0, ctx->stream>>>(q);
+    }
+    CK(cudaGetLastError());
+    return JPGB200_OK;
+}
+
+/* KC + K6: concatenate and stuff into d_out */
 static int launch_pack(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3], uint8_t *d_out, size_t cap,
                        unsigned long long *len_out)
 {
-    EcParams e;
-    fill_ec(ctx, e, zz, n);
-    const unsigned nc = (unsigned)n_chunks(n);
+    (void)zz;
+    (void)ratio;
+    int rc = launch_concat(ctx, n, 0ull, 1);
+    if (rc) return rc;
     const unsigned pgrid = (unsigned)ctx->sm_count * 8;
-    {
-        LaunchScope ls(ctx, KI_K5);
-        if (ratio == 0)
-            k5_pack<0><<<nc, EcCfg<0>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
-        else
-            k5_pack<1><<<nc, EcCfg<1>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
-    }
-    CK(cudaGetLastError());
     {
         LaunchScope ls(ctx, KI_K6COUNT);
         k6_count<<<pgrid, K6_THREADS, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(ctx->d_ubuf), ctx->d_state,
@@ -1031,24 +1044,11 @@ extern "C" int jpgb200_band_pack(jpgb200_ctx *ctx, int bit_phase, int is_last, u
                                  uint8_t *tail_byte)
 {
     if (!ctx || !owned_bytes || !tail_byte || bit_phase < 0 || bit_phase > 7) return JPGB200_ERR_BAD_ARG;
-    const int *pred_dc = ctx->band_pred;
     CK(cudaSetDevice(ctx->device));
-    EcParams e;
-    fill_ec(ctx, e, ctx->d_zz, ctx->band_n);
-    e.dc_pred[0] = pred_dc[0];
-    e.dc_pred[1] = pred_dc[1];
-    e.dc_pred[2] = pred_dc[2];
-    e.bit_base = (unsigned long long)bit_phase;
-    e.is_last_band = is_last ? 1 : 0;
-    const unsigned nc = (unsigned)n_chunks(ctx->band_n);
     {
-        LaunchScope ls(ctx, KI_K5);
-        if (ctx->band_ratio == 0)
-            k5_pack<0><<<nc, EcCfg<0>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
-        else
-            k5_pack<1><<<nc, EcCfg<1>::NT, 0, ctx->stream>>>(e, ctx->d_huff);
+        int rc = launch_concat(ctx, ctx->band_n, (unsigned long long)bit_phase, is_last ? 1 : 0);
+        if (rc) return rc;
     }
-    CK(cudaGetLastError());
     const unsigned long long end = (unsigned long long)bit_phase + ctx->band_bits;
     unsigned long long own = end >> 3;
     if (is_last && (end & 7ull)) own += 1; /* the 1-padded final byte */
