@@ -98,6 +98,121 @@ JPGB_HD void fdct8x8(float *f)
         fdct8(f[0 * 8 + x], f[1 * 8 + x], f[2 * 8 + x], f[3 * 8 + x], f[4 * 8 + x], f[5 * 8 + x], f[6 * 8 + x], f[7 * 8 + x]);
 }
 
+#ifdef __CUDACC__
+/* ---- packed FP32x2 forms (sm_100a FADD2 / FMUL2 / FFMA2: two IEEE-RN FP32 operations per
+ * issue slot, immediates broadcast to both halves).  Every operation below is the scalar
+ * function's operation applied to two independent instances, in the same order, so the results
+ * are bit-identical to fdct8x8 / colour_* above -- only the instruction count halves. */
+typedef float2 f32x2;
+__device__ __forceinline__ f32x2 p_bc(float x) { return make_float2(x, x); }
+__device__ __forceinline__ f32x2 p_add(f32x2 a, f32x2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ f32x2 p_sub(f32x2 a, f32x2 b) { return __fadd2_rn(a, make_float2(-b.x, -b.y)); }
+__device__ __forceinline__ f32x2 p_mul(f32x2 a, f32x2 b) { return __fmul2_rn(a, b); }
+__device__ __forceinline__ f32x2 p_fma(f32x2 a, f32x2 b, f32x2 c) { return __ffma2_rn(a, b, c); }
+
+__device__ __forceinline__ f32x2 colour_y_p(f32x2 r, f32x2 g, f32x2 b)
+{
+    return p_fma(p_bc(0.114f), b, p_fma(p_bc(0.587f), g, p_fma(p_bc(0.299f), r, p_bc(-128.0f))));
+}
+__device__ __forceinline__ f32x2 colour_cb_p(f32x2 r, f32x2 g, f32x2 b)
+{
+    return p_fma(p_bc(-0.5f), b, p_fma(p_bc(0.331264f), g, p_mul(p_bc(-0.168736f), r)));
+}
+__device__ __forceinline__ f32x2 colour_cr_p(f32x2 r, f32x2 g, f32x2 b)
+{
+    return p_fma(p_bc(-0.081312f), b, p_fma(p_bc(-0.418688f), g, p_mul(p_bc(0.5f), r)));
+}
+__device__ __forceinline__ f32x2 colour_cb2_p(f32x2 rs, f32x2 gs, f32x2 bs)
+{
+    return p_fma(p_bc(-0.25f), bs, p_fma(p_bc(0.165632f), gs, p_mul(p_bc(-0.084368f), rs)));
+}
+__device__ __forceinline__ f32x2 colour_cr2_p(f32x2 rs, f32x2 gs, f32x2 bs)
+{
+    return p_fma(p_bc(-0.040656f), bs, p_fma(p_bc(-0.209344f), gs, p_mul(p_bc(0.25f), rs)));
+}
+
+/* fdct8 after its first butterfly stage (t0..t7 given) */
+__device__ __forceinline__ void fdct8_tail_p(f32x2 t0, f32x2 t1, f32x2 t2, f32x2 t3, f32x2 t4, f32x2 t5, f32x2 t6, f32x2 t7,
+                                             f32x2 &d0, f32x2 &d1, f32x2 &d2, f32x2 &d3, f32x2 &d4, f32x2 &d5, f32x2 &d6,
+                                             f32x2 &d7)
+{
+    const float c4 = 0.707106781f, c6 = 0.382683433f, a2 = 0.541196100f, a4 = 1.306562965f;
+    f32x2 e0 = p_add(t0, t3), e3 = p_sub(t0, t3);
+    f32x2 e1 = p_add(t1, t2), e2 = p_sub(t1, t2);
+    d0 = p_add(e0, e1);
+    d4 = p_sub(e0, e1);
+    f32x2 s = p_add(e2, e3);
+    d2 = p_fma(p_bc(c4), s, e3);
+    d6 = p_fma(p_bc(-c4), s, e3);
+    f32x2 o0 = p_add(t4, t5), o1 = p_add(t5, t6), o2 = p_add(t6, t7);
+    f32x2 z5 = p_mul(p_sub(o0, o2), p_bc(c6));
+    f32x2 z2 = p_fma(p_bc(a2), o0, z5);
+    f32x2 z4 = p_fma(p_bc(a4), o2, z5);
+    f32x2 z11 = p_fma(p_bc(c4), o1, t7);
+    f32x2 z13 = p_fma(p_bc(-c4), o1, t7);
+    d5 = p_add(z13, z2);
+    d3 = p_sub(z13, z2);
+    d1 = p_add(z11, z4);
+    d7 = p_sub(z11, z4);
+}
+__device__ __forceinline__ void fdct8_p(f32x2 &d0, f32x2 &d1, f32x2 &d2, f32x2 &d3, f32x2 &d4, f32x2 &d5, f32x2 &d6,
+                                        f32x2 &d7)
+{
+    f32x2 t0 = p_add(d0, d7), t7 = p_sub(d0, d7);
+    f32x2 t1 = p_add(d1, d6), t6 = p_sub(d1, d6);
+    f32x2 t2 = p_add(d2, d5), t5 = p_sub(d2, d5);
+    f32x2 t3 = p_add(d3, d4), t4 = p_sub(d3, d4);
+    fdct8_tail_p(t0, t1, t2, t3, t4, t5, t6, t7, d0, d1, d2, d3, d4, d5, d6, d7);
+}
+
+/* 2-D transform of one block held as row pairs P[k][x] = (f[k][x], f[7-k][x]), k = 0..3.
+ * Pass A transforms the eight rows two at a time.  The column pass's first butterfly stage
+ * combines exactly the two rows of a pair (t_k = F_k + F_{7-k}, t_{7-k} = F_k - F_{7-k}), so
+ * it is done with scalar adds that write their results already paired over the horizontal
+ * frequency -- no register transposition anywhere.  Result Q[v][h] = (G[v][2h], G[v][2h+1]),
+ * the natural order f[v*8+u] of fdct8x8, bit-identical to it. */
+__device__ __forceinline__ void fdct8x8_p(f32x2 (&P)[4][8], f32x2 (&Q)[8][4])
+{
+#pragma unroll
+    for (int k = 0; k < 4; k++) fdct8_p(P[k][0], P[k][1], P[k][2], P[k][3], P[k][4], P[k][5], P[k][6], P[k][7]);
+#pragma unroll
+    for (int h = 0; h < 4; h++) {
+        f32x2 t[8];
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const f32x2 a = P[k][2 * h], b = P[k][2 * h + 1];
+            t[k] = make_float2(a.x + a.y, b.x + b.y);
+            t[7 - k] = make_float2(a.x - a.y, b.x - b.y);
+        }
+        fdct8_tail_p(t[0], t[1], t[2], t[3], t[4], t[5], t[6], t[7], Q[0][h], Q[1][h], Q[2][h], Q[3][h], Q[4][h], Q[5][h],
+                     Q[6][h], Q[7][h]);
+    }
+}
+
+/* bytes -> exact FP32 without a conversion instruction: PRMT builds the bit pattern of
+ * 2^23 + byte, one FADD2 removes the 2^23 from two values */
+#define JPGB_BYTE_MAGIC 0x4B000000u
+__device__ __forceinline__ f32x2 bytes_to_f32x2(uint32_t wa, uint32_t wb, int byte_index)
+{
+    /* (byte `byte_index` of wa, same byte of wb) */
+    /* magic first: the selector stays an immediate and the magic word one loop-invariant register */
+    const uint32_t sel = 0x3104u + (uint32_t)byte_index;
+    f32x2 v;
+    v.x = __uint_as_float(__byte_perm(JPGB_BYTE_MAGIC, wa, sel));
+    v.y = __uint_as_float(__byte_perm(JPGB_BYTE_MAGIC, wb, sel));
+    return p_add(v, p_bc(-8388608.0f));
+}
+/* same for 16-bit halves (pair sums of two bytes, <= 510): half 0 or 1 of wa / wb */
+__device__ __forceinline__ f32x2 halves_to_f32x2(uint32_t wa, uint32_t wb, int half_index)
+{
+    const uint32_t sel = half_index ? 0x3176u : 0x3154u;
+    f32x2 v;
+    v.x = __uint_as_float(__byte_perm(JPGB_BYTE_MAGIC, wa, sel));
+    v.y = __uint_as_float(__byte_perm(JPGB_BYTE_MAGIC, wb, sel));
+    return p_add(v, p_bc(-8388608.0f));
+}
+#endif /* __CUDACC__ */
+
 /* ---- quantise: one FFMA per coefficient ---------------------------------------
  * q = coef * m + 1.5*2^23 rounds (to nearest, ties to even) at unit granularity; the
  * low 16 bits of the float's bit pattern are then the two's-complement integer.

@@ -18,12 +18,17 @@
  *
  * Work decomposition: a tile = 32 horizontally consecutive 8x8 blocks (256 x 8 pixels) of one
  * block row, processed by 128 threads in three phases:
- *   phase 1 (all threads): thread (row y, 16-pixel segment s) converts 16 pixels of the three
- *           planes to FP32 Y/Cb/Cr and stores float4s to shared memory in a
- *           [comp][y][half][slot][4] layout that writer and reader both touch conflict-free.
+ *   phase 1 (all threads): thread (k, block j) converts rows k and 7-k of block j (2 x 8 pixels
+ *           of the three planes) to FP32 Y/Cb/Cr held as ROW PAIRS (f[k][x], f[7-k][x]): bytes
+ *           become floats by PRMT + one FADD2, the colour maths is FFMA2 on the pairs; float2
+ *           stores to a [comp][k][x][slot] layout that writer and reader touch conflict-free.
  *   phase 2 (warp c = component c): one thread per 8x8 block keeps all 64 samples in
- *           registers: 16 x 8-point butterflies, 64 FFMA quantise, static zig-zag pack to
- *           32 words, stored as 8 x 16 B to a 128-byte-row shared tile with an XOR swizzle.
+ *           registers as 32 FP32x2 pairs: row pass = 4 packed 8-point butterflies, column pass
+ *           = 64 scalar adds (its first stage, which combines the two rows of a pair and writes
+ *           results paired over the horizontal frequency) + 4 packed butterfly tails, 32 FFMA2
+ *           quantise, static zig-zag pack to 32 words, stored as 8 x 16 B to a 128-byte-row
+ *           shared tile with an XOR swizzle.  (FADD2/FMUL2/FFMA2 are sm_100a's two-wide FP32
+ *           instructions: bit-identical results, half the issue slots.)
  *   phase 3 (all threads): the tile's coefficients are contiguous in HBM per component
  *           (32 blocks x 128 B = 4 KB); they are copied out with fully coalesced 16 B stores.
  *
@@ -63,27 +68,6 @@ struct K1Params {
 #define K1_THREADS 128
 #define K1_TILE_BLOCKS 32
 
-__device__ __forceinline__ void unpack8(uint2 v, float *f)
-{
-    f[0] = (float)(v.x & 0xffu);
-    f[1] = (float)((v.x >> 8) & 0xffu);
-    f[2] = (float)((v.x >> 16) & 0xffu);
-    f[3] = (float)(v.x >> 24);
-    f[4] = (float)(v.y & 0xffu);
-    f[5] = (float)((v.y >> 8) & 0xffu);
-    f[6] = (float)((v.y >> 16) & 0xffu);
-    f[7] = (float)(v.y >> 24);
-}
-
-/* pairwise byte sums of 8 pixels -> 4 floats (exact small integers) */
-__device__ __forceinline__ void unpack8_pairsum(uint2 v, float *f)
-{
-    f[0] = (float)((v.x & 0xffu) + ((v.x >> 8) & 0xffu));
-    f[1] = (float)(((v.x >> 16) & 0xffu) + (v.x >> 24));
-    f[2] = (float)((v.y & 0xffu) + ((v.y >> 8) & 0xffu));
-    f[3] = (float)(((v.y >> 16) & 0xffu) + (v.y >> 24));
-}
-
 __device__ __forceinline__ uint2 ld_oob(const uint8_t *o)
 {
     uint2 v;
@@ -92,90 +76,110 @@ __device__ __forceinline__ uint2 ld_oob(const uint8_t *o)
     return v;
 }
 
-/* slot of tile-local block j in the shared layouts: even blocks first, then odd ones, so
- * that the 16 segment-threads of a row write consecutive slots */
-__device__ __forceinline__ int k1_slot(int j) { return (j >> 1) | ((j & 1) << 4); }
-
-typedef float4 K1F[8][2][32];   /* [y][half][slot] per component        : 8 KB  */
+/* FP32 samples between phase 1 and phase 2.  A block is held as ROW PAIRS
+ * P[k][x] = (f[k][x], f[7-k][x]), k = 0..3 (the pairing fdct8x8_p wants), one float2 each --
+ * the unit the packed arithmetic produces and consumes, so neither side shuffles registers.
+ * [k][x][slot]: the 32 phase-1 threads of a (k) warp and the 32 phase-2 threads of a component
+ * warp both touch 32 consecutive float2 -> conflict-free. */
+typedef float2 K1F[4][8][32];   /* per component row : 8 KB */
 typedef uint4 K1Out[32][8];     /* [slot][chunk ^ (slot & 7)] per component row : 4 KB */
 
-/* phase 1 body for one thread: 2 x 8 pixels of row y (tile-local blocks 2*seg, 2*seg+1) */
-template <int RATIO>
-__device__ __forceinline__ void k1_convert(K1F *sF, int y, int seg, const uint2 (&vr)[2], const uint2 (&vg)[2],
-                                           const uint2 (&vb)[2])
+/* the 8 pixels of rows k and 7-k of one plane -> 8 row pairs */
+__device__ __forceinline__ void k1_pairs8(const uint2 a, const uint2 b, f32x2 *o)
 {
-    float cs_r[8], cs_g[8], cs_b[8]; /* 4:2:2 pair sums of both halves */
 #pragma unroll
-    for (int e = 0; e < 2; e++) {
-        float fr[8], fg[8], fb[8], o[8];
-        unpack8(vr[e], fr);
-        unpack8(vg[e], fg);
-        unpack8(vb[e], fb);
-        const int slot = seg + 16 * e;
-#pragma unroll
-        for (int i = 0; i < 8; i++) o[i] = colour_y(fr[i], fg[i], fb[i]);
-        sF[0][y][0][slot] = make_float4(o[0], o[1], o[2], o[3]);
-        sF[0][y][1][slot] = make_float4(o[4], o[5], o[6], o[7]);
-        if (RATIO == 0) {
-#pragma unroll
-            for (int i = 0; i < 8; i++) o[i] = colour_cb(fr[i], fg[i], fb[i]);
-            sF[1][y][0][slot] = make_float4(o[0], o[1], o[2], o[3]);
-            sF[1][y][1][slot] = make_float4(o[4], o[5], o[6], o[7]);
-#pragma unroll
-            for (int i = 0; i < 8; i++) o[i] = colour_cr(fr[i], fg[i], fb[i]);
-            sF[2][y][0][slot] = make_float4(o[0], o[1], o[2], o[3]);
-            sF[2][y][1][slot] = make_float4(o[4], o[5], o[6], o[7]);
-        } else {
-            unpack8_pairsum(vr[e], cs_r + 4 * e);
-            unpack8_pairsum(vg[e], cs_g + 4 * e);
-            unpack8_pairsum(vb[e], cs_b + 4 * e);
-        }
-    }
-    if (RATIO == 1) {
-        /* one chroma block row (8 averaged samples) per thread: Cb -> slot seg,
-         * Cr -> slot 16+seg of component row 1 */
-        float o[8];
-#pragma unroll
-        for (int i = 0; i < 8; i++) o[i] = colour_cb2(cs_r[i], cs_g[i], cs_b[i]);
-        sF[1][y][0][seg] = make_float4(o[0], o[1], o[2], o[3]);
-        sF[1][y][1][seg] = make_float4(o[4], o[5], o[6], o[7]);
-#pragma unroll
-        for (int i = 0; i < 8; i++) o[i] = colour_cr2(cs_r[i], cs_g[i], cs_b[i]);
-        sF[1][y][0][16 + seg] = make_float4(o[0], o[1], o[2], o[3]);
-        sF[1][y][1][16 + seg] = make_float4(o[4], o[5], o[6], o[7]);
+    for (int x = 0; x < 4; x++) {
+        o[x] = bytes_to_f32x2(a.x, b.x, x);
+        o[4 + x] = bytes_to_f32x2(a.y, b.y, x);
     }
 }
 
-/* phase 2: one thread per 8x8 block */
+/* sums of horizontally adjacent pixel pairs of 16 pixels (rows k and 7-k) -> 8 row pairs */
+__device__ __forceinline__ void k1_pairsums16(const uint4 a, const uint4 b, f32x2 *o)
+{
+    const uint32_t wa[4] = {a.x, a.y, a.z, a.w}, wb[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+    for (int w = 0; w < 4; w++) {
+        const uint32_t sa = (wa[w] & 0x00ff00ffu) + ((wa[w] >> 8) & 0x00ff00ffu);
+        const uint32_t sb = (wb[w] & 0x00ff00ffu) + ((wb[w] >> 8) & 0x00ff00ffu);
+        o[2 * w] = halves_to_f32x2(sa, sb, 0);
+        o[2 * w + 1] = halves_to_f32x2(sa, sb, 1);
+    }
+}
+
+__device__ __forceinline__ void k1_store_pairs(K1F &F, int k, int slot, const f32x2 *o)
+{
+#pragma unroll
+    for (int x = 0; x < 8; x++) F[k][x][slot] = o[x];
+}
+
+/* phase 1, full-resolution components: thread (k, j) converts rows k and 7-k of block j.
+ * ra/rb etc. = the 8 bytes of row k / row 7-k of the three planes. */
+template <int RATIO>
+__device__ __forceinline__ void k1_convert_full(K1F *sF, int k, int j, const uint2 (&pa)[3], const uint2 (&pb)[3])
+{
+    f32x2 r[8], g[8], b[8], o[8];
+    k1_pairs8(pa[0], pb[0], r);
+    k1_pairs8(pa[1], pb[1], g);
+    k1_pairs8(pa[2], pb[2], b);
+#pragma unroll
+    for (int x = 0; x < 8; x++) o[x] = colour_y_p(r[x], g[x], b[x]);
+    k1_store_pairs(sF[0], k, j, o);
+    if (RATIO == 0) {
+#pragma unroll
+        for (int x = 0; x < 8; x++) o[x] = colour_cb_p(r[x], g[x], b[x]);
+        k1_store_pairs(sF[1], k, j, o);
+#pragma unroll
+        for (int x = 0; x < 8; x++) o[x] = colour_cr_p(r[x], g[x], b[x]);
+        k1_store_pairs(sF[2], k, j, o);
+    }
+}
+
+/* phase 1, 4:2:2 chroma: thread (k, lane) with lane = which*16 + jc averages the 16 pixels of
+ * rows k and 7-k under chroma block jc and stores Cb (which = 0, slot jc) or Cr (slot 16+jc) */
+__device__ __forceinline__ void k1_convert_chroma422(K1F *sF, int k, int lane, const uint4 (&pa)[3], const uint4 (&pb)[3])
+{
+    f32x2 r[8], g[8], b[8], o[8];
+    k1_pairsums16(pa[0], pb[0], r);
+    k1_pairsums16(pa[1], pb[1], g);
+    k1_pairsums16(pa[2], pb[2], b);
+    if (lane < 16) {
+#pragma unroll
+        for (int x = 0; x < 8; x++) o[x] = colour_cb2_p(r[x], g[x], b[x]);
+    } else {
+#pragma unroll
+        for (int x = 0; x < 8; x++) o[x] = colour_cr2_p(r[x], g[x], b[x]);
+    }
+    k1_store_pairs(sF[1], k, lane, o);
+}
+
+/* phase 2: one thread per 8x8 block (warp = component row, lane = slot) */
 template <int RATIO>
 __device__ __forceinline__ void k1_phase2(const K1F *sF, K1Out *sOut, const float (*sMul)[64], int tid)
 {
     const int c = tid >> 5, lane = tid & 31;
     const int ncomp_rows = (RATIO == 0) ? 3 : 2;
     if (c < ncomp_rows) {
+        f32x2 P[4][8], Q[8][4];
+#pragma unroll
+        for (int k = 0; k < 4; k++)
+#pragma unroll
+            for (int x = 0; x < 8; x++) P[k][x] = sF[c][k][x][lane];
+        fdct8x8_p(P, Q);
+        const float4 *m4 = reinterpret_cast<const float4 *>(sMul[c == 0 ? 0 : 1]);
         float f[64];
 #pragma unroll
-        for (int y = 0; y < 8; y++) {
-            float4 a = sF[c][y][0][lane], b4 = sF[c][y][1][lane];
-            f[y * 8 + 0] = a.x;
-            f[y * 8 + 1] = a.y;
-            f[y * 8 + 2] = a.z;
-            f[y * 8 + 3] = a.w;
-            f[y * 8 + 4] = b4.x;
-            f[y * 8 + 5] = b4.y;
-            f[y * 8 + 6] = b4.z;
-            f[y * 8 + 7] = b4.w;
-        }
-        fdct8x8(f);
-        const float4 *m4 = reinterpret_cast<const float4 *>(sMul[c == 0 ? 0 : 1]);
+        for (int v = 0; v < 8; v++)
 #pragma unroll
-        for (int i = 0; i < 16; i++) {
-            float4 m = m4[i];
-            f[4 * i + 0] = jfma(f[4 * i + 0], m.x, JPGB_ROUND_MAGIC);
-            f[4 * i + 1] = jfma(f[4 * i + 1], m.y, JPGB_ROUND_MAGIC);
-            f[4 * i + 2] = jfma(f[4 * i + 2], m.z, JPGB_ROUND_MAGIC);
-            f[4 * i + 3] = jfma(f[4 * i + 3], m.w, JPGB_ROUND_MAGIC);
-        }
+            for (int hh = 0; hh < 2; hh++) {
+                const float4 m = m4[v * 2 + hh];
+                const f32x2 q0 = p_fma(Q[v][2 * hh], make_float2(m.x, m.y), p_bc(JPGB_ROUND_MAGIC));
+                const f32x2 q1 = p_fma(Q[v][2 * hh + 1], make_float2(m.z, m.w), p_bc(JPGB_ROUND_MAGIC));
+                f[v * 8 + 4 * hh + 0] = q0.x;
+                f[v * 8 + 4 * hh + 1] = q0.y;
+                f[v * 8 + 4 * hh + 2] = q1.x;
+                f[v * 8 + 4 * hh + 3] = q1.y;
+            }
         uint32_t o[32];
         zigzag_pack(f, o);
 #pragma unroll
@@ -200,7 +204,7 @@ __device__ __forceinline__ void k1_phase3(const K1Out *sOut, const K1Params &p, 
         bool ok;
         if (RATIO == 0 || crow == 0) {
             /* j = tile-local block of a full-resolution component */
-            slot = k1_slot(j);
+            slot = j;
             ok = (tb0 + j) < p.BW;
             int16_t *base = (crow == 0) ? zy : (crow == 1 ? zcb : zcr);
             dst = reinterpret_cast<uint4 *>(base + ((long long)by * p.BW + tb0 + j) * 64) + ch;
@@ -238,27 +242,34 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform(const K1Params p)
     if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
         for (int i = tid; i < p.clear_n; i += K1_THREADS) p.clear[i] = 0u;
     {
-        const int y = tid >> 4, seg = tid & 15;
-        uint2 vr[2], vg[2], vb[2];
+        const int k = tid >> 5, lane = tid & 31;
+        const uint8_t *pl[3] = {pr, pg, pb};
+        /* 8 bytes of image row by*8+rr of block column bx (one row higher for the last column) */
+        auto ld8 = [&](int c, int rr, int bx) -> uint2 {
+            if (bx >= p.BW) return make_uint2(0u, 0u);
+            const long long row = (long long)by * 8 + rr - (bx == p.BW - 1 ? 1 : 0);
+            if (row >= 0 || p.has_halo) return __ldg(reinterpret_cast<const uint2 *>(pl[c] + row * p.W + (long long)bx * 8));
+            return ld_oob(p.oob + 8 * c);
+        };
+        uint2 pa[3], pb2[3];
 #pragma unroll
-        for (int e = 0; e < 2; e++) {
-            const int bx = tb0 + 2 * seg + e;
-            vr[e] = vg[e] = vb[e] = make_uint2(0, 0);
-            if (bx < p.BW) {
-                long long row = (long long)by * 8 + y - (bx == p.BW - 1 ? 1 : 0);
-                if (row >= 0 || p.has_halo) {
-                    long long idx = row * p.W + (long long)bx * 8;
-                    vr[e] = __ldg(reinterpret_cast<const uint2 *>(pr + idx));
-                    vg[e] = __ldg(reinterpret_cast<const uint2 *>(pg + idx));
-                    vb[e] = __ldg(reinterpret_cast<const uint2 *>(pb + idx));
-                } else {
-                    vr[e] = ld_oob(p.oob);
-                    vg[e] = ld_oob(p.oob + 8);
-                    vb[e] = ld_oob(p.oob + 16);
-                }
-            }
+        for (int c = 0; c < 3; c++) {
+            pa[c] = ld8(c, k, tb0 + lane);
+            pb2[c] = ld8(c, 7 - k, tb0 + lane);
         }
-        k1_convert<RATIO>(sF, y, seg, vr, vg, vb);
+        k1_convert_full<RATIO>(sF, k, lane, pa, pb2);
+        if (RATIO == 1) {
+            const int jc = lane & 15;
+            uint4 ca[3], cb[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const uint2 l0 = ld8(c, k, tb0 + 2 * jc), l1 = ld8(c, k, tb0 + 2 * jc + 1);
+                const uint2 h0 = ld8(c, 7 - k, tb0 + 2 * jc), h1 = ld8(c, 7 - k, tb0 + 2 * jc + 1);
+                ca[c] = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                cb[c] = make_uint4(h0.x, h0.y, h1.x, h1.y);
+            }
+            k1_convert_chroma422(sF, k, lane, ca, cb);
+        }
     }
     __syncthreads();
     k1_phase2<RATIO>(sF, sOut, sMul, tid);
@@ -388,42 +399,37 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform_tma(const K1Params
         /* ---- phase 1: raw bytes (shared) -> FP32 Y/Cb/Cr (shared) ---- */
         {
             const K1Stage &st = S.stage[s];
-            const int y = tid >> 4, seg = tid & 15;
-            uint2 vr[2], vg[2], vb[2];
-            const uint4 qr = *reinterpret_cast<const uint4 *>(&st.raw[0][y][seg * 16]);
-            const uint4 qg = *reinterpret_cast<const uint4 *>(&st.raw[1][y][seg * 16]);
-            const uint4 qb = *reinterpret_cast<const uint4 *>(&st.raw[2][y][seg * 16]);
-            vr[0] = make_uint2(qr.x, qr.y);
-            vr[1] = make_uint2(qr.z, qr.w);
-            vg[0] = make_uint2(qg.x, qg.y);
-            vg[1] = make_uint2(qg.z, qg.w);
-            vb[0] = make_uint2(qb.x, qb.y);
-            vb[1] = make_uint2(qb.z, qb.w);
-            /* block column BW-1 is read one pixel row higher */
+            const int k = tid >> 5;
+            /* block column BW-1 is read one pixel row higher: its rows come from
+             * `alt`, row -1 of the image from the caller's out-of-bounds bytes */
             const int jl = p.BW - 1 - tl.tb0; /* its tile-local index, if inside this tile */
-            if ((jl >> 1) == seg && jl >= 0 && jl < K1_TILE_BLOCKS) {
-                const int e = jl & 1;
-                uint2 ar, ag, ab;
-                if (tl.by == 0 && y == 0 && !p.has_halo) {
-                    ar = ld_oob(p.oob);
-                    ag = ld_oob(p.oob + 8);
-                    ab = ld_oob(p.oob + 16);
-                } else {
-                    ar = *reinterpret_cast<const uint2 *>(&st.alt[0][y][8]);
-                    ag = *reinterpret_cast<const uint2 *>(&st.alt[1][y][8]);
-                    ab = *reinterpret_cast<const uint2 *>(&st.alt[2][y][8]);
+            const bool top_oob = (tl.by == 0 && !p.has_halo);
+            auto ld8 = [&](int c, int rr, int j) -> uint2 {
+                if (j == jl) {
+                    if (top_oob && rr == 0) return ld_oob(p.oob + 8 * c);
+                    return *reinterpret_cast<const uint2 *>(&st.alt[c][rr][8]);
                 }
-                if (e == 0) {
-                    vr[0] = ar;
-                    vg[0] = ag;
-                    vb[0] = ab;
-                } else {
-                    vr[1] = ar;
-                    vg[1] = ag;
-                    vb[1] = ab;
-                }
+                return *reinterpret_cast<const uint2 *>(&st.raw[c][rr][j * 8]);
+            };
+            uint2 pa[3], pb[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                pa[c] = ld8(c, k, lane);
+                pb[c] = ld8(c, 7 - k, lane);
             }
-            k1_convert<RATIO>(S.sF, y, seg, vr, vg, vb);
+            k1_convert_full<RATIO>(S.sF, k, lane, pa, pb);
+            if (RATIO == 1) {
+                const int jc = lane & 15;
+                uint4 ca[3], cb[3];
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const uint2 l0 = ld8(c, k, 2 * jc), l1 = ld8(c, k, 2 * jc + 1);
+                    const uint2 h0 = ld8(c, 7 - k, 2 * jc), h1 = ld8(c, 7 - k, 2 * jc + 1);
+                    ca[c] = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                    cb[c] = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                }
+                k1_convert_chroma422(S.sF, k, lane, ca, cb);
+            }
         }
         __syncthreads();
         /* the stage's raw bytes are consumed: refill it with the tile K1_STAGES iterations ahead.
