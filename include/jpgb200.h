@@ -64,8 +64,10 @@ int jpgb200_sync(jpgb200_ctx *ctx);
  * K3 (bit lengths) / K4 (scan) / K5 (pack) / K6 (stuffing) pipeline, kept for the MCU-row
  * partition and as a cross-check -- both produce identical bytes. */
 int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on);
-/* K1 selection: 0 (default) = persistent kernel fed by TMA bulk copies whenever width % 16 == 0;
- * 1 = always the direct-load kernel (the only one for width % 16 == 8).  Identical results. */
+/* K1 selection: 0 (default) = persistent kernel of autonomous warps fed by TMA bulk copies
+ * whenever width % 16 == 0; 1 = always the direct-load kernel (the only one for
+ * width % 16 == 8); 2 = the earlier TMA kernel whose phases are separated by CTA barriers.
+ * Identical results. */
 int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on);
 /* The 8 bytes the reference reads in front of each plane buffer for block W/8-1
  * (src/preprocess.c:159,206-210): oob[0..7]=r, [8..15]=g, [16..23]=b.

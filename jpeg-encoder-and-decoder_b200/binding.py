@@ -163,7 +163,7 @@ class Encoder:
         self._ck(lib().jpgb200_set_staged_entropy(self._h, 1 if on else 0))
 
     def set_plain_transform(self, on):
-        self._ck(lib().jpgb200_set_plain_transform(self._h, 1 if on else 0))
+        self._ck(lib().jpgb200_set_plain_transform(self._h, int(on)))
 
     def set_oob_bytes(self, oob):
         oob = _c(oob)

@@ -27,6 +27,7 @@
 #include "jpgb200_math.cuh"
 #include "jpgb200_tables.h"
 #include "k1_transform.cuh"
+#include "k1_warp.cuh"
 #include "stuffing.cuh"
 #include "taps.cuh"
 
@@ -70,6 +71,7 @@ struct jpgb200_ctx {
     size_t chain_cap;
     bool fused_attr_set, k1_attr_set;
     bool k1_plain; /* force the non-TMA K1 (tests) */
+    bool k1_cta;   /* force the CTA-barrier TMA K1 instead of the warp-autonomous one (tests, A/B runs) */
     unsigned long long *d_tile_base;
     size_t tile_cap, tile_bytes;
     EncState *d_state;
@@ -295,6 +297,7 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         if (e && !strcmp(e, "fused")) ctx->legacy_entropy = false;
         const char *k = getenv("JPGB200_K1"); /* "plain" | "tma" */
         if (k && !strcmp(k, "plain")) ctx->k1_plain = true;
+        if (k && !strcmp(k, "cta")) ctx->k1_cta = true;
     }
     ctx->hdr_w = -1;
     ctx->err[0] = 0;
@@ -379,7 +382,8 @@ extern "C" int jpgb200_sync(jpgb200_ctx *ctx)
 extern "C" int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;
-    ctx->k1_plain = on != 0;
+    ctx->k1_plain = (on == 1);
+    ctx->k1_cta = (on == 2);
     return JPGB200_OK;
 }
 
@@ -646,11 +650,37 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
     memcpy(p.oob, ctx->oob, 24);
     p.tiles_per_row = (p.BW + K1_TILE_BLOCKS - 1) / K1_TILE_BLOCKS;
     p.n_frames = nframes;
+    {
+        const unsigned long long per_frame = (unsigned long long)p.tiles_per_row * (unsigned long long)(h / 8);
+        const unsigned long long total = per_frame * (unsigned long long)nframes;
+        const bool ok = total * per_frame < (1ull << 40) && total < (1ull << 31);
+        p.magic_pf = ok ? ((1ull << 40) + per_frame - 1) / per_frame : 0ull;
+        p.magic_tpr = ok ? ((1ull << 40) + (unsigned long long)p.tiles_per_row - 1) / (unsigned long long)p.tiles_per_row : 0ull;
+    }
     const bool aligned16 = (w % 16 == 0) && (((uintptr_t)d_r | (uintptr_t)d_g | (uintptr_t)d_b) % 16 == 0) &&
                            (plane_stride % 16 == 0);
-    if (aligned16 && !ctx->k1_plain) {
-        /* persistent CTAs fed by TMA bulk copies */
+    if (aligned16 && !ctx->k1_plain && !ctx->k1_cta) {
+        /* persistent CTAs of four autonomous warps fed by TMA bulk copies (k1_warp.cuh) */
         if (!ctx->k1_attr_set) {
+            CK(cudaFuncSetAttribute(k1_transform_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemTma)));
+            CK(cudaFuncSetAttribute(k1_transform_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemTma)));
+            CK(cudaFuncSetAttribute(k1_transform_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1WSmem)));
+            CK(cudaFuncSetAttribute(k1_transform_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1WSmem)));
+            ctx->k1_attr_set = true;
+        }
+        const long long n_tiles = (long long)p.tiles_per_row * (h / 8) * nframes;
+        const long long resident = (long long)ctx->sm_count * K1W_MIN_CTAS;
+        const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+        LaunchScope ls(ctx, KI_K1);
+        if (ratio == 0)
+            k1_transform_ws<0><<<grid, K1_THREADS, sizeof(K1WSmem), ctx->stream>>>(p, n_tiles);
+        else
+            k1_transform_ws<1><<<grid, K1_THREADS, sizeof(K1WSmem), ctx->stream>>>(p, n_tiles);
+    } else if (aligned16 && !ctx->k1_plain) {
+        /* persistent CTAs fed by TMA bulk copies, phases separated by CTA barriers */
+        if (!ctx->k1_attr_set) {
+            CK(cudaFuncSetAttribute(k1_transform_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1WSmem)));
+            CK(cudaFuncSetAttribute(k1_transform_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1WSmem)));
             CK(cudaFuncSetAttribute(k1_transform_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemTma)));
             CK(cudaFuncSetAttribute(k1_transform_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemTma)));
             ctx->k1_attr_set = true;

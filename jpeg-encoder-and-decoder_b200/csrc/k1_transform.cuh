@@ -59,6 +59,7 @@ struct K1Params {
     int W, H, BW;           /* pixels, pixels, W/8 */
     int has_halo;           /* row -1 of the band is valid memory (MCU-row partition) */
     int tiles_per_row, n_frames;
+    unsigned long long magic_pf, magic_tpr; /* ceil(2^40 / tiles per frame), ceil(2^40 / tiles per row); 0 = divide */
     uint32_t *clear; /* small scratch array the entropy stage accumulates into: cleared here, for free */
     int clear_n;
     float mul[2][64];       /* quantiser multipliers [lum|chr][v*8+u] */
@@ -336,6 +337,14 @@ __device__ __forceinline__ K1Tile k1_tile(const K1Params &p, long long t)
     K1Tile o;
     const unsigned tpr = (unsigned)p.tiles_per_row, per_frame = tpr * (unsigned)(p.H >> 3);
     const unsigned tt = (unsigned)t; /* tile counts stay far below 2^32 */
+    if (p.magic_pf) {
+        /* exact for n * d < 2^40 (checked by the host): two wide multiplies instead of two divisions */
+        o.frame = (int)(((unsigned long long)tt * p.magic_pf) >> 40);
+        const unsigned rem = tt - (unsigned)o.frame * per_frame;
+        o.by = (int)(((unsigned long long)rem * p.magic_tpr) >> 40);
+        o.tb0 = (int)(rem - (unsigned)o.by * tpr) * K1_TILE_BLOCKS;
+        return o;
+    }
     o.frame = (int)(tt / per_frame);
     const unsigned rem = tt - (unsigned)o.frame * per_frame;
     o.by = (int)(rem / tpr);
