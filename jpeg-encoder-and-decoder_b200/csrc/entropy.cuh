@@ -115,18 +115,36 @@ __device__ __forceinline__ void cp_async_wait_all()
     asm volatile("cp.async.wait_group 0;\n" ::: "memory");
 }
 
-/* asynchronous fill of the chunk's coefficient rows: 8 chunks of 16 B per thread, a warp's
- * 32 copies cover 512 contiguous bytes of one component */
+/* asynchronous fill of the chunk's coefficient rows.  Rows are component-major (EcMap) and a
+ * component's blocks of the chunk are contiguous in HBM, so each component is one linear run of
+ * 16-byte chunks: chunk i -> row i/8, column i%8 (rows padded to 144 B in shared memory) */
 template <int RATIO>
 __device__ __forceinline__ void ec_fill(uint4 (*sC)[EC_ROW_CHUNKS], const EcParams &p, long long m0, int tid)
 {
     constexpr int NT = EcCfg<RATIO>::NT;
+    const long long left = p.n_mcu - m0;
+    const int nv = left < EC_MCUS ? (int)left : EC_MCUS; /* valid MCUs of this chunk */
     const uint4 *z = reinterpret_cast<const uint4 *>(p.zz);
+    {
+        const int n0 = (RATIO == 0 ? nv : 2 * nv) * 8;
+        const uint4 *src = z + (RATIO == 0 ? m0 : 2 * m0) * 8;
 #pragma unroll
-    for (int k = 0; k < 8; k++) {
-        const int i = k * NT + tid, row = i >> 3, q = i & 7;
-        const EcMap<RATIO> mp(p, m0, row);
-        if (mp.valid) cp_async16(&sC[row][q], z + mp.gabs * 8 + q);
+        for (int k = 0; k < (RATIO == 0 ? 3 : 4); k++) {
+            const int i = k * NT + tid;
+            if (i < n0) cp_async16(&sC[i >> 3][i & 7], src + i);
+        }
+    }
+    {
+        const int n1 = nv * 8, r1 = (RATIO == 0 ? 64 : 128);
+        const uint4 *s1 = z + (p.coff1 + m0) * 8, *s2 = z + (p.coff2 + m0) * 8;
+#pragma unroll
+        for (int k = 0; k < (RATIO == 0 ? 3 : 2); k++) {
+            const int i = k * NT + tid;
+            if (i < n1) {
+                cp_async16(&sC[r1 + (i >> 3)][i & 7], s1 + i);
+                cp_async16(&sC[r1 + 64 + (i >> 3)][i & 7], s2 + i);
+            }
+        }
     }
 }
 
@@ -402,17 +420,49 @@ __device__ __forceinline__ unsigned long long cs_lookback(volatile unsigned long
     return excl;
 }
 
-/* ---- KE (k_encode_chunks): per-block bit lengths AND the bit pack, chunk-locally -------------
- * One CTA per chunk of EC_MCUS MCUs, coefficients read from HBM once:
- *   count pass  : bits per block (ec_count_block) -> CTA scan in scan order -> chunk total T
- *   pack pass   : every block writes its codes at its offset inside the CHUNK's own stream
- *                 (bit 0 = the chunk's first bit), assembled in shared memory and copied to the
- *                 chunk's slot of a temporary buffer with coalesced stores -- a chunk owns its
- *                 slot, so nothing in HBM is shared between CTAs
- *   totals      : T per chunk and, atomically, per 64 chunks: the two-level sums from which KC
- *                 derives every chunk's global bit offset (the device-wide exclusive prefix sum)
- * A chunk whose stream exceeds the staging buffer clears its slot and packs straight into it
- * (atomics on block-boundary words).  Slots need no initialisation between encodes. */
+/* ---- bit writer into a thread-private region: numeric (MSB-first) 32-bit words; words past
+ * the region are dropped but still counted, so the bit length is always right */
+struct PrivSink {
+    unsigned long long acc;
+    int nacc;
+    uint32_t *wp, *end;
+    uint32_t nwords;
+    __device__ __forceinline__ void put(uint32_t v, int n)
+    {
+        acc = (acc << n) | (unsigned long long)v;
+        nacc += n;
+        if (nacc >= 32) {
+            nacc -= 32;
+            if (wp < end) *wp = (uint32_t)(acc >> nacc);
+            wp++;
+            nwords++;
+        }
+    }
+    /* returns the number of bits written */
+    __device__ __forceinline__ uint32_t finish()
+    {
+        const uint32_t bits = nwords * 32u + (uint32_t)nacc;
+        if (nacc > 0 && wp < end) *wp = (uint32_t)(acc << (32 - nacc));
+        return bits;
+    }
+};
+
+/* ---- KE (k_encode_chunks): every block is coded ONCE -----------------------------------------
+ * One CTA per chunk of EC_MCUS MCUs, coefficients read from HBM once, one thread per block:
+ *   code     : the block's codes go, at bit 0, into a thread-private region of shared memory
+ *              (EC_PRIV words); the thread learns its bit length as a by-product -- there is no
+ *              separate counting pass
+ *   scan     : CTA scan of the lengths in scan (MCU-interleaved) order -> the block's offset
+ *              inside the CHUNK's own stream (bit 0 = the chunk's first bit), chunk total T
+ *   relocate : the private words are funnel-shifted to that offset and OR-ed into the chunk
+ *              stream, assembled in shared memory over the (now dead) coefficient rows, then
+ *              copied to the chunk's slot of a temporary buffer with coalesced stores -- a chunk
+ *              owns its slot, so nothing in HBM is shared between CTAs
+ *   totals   : T per chunk and, atomically, per 64 chunks: the two-level sums from which KC
+ *              derives every chunk's global bit offset (the device-wide exclusive prefix sum)
+ * A chunk with a block longer than its private region, or a stream longer than the staging
+ * area, is rare (> 64 bytes for one 8x8 block): it clears its slot and packs straight into it
+ * at the offsets just computed (atomics on block-boundary words). */
 struct KeParams {
     const int16_t *zz;
     long long coff1, coff2, n_mcu;
@@ -425,16 +475,33 @@ struct KeParams {
 };
 
 template <int RATIO>
-__global__ void __launch_bounds__(EcCfg<RATIO>::NT) k_encode_chunks(const KeParams q, const HuffBits *hbits,
-                                                                    const HuffDev *huff)
+struct KeSmem {
+    static const int NT = EcCfg<RATIO>::NT;
+    static const int PRIV = (RATIO == 0) ? 16 : 12;  /* words of private stream per block */
+    static const int PSTRIDE = PRIV + 1;             /* odd: lanes hit distinct banks */
+    static const int ROW_BYTES = NT * EC_ROW_CHUNKS * 16;
+    static const int STAGE_WORDS = ROW_BYTES / 4;    /* the chunk stream reuses the coefficient rows */
+    static const int OFF_PRIV = ROW_BYTES;
+    static const int OFF_H = OFF_PRIV + NT * PSTRIDE * 4;
+    static const int OFF_OFF = OFF_H + (int)sizeof(HuffDev);
+    static const int OFF_WARP = OFF_OFF + NT * 4;
+    static const int OFF_FLAG = OFF_WARP + (NT / 32) * 4;
+    static const int BYTES = OFF_FLAG + 16;
+};
+
+template <int RATIO>
+__global__ void __launch_bounds__(EcCfg<RATIO>::NT) k_encode_chunks(const KeParams q, const HuffDev *huff)
 {
-    constexpr int BPM = EcCfg<RATIO>::BPM, NT = EcCfg<RATIO>::NT, STAGE = EcCfg<RATIO>::STAGE_WORDS;
-    __shared__ uint4 sC[NT][EC_ROW_CHUNKS];
-    __shared__ __align__(16) HuffBits sB;
-    __shared__ __align__(16) HuffDev sH;
-    __shared__ uint32_t sOff[NT];
-    __shared__ uint32_t sWarp[NT / 32];
-    __shared__ __align__(16) uint32_t sS[STAGE];
+    constexpr int BPM = EcCfg<RATIO>::BPM, NT = EcCfg<RATIO>::NT;
+    typedef KeSmem<RATIO> L;
+    extern __shared__ __align__(16) unsigned char ke_smem[];
+    uint4(*sC)[EC_ROW_CHUNKS] = reinterpret_cast<uint4(*)[EC_ROW_CHUNKS]>(ke_smem);
+    uint32_t *sS = reinterpret_cast<uint32_t *>(ke_smem); /* chunk stream, over the rows */
+    uint32_t *sP = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_PRIV);
+    HuffDev &sH = *reinterpret_cast<HuffDev *>(ke_smem + L::OFF_H);
+    uint32_t *sOff = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_OFF);
+    uint32_t *sWarp = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_WARP);
+    uint32_t *sFlag = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_FLAG);
     const int tid = threadIdx.x;
     const long long chunk = blockIdx.x;
     const long long m0 = chunk * EC_MCUS;
@@ -449,20 +516,28 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k_encode_chunks(const KePara
     p.dc_pred[2] = q.dc_pred[2];
 
     ec_fill<RATIO>(sC, p, m0, tid);
-    ec_load_table(&sB, hbits, tid);
     ec_load_table(&sH, huff, tid);
     const EcMap<RATIO> mp(p, m0, tid);
-    for (int i = tid; i < STAGE; i += NT) sS[i] = 0u;
+    if (tid == 0) *sFlag = 0u;
     cp_async_wait_all();
     __syncthreads();
 
-    /* count pass */
+    /* code every block once, privately */
     uint32_t nbits = 0;
     int diff = 0;
+    uint32_t *priv = sP + tid * L::PSTRIDE;
     if (mp.valid) {
         const int pred = ec_dc_pred<RATIO>(sC, p, m0, tid, mp);
         diff = (int)(short)(sC[tid][0].x & 0xffffu) - pred;
-        nbits = ec_count_block(sC[tid], diff, sB.ac[mp.comp ? 1 : 0], sB.dc[mp.comp ? 1 : 0]);
+        PrivSink s;
+        s.acc = 0;
+        s.nacc = 0;
+        s.wp = priv;
+        s.end = priv + L::PRIV;
+        s.nwords = 0;
+        ec_pack_block(sC[tid], diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
+        nbits = s.finish();
+        if (nbits > (uint32_t)L::PRIV * 32u) *sFlag = 1u;
     }
     sOff[mp.s_local] = nbits; /* scan (MCU-interleaved) order */
     __syncthreads();
@@ -477,39 +552,42 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k_encode_chunks(const KePara
         q.cta_bits[chunk] = total;
         atomicAdd(&q.super_bits[chunk >> EC_SUPER_SHIFT], total);
     }
-    __syncthreads();
-
-    /* pack pass */
     const uint32_t nwords = (total + 31u) >> 5;
-    const bool staged = nwords <= (uint32_t)STAGE;
+    const bool staged = (*sFlag == 0u) && nwords < (uint32_t)L::STAGE_WORDS; /* word [nwords] may receive an empty OR */
     uint32_t *slot = q.tmp + chunk * q.slot_words;
-    if (!staged) {
-        for (uint32_t i = tid; i < nwords; i += NT) slot[i] = 0u;
+    if (staged) {
+        /* the coefficient rows are dead (every block is coded): the chunk stream takes their place */
+        for (uint32_t i = tid; i < nwords + 1u; i += NT) sS[i] = 0u;
         __syncthreads();
+        if (mp.valid) {
+            const uint32_t loff = sOff[mp.s_local];
+            const uint32_t sh = loff & 31u, nw = (nbits + 31u) >> 5;
+            uint32_t *dst = sS + (loff >> 5);
+            for (uint32_t i = 0; i < nw; i++) {
+                const uint32_t v = priv[i];
+                const unsigned a0 = (unsigned)__cvta_generic_to_shared(dst + i);
+                asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a0), "r"(v >> sh) : "memory");
+                if (sh) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a0 + 4u), "r"(v << (32u - sh)) : "memory");
+            }
+        }
+        __syncthreads();
+        for (uint32_t i = tid; i < nwords; i += NT) slot[i] = __byte_perm(sS[i], 0, 0x0123);
+        return;
     }
+    /* rare: straight into the slot */
+    __syncthreads();
+    for (uint32_t i = tid; i < nwords; i += NT) slot[i] = 0u;
+    __syncthreads();
     if (mp.valid) {
         const uint32_t loff = sOff[mp.s_local];
-        if (staged) {
-            PackSink<true> s;
-            s.acc = 0;
-            s.nacc = (int)(loff & 31u);
-            s.wp = sS + (loff >> 5);
-            s.first = true;
-            ec_pack_block(sC[tid], diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
-            s.finish();
-        } else {
-            PackSink<false> s;
-            s.acc = 0;
-            s.nacc = (int)(loff & 31u);
-            s.wp = slot + (loff >> 5);
-            s.first = true;
-            ec_pack_block(sC[tid], diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
-            s.finish();
-        }
+        PackSink<false> s;
+        s.acc = 0;
+        s.nacc = (int)(loff & 31u);
+        s.wp = slot + (loff >> 5);
+        s.first = true;
+        ec_pack_block(sC[tid], diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
+        s.finish();
     }
-    if (!staged) return;
-    __syncthreads();
-    for (uint32_t i = tid; i < nwords; i += NT) slot[i] = sS[i];
 }
 
 /* ---- KC (k_concat_chunks): place every chunk's stream at its global bit offset ---------------

@@ -69,7 +69,7 @@ struct jpgb200_ctx {
     uint32_t *d_tile_ff;
     unsigned long long *d_bit_state, *d_ff_state;
     size_t chain_cap;
-    bool fused_attr_set, k1_attr_set;
+    bool fused_attr_set, k1_attr_set, ke_attr_set;
     bool k1_plain; /* force the non-TMA K1 (tests) */
     bool k1_cta;   /* force the CTA-barrier TMA K1 instead of the warp-autonomous one (tests, A/B runs) */
     unsigned long long *d_tile_base;
@@ -722,12 +722,17 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     e.super_bits = ctx->d_super;
     e.local_off = ctx->d_local_off;
     const unsigned nc = (unsigned)n_chunks(n);
+    if (!ctx->ke_attr_set) {
+        CK(cudaFuncSetAttribute(k_encode_chunks<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<0>::BYTES));
+        CK(cudaFuncSetAttribute(k_encode_chunks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<1>::BYTES));
+        ctx->ke_attr_set = true;
+    }
     {
         LaunchScope ls(ctx, KI_KE);
         if (ratio == 0)
-            k_encode_chunks<0><<<nc, EcCfg<0>::NT, 0, ctx->stream>>>(e, ctx->d_hbits, ctx->d_huff);
+            k_encode_chunks<0><<<nc, EcCfg<0>::NT, KeSmem<0>::BYTES, ctx->stream>>>(e, ctx->d_huff);
         else
-            k_encode_chunks<1><<<nc, EcCfg<1>::NT, 0, ctx->stream>>>(e, ctx->d_hbits, ctx->d_huff);
+            k_encode_chunks<1><<<nc, EcCfg<1>::NT, KeSmem<1>::BYTES, ctx->stream>>>(e, ctx->d_huff);
     }
     CK(cudaGetLastError());
     ctx->have_bits = true;
