@@ -45,7 +45,7 @@ extern "C" {
 #define JPGB200_SYM_REF 0           /* AC histogram index run|size (src/huffman.c:218)          */
 #define JPGB200_SYM_SPEC 1          /* (run<<4)|size                                            */
 
-#define JPGB200_NUM_KERNELS 6 /* K1 transform, K35 fused entropy; staged: K3 block bits, K5 pack, K6 count, K6 scatter */
+#define JPGB200_NUM_KERNELS 5 /* K1 transform, K35 fused entropy; staged: KE encode chunks, KF count 0xFF, KS scatter */
 
 typedef struct jpgb200_ctx jpgb200_ctx;
 

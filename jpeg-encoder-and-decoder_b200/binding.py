@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libjpgb200.so")
 
 DC_REF, DC_SPEC = 0, 1
 SYM_REF, SYM_SPEC = 0, 1
-NUM_KERNELS = 6
+NUM_KERNELS = 5
 
 ERR_NO_DEVICE, ERR_BAD_DIMS, ERR_BAD_QUALITY, ERR_CUDA, ERR_OUT_TOO_SMALL, ERR_BAD_ARG, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
 

@@ -590,83 +590,5 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k_encode_chunks(const KePara
     }
 }
 
-/* ---- KC (k_concat_chunks): place every chunk's stream at its global bit offset ---------------
- * g0(chunk) = bit_base + sum of the totals of all earlier chunks, added up from the two-level
- * sums (at most n_chunks/64 + 63 numbers per CTA: no scan kernel, no chain between CTAs).
- * The chunk's words are funnel-shifted by g0 & 31 into the un-stuffed stream; only a chunk's
- * first and last word, which its neighbours also write, are OR-ed (the stream buffer is
- * all-zero on entry: K6 clears every line it consumes).  The last chunk completes the final
- * byte with 1-bits (T.81 F.1.2.3) and publishes the totals. */
-struct KcParams {
-    const uint32_t *tmp;
-    long long slot_words, n_chunks;
-    const uint32_t *cta_bits, *super_bits;
-    unsigned long long bit_base; /* global bit offset of this band (multi-GPU) */
-    int is_last_band;
-    uint32_t *ubuf;
-    unsigned long long ubuf_cap_bytes;
-    EncState *st;
-    int tile_bytes;
-};
-
-#define KC_THREADS 256
-__global__ void __launch_bounds__(KC_THREADS) k_concat_chunks(const KcParams q)
-{
-    __shared__ unsigned long long sPart[KC_THREADS / 32];
-    const int tid = threadIdx.x;
-    const long long chunk = blockIdx.x;
-    const uint32_t tbits = q.cta_bits[chunk];
-    unsigned long long part = 0ull;
-    {
-        const long long sup = chunk >> EC_SUPER_SHIFT;
-        for (long long i = tid; i < sup; i += KC_THREADS) part += q.super_bits[i];
-        for (long long i = (sup << EC_SUPER_SHIFT) + tid; i < chunk; i += KC_THREADS) part += q.cta_bits[i];
-    }
-#pragma unroll
-    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
-    if ((tid & 31) == 0) sPart[tid >> 5] = part;
-    __syncthreads();
-    unsigned long long g0 = q.bit_base;
-#pragma unroll
-    for (int i = 0; i < KC_THREADS / 32; i++) g0 += sPart[i];
-    const bool fits = ((g0 + tbits + 7ull) >> 3) + 64ull <= q.ubuf_cap_bytes; /* only trips on corrupted lengths */
-    const bool last_chunk = (chunk == q.n_chunks - 1);
-    if (last_chunk && tid == 0) {
-        const unsigned long long all = g0 - q.bit_base + tbits;
-        EncState *st = q.st;
-        st->total_bits = fits ? all : 0ull;
-        st->nbytes = fits ? (all + 7) >> 3 : 0ull;
-        st->n_tiles = (st->nbytes + (unsigned long long)q.tile_bytes - 1) / (unsigned long long)q.tile_bytes;
-        st->total_ff = 0;
-        st->out_len = 0;
-        st->error = fits ? 0 : 1;
-    }
-    const uint32_t *slot = q.tmp + chunk * q.slot_words;
-    const uint32_t nin = (tbits + 31u) >> 5;
-    if (!fits) return;
-    const uint32_t sh = (uint32_t)(g0 & 31ull);
-    uint32_t pad = 0;
-    if (last_chunk && q.is_last_band) pad = (8u - (uint32_t)((g0 + tbits) & 7ull)) & 7u;
-    const uint32_t nout = (sh + tbits + pad + 31u) >> 5;
-    uint32_t *gw = q.ubuf + (g0 >> 5);
-    /* output word i holds chunk bits [32 i - sh, 32 i - sh + 32): the low sh bits of input word
-     * i-1 and the high 32-sh bits of input word i (numeric big-endian values) */
-    for (uint32_t i = tid; i < nout; i += KC_THREADS) {
-        const uint32_t lo = (i < nin) ? __byte_perm(slot[i], 0, 0x0123) : 0u;
-        const uint32_t hi = (i >= 1 && i - 1 < nin) ? __byte_perm(slot[i - 1], 0, 0x0123) : 0u;
-        uint32_t v = sh ? ((hi << (32 - sh)) | (lo >> sh)) : lo;
-        if (pad && i == nout - 1) {
-            const uint32_t endbit = (sh + tbits) - 32u * i; /* valid bits of the last word, 1..32 */
-            v |= (pad >= 32u - 0u ? 0u : (((1u << pad) - 1u) << (32u - endbit - pad)));
-        }
-        const uint32_t be = __byte_perm(v, 0, 0x0123);
-        if (i == 0 || i == nout - 1) {
-            if (be) atomicOr(gw + i, be);
-        } else {
-            gw[i] = be;
-        }
-    }
-}
-
 }  // namespace jpgb200
 #endif

@@ -8,9 +8,10 @@
  *   KE k_encode_chunks  per-block code lengths and the bit pack, chunk-locally: coefficients are
  *                     read once; every chunk's stream goes to its own slot, its length into
  *                     two-level sums (the device-wide exclusive prefix sum of bit offsets)
- *   KC k_concat_chunks  chunk streams funnel-shifted to their global bit offsets
- *   K6 k6_count / k6_scatter  0xFF00 stuffing by a second length/offset scan (two-level sums),
- *                     JFIF header, EOI and length word
+ *   KF k_count_ff     a warp per chunk: global bit offset from the two-level sums, the chunk's
+ *                     bytes on the global byte grid, 0xFF count -> second pair of two-level sums
+ *   KS k_scatter      a warp per chunk: 0xFF00-stuffed bytes straight to their final position
+ *                     (the second length/offset scan), JFIF header, EOI and length word
  * There is no CPU arithmetic path in this library.
  */
 #include <cuda_runtime.h>
@@ -28,14 +29,14 @@
 #include "jpgb200_tables.h"
 #include "k1_transform.cuh"
 #include "k1_warp.cuh"
-#include "stuffing.cuh"
+#include "tail.cuh"
 #include "taps.cuh"
 
 using namespace jpgb200;
 
-enum { KI_K1 = 0, KI_K35, KI_KE, KI_KC, KI_K6COUNT, KI_K6SCATTER };
-static const char *kKernelNames[JPGB200_NUM_KERNELS] = {"k1_transform",    "k35_entropy", "k_encode_chunks",
-                                                        "k_concat_chunks", "k6_count",    "k6_scatter"};
+enum { KI_K1 = 0, KI_K35, KI_KE, KI_KF, KI_KS };
+static const char *kKernelNames[JPGB200_NUM_KERNELS] = {"k1_transform", "k35_entropy", "k_encode_chunks", "k_count_ff",
+                                                        "k_scatter"};
 
 struct EvPair {
     int k;
@@ -62,18 +63,14 @@ struct jpgb200_ctx {
     size_t n_super_bits, n_super_ff;
     unsigned long long *d_cta_base;
     size_t cta_cap;
-    uint32_t *d_ubuf;
-    size_t ubuf_cap;
+    uint32_t *d_cta_ff; /* [n_chunks] 0xFF bytes owned by every chunk (KF) */
     uint32_t *d_tmp; /* chunk-local streams written by KE, one slot per chunk */
     size_t tmp_cap;
-    uint32_t *d_tile_ff;
     unsigned long long *d_bit_state, *d_ff_state;
     size_t chain_cap;
     bool fused_attr_set, k1_attr_set, ke_attr_set;
     bool k1_plain; /* force the non-TMA K1 (tests) */
     bool k1_cta;   /* force the CTA-barrier TMA K1 instead of the warp-autonomous one (tests, A/B runs) */
-    unsigned long long *d_tile_base;
-    size_t tile_cap, tile_bytes;
     EncState *d_state;
     uint8_t *d_header;
     int hdr_w, hdr_h, hdr_q, hdr_ratio, hdr_len;
@@ -345,7 +342,7 @@ extern "C" void jpgb200_destroy(jpgb200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {ctx->d_huff,     ctx->d_hbits, ctx->d_scan_order, ctx->d_planes[0], ctx->d_planes[1], ctx->d_zz,   ctx->d_local_off,
-                    ctx->d_cta_bits, ctx->d_super, ctx->d_cta_base,   ctx->d_ubuf,      ctx->d_tmp,       ctx->d_tile_ff,   ctx->d_tile_base,
+                    ctx->d_cta_bits, ctx->d_super, ctx->d_cta_base,   ctx->d_cta_ff,    ctx->d_tmp,
                     ctx->d_state,    ctx->d_bit_state, ctx->d_ff_state, ctx->d_header,     ctx->d_out[0],    ctx->d_out[1],    ctx->d_len,  ctx->d_dc,
                     ctx->d_tile_sum, ctx->d_freq};
     for (void *p : ptrs)
@@ -539,6 +536,10 @@ static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_
         }
         if ((rc = grow(ctx, &ctx->d_cta_bits, &c1, nc * 4))) return rc;
         if ((rc = grow(ctx, &ctx->d_cta_base, &c2, nc * 8))) return rc;
+        if (ctx->d_cta_ff) CK(cudaFree(ctx->d_cta_ff));
+        ctx->d_cta_ff = NULL;
+        size_t c3 = 0;
+        if ((rc = grow(ctx, &ctx->d_cta_ff, &c3, nc * 4))) return rc;
         ctx->cta_cap = nc * 8;
     }
     if (ctx->chain_cap < nc || !ctx->d_bit_state) {
@@ -556,34 +557,9 @@ static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_
         CK(cudaMemsetAsync(ctx->d_ff_state, 0, c2, ctx->stream));
         ctx->chain_cap = c1 / 8;
     }
-    /* worst case 1658 bits per block (20-bit DC + 63 x 26-bit AC) */
-    const size_t ub = (size_t)nb * 208 + 65536;
-    {
-        const uint32_t *before = ctx->d_ubuf;
-        const size_t cap_before = ctx->ubuf_cap;
-        if ((rc = grow(ctx, &ctx->d_ubuf, &ctx->ubuf_cap, ub))) return rc;
-        if (ctx->d_ubuf != before || ctx->ubuf_cap != cap_before) /* K5's invariant: all-zero on entry */
-            CK(cudaMemsetAsync(ctx->d_ubuf, 0, ctx->ubuf_cap, ctx->stream));
-    }
     if ((rc = grow(ctx, &ctx->d_tmp, &ctx->tmp_cap, nc * (size_t)slot_words(n) * 4))) return rc;
-    const size_t nt = ctx->ubuf_cap / K6_TILE + 2;
-    if (ctx->tile_cap < nt || !ctx->d_tile_ff) {
-        size_t c1 = 0, c2 = 0;
-        if (ctx->d_tile_ff) {
-            CK(cudaStreamSynchronize(ctx->stream));
-            CK(cudaFree(ctx->d_tile_ff));
-            CK(cudaFree(ctx->d_tile_base));
-            ctx->d_tile_ff = NULL;
-            ctx->d_tile_base = NULL;
-        }
-        if ((rc = grow(ctx, &ctx->d_tile_ff, &c1, nt * 4))) return rc;
-        if ((rc = grow(ctx, &ctx->d_tile_base, &c2, nt * 8))) return rc;
-        CK(cudaMemsetAsync(ctx->d_tile_base, 0, c2, ctx->stream));
-        ctx->tile_bytes = c2;
-        ctx->tile_cap = nt;
-    }
     {
-        const size_t nsb = nc / 64 + 2, nsf = ctx->tile_cap / 64 + 2;
+        const size_t nsb = nc / 64 + 2, nsf = nc / 64 + 2;
         if (!ctx->d_super || ctx->n_super_bits < nsb || ctx->n_super_ff < nsf) {
             if (ctx->d_super) {
                 CK(cudaStreamSynchronize(ctx->stream));
@@ -739,52 +715,48 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     return JPGB200_OK;
 }
 
-/* KC: chunk streams -> the un-stuffed stream at their global bit offsets */
-static int launch_concat(jpgb200_ctx *ctx, const long long n[3], unsigned long long bit_base, int is_last_band)
+/* KF + KS: chunk streams -> stuffed bytes at d_out (+ header, EOI, length word) */
+static int launch_tail(jpgb200_ctx *ctx, const long long n[3], unsigned bit_phase, unsigned carry, int is_last_band,
+                       int header_len, int write_eoi, uint8_t *d_out, size_t cap, unsigned long long *len_out)
 {
-    KcParams q;
+    TailParams q;
     q.tmp = ctx->d_tmp;
     q.slot_words = slot_words(n);
     q.n_chunks = n_chunks(n);
     q.cta_bits = ctx->d_cta_bits;
     q.super_bits = ctx->d_super;
-    q.bit_base = bit_base;
+    q.cta_ff = ctx->d_cta_ff;
+    q.super_ff = ctx->d_super + ctx->n_super_bits;
+    q.bit_phase = bit_phase;
+    q.carry = carry;
     q.is_last_band = is_last_band;
-    q.ubuf = ctx->d_ubuf;
-    q.ubuf_cap_bytes = (unsigned long long)ctx->ubuf_cap;
+    q.header = ctx->d_header;
+    q.header_len = header_len;
+    q.out = d_out;
+    q.cap = (unsigned long long)cap;
+    q.len_out = len_out;
+    q.write_eoi = write_eoi;
     q.st = ctx->d_state;
-    q.tile_bytes = K6_TILE;
+    const unsigned grid = (unsigned)((q.n_chunks + TAIL_WARPS - 1) / TAIL_WARPS);
     {
-        LaunchScope ls(ctx, KI_KC);
-        k_concat_chunks<<<(unsigned)q.n_chunks, KC_THREADS, 0, ctx->stream>>>(q);
+        LaunchScope ls(ctx, KI_KF);
+        k_count_ff<<<grid, TAIL_THREADS, 0, ctx->stream>>>(q);
+    }
+    CK(cudaGetLastError());
+    {
+        LaunchScope ls(ctx, KI_KS);
+        k_scatter<<<grid, TAIL_THREADS, 0, ctx->stream>>>(q);
     }
     CK(cudaGetLastError());
     return JPGB200_OK;
 }
 
-/* KC + K6: concatenate and stuff into d_out */
 static int launch_pack(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3], uint8_t *d_out, size_t cap,
                        unsigned long long *len_out)
 {
     (void)zz;
     (void)ratio;
-    int rc = launch_concat(ctx, n, 0ull, 1);
-    if (rc) return rc;
-    const unsigned pgrid = (unsigned)ctx->sm_count * 8;
-    {
-        LaunchScope ls(ctx, KI_K6COUNT);
-        k6_count<<<pgrid, K6_THREADS, 0, ctx->stream>>>(reinterpret_cast<const uint4 *>(ctx->d_ubuf), ctx->d_state,
-                                                        ctx->d_tile_ff, ctx->d_super + ctx->n_super_bits, -1ll);
-    }
-    CK(cudaGetLastError());
-    {
-        LaunchScope ls(ctx, KI_K6SCATTER);
-        k6_scatter<<<pgrid, K6_THREADS, 0, ctx->stream>>>(reinterpret_cast<uint4 *>(ctx->d_ubuf), ctx->d_state,
-                                                          ctx->d_tile_ff, ctx->d_super + ctx->n_super_bits, ctx->d_header,
-                                                          ctx->hdr_len, d_out, (unsigned long long)cap, len_out, -1ll, 1);
-    }
-    CK(cudaGetLastError());
-    return JPGB200_OK;
+    return launch_tail(ctx, n, 0u, 0u, 1, ctx->hdr_len, 1, d_out, cap, len_out);
 }
 
 /* K35: the whole entropy stage in one launch (entropy_fused.cuh) */
@@ -955,7 +927,7 @@ extern "C" int jpgb200_encode_rgb(jpgb200_ctx *ctx, const uint8_t *rgb, int w, i
 }
 
 /* Host batch: H2D of frame f+1 and D2H of frame f-1 overlap the kernels of frame f.
- * The stream length reaches the host through mapped pinned memory written by k6_scan, so the
+ * The stream length reaches the host through mapped pinned memory written by k_scatter, so the
  * only host wait per frame is on that frame's own completion event. */
 extern "C" int jpgb200_encode_batch_host(jpgb200_ctx *ctx, const uint8_t *const *frames, int n_frames, int w, int h,
                                          int quality, int ratio, uint8_t *const *outs, size_t cap, size_t *lens)
@@ -1080,18 +1052,21 @@ extern "C" int jpgb200_band_pack(jpgb200_ctx *ctx, int bit_phase, int is_last, u
 {
     if (!ctx || !owned_bytes || !tail_byte || bit_phase < 0 || bit_phase > 7) return JPGB200_ERR_BAD_ARG;
     CK(cudaSetDevice(ctx->device));
-    {
-        int rc = launch_concat(ctx, ctx->band_n, (unsigned long long)bit_phase, is_last ? 1 : 0);
-        if (rc) return rc;
-    }
     const unsigned long long end = (unsigned long long)bit_phase + ctx->band_bits;
     unsigned long long own = end >> 3;
     if (is_last && (end & 7ull)) own += 1; /* the 1-padded final byte */
     *tail_byte = 0;
-    if (!is_last && (end & 7ull))
-        CK(cudaMemcpyAsync(tail_byte, reinterpret_cast<const uint8_t *>(ctx->d_ubuf) + (end >> 3), 1, cudaMemcpyDeviceToHost,
-                           ctx->stream));
-    CK(cudaStreamSynchronize(ctx->stream));
+    if (!is_last && (end & 7ull)) {
+        /* the band's trailing partial byte, which the next band owns */
+        k_band_tail<<<1, 1, 0, ctx->stream>>>(ctx->d_tmp, slot_words(ctx->band_n), n_chunks(ctx->band_n), ctx->d_cta_bits,
+                                              (unsigned)(end & 7ull), ctx->d_len + 1);
+        ctx->launch_total++;
+        CK(cudaGetLastError());
+        unsigned long long t = 0;
+        CK(cudaMemcpyAsync(&t, ctx->d_len + 1, sizeof t, cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        *tail_byte = (uint8_t)t;
+    }
     ctx->band_phase = bit_phase;
     ctx->band_last = is_last ? 1 : 0;
     *owned_bytes = own;
@@ -1106,27 +1081,11 @@ extern "C" int jpgb200_band_finish(jpgb200_ctx *ctx, int carry_byte, uint8_t *d_
     const unsigned long long end = (unsigned long long)ctx->band_phase + ctx->band_bits;
     unsigned long long own = end >> 3;
     if (ctx->band_last && (end & 7ull)) own += 1;
-    if (ctx->band_phase) {
-        k_or_first_byte<<<1, 1, 0, ctx->stream>>>(ctx->d_ubuf, (uint32_t)carry_byte);
-        ctx->launch_total++;
-    }
-    /* K1 cleared the two-level sums at band_transform; K3 used the bit half, this is the 0xFF half */
-    {
-        LaunchScope ls(ctx, KI_K6COUNT);
-        k6_count<<<(unsigned)ctx->sm_count * 8, K6_THREADS, 0, ctx->stream>>>(
-            reinterpret_cast<const uint4 *>(ctx->d_ubuf), ctx->d_state, ctx->d_tile_ff, ctx->d_super + ctx->n_super_bits,
-            (long long)own);
-    }
-    CK(cudaGetLastError());
-    {
-        LaunchScope ls(ctx, KI_K6SCATTER);
-        k6_scatter<<<(unsigned)ctx->sm_count * 8, K6_THREADS, 0, ctx->stream>>>(
-            reinterpret_cast<uint4 *>(ctx->d_ubuf), ctx->d_state, ctx->d_tile_ff, ctx->d_super + ctx->n_super_bits,
-            ctx->d_header, 0, d_segment, (unsigned long long)cap, ctx->d_len, (long long)own, 0);
-    }
-    CK(cudaGetLastError());
-    /* the trailing partial byte belongs to the next band: clear its line for the next encode's K5 */
-    CK(cudaMemsetAsync(reinterpret_cast<uint8_t *>(ctx->d_ubuf) + ((end >> 3) & ~15ull), 0, 32, ctx->stream));
+    /* K1 cleared the two-level sums at band_transform; KE used the bit half, KF uses the 0xFF half.
+     * carry_byte holds the previous band's trailing bits left-aligned: bring them to the low end. */
+    const unsigned carry = ctx->band_phase ? ((unsigned)(carry_byte & 0xff) >> (8 - ctx->band_phase)) : 0u;
+    int rc = launch_tail(ctx, ctx->band_n, (unsigned)ctx->band_phase, carry, ctx->band_last, 0, 0, d_segment, cap, ctx->d_len);
+    if (rc) return rc;
     unsigned long long l = 0;
     CK(cudaMemcpyAsync(&l, ctx->d_len, sizeof l, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));

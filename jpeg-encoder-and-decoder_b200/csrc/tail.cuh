@@ -1,0 +1,239 @@
+/*
+ * Tail of the entropy stage: chunk streams -> the byte-stuffed JFIF scan, with no intermediate
+ * un-stuffed stream in HBM.
+ *
+ *   KF k_count_ff : a warp per chunk.  The chunk's global bit offset g0 is added up from KE's
+ *                   two-level sums (per chunk, per 64 chunks: at most n/64 + 63 numbers, no scan
+ *                   kernel, no chain between CTAs).  The chunk OWNS the stream bytes whose last
+ *                   bit lies in its bit range, [g0 >> 3, (g0 + T) >> 3); their leading g0 & 7 bits
+ *                   are the previous chunk's last bits.  The warp funnel-shifts its chunk to the
+ *                   byte grid, counts the 0xFF bytes among the owned ones and leaves the count per
+ *                   chunk and (atomically) per 64 chunks.
+ *   KS k_scatter  : a warp per chunk again: g0 as above, the number of stuffed zeros before the
+ *                   chunk from the second pair of two-level sums; bytes are written straight to
+ *                   their final position header_len + byte index + zeros before, each 0xFF
+ *                   followed by 0x00 (T.81 F.1.2.3).  Chunk 0 writes the JFIF header, the last
+ *                   chunk completes the final byte with 1-bits, writes EOI and the length word.
+ * This is BASELINE.json's "second length/offset scan" for the 0xFF00 stuffing; the reference
+ * emits no byte stream at all, the oracle for these bytes is
+ * oracle/jpgb200_oracle.c (bw_byte), cross-checked by PIL/OpenCV decodes in tests/.
+ *
+ * MCU-row bands (jpgb200_band_*): bit_base is the band's bit phase (0..7), `carry` holds the
+ * previous band's trailing bits, and a band that is not the last leaves its trailing partial byte
+ * to the next band.
+ */
+#ifndef JPGB200_TAIL_CUH
+#define JPGB200_TAIL_CUH
+
+#include "entropy.cuh"
+
+namespace jpgb200 {
+
+#define TAIL_THREADS 256
+#define TAIL_WARPS (TAIL_THREADS / 32)
+
+struct TailParams {
+    const uint32_t *tmp; /* [n_chunks][slot_words] chunk streams, big-endian words (KE) */
+    long long slot_words, n_chunks;
+    const uint32_t *cta_bits, *super_bits;
+    uint32_t *cta_ff, *super_ff;
+    unsigned int bit_phase; /* global bit offset of chunk 0, 0..7 */
+    unsigned int carry;     /* its low bit_phase bits precede the band's first bit */
+    int is_last_band;
+    /* KS only */
+    const uint8_t *header;
+    int header_len;
+    uint8_t *out;
+    unsigned long long cap;
+    unsigned long long *len_out;
+    int write_eoi;
+    EncState *st;
+};
+
+__device__ __forceinline__ uint32_t be32(uint32_t w) { return __byte_perm(w, 0, 0x0123); }
+
+/* sum over the warp of the two-level sums before `chunk` */
+__device__ __forceinline__ unsigned long long tail_prefix(const uint32_t *cta, const uint32_t *sup, long long chunk, int lane)
+{
+    unsigned long long part = 0ull;
+    const long long s = chunk >> EC_SUPER_SHIFT;
+    for (long long i = lane; i < s; i += 32) part += sup[i];
+    for (long long i = (s << EC_SUPER_SHIFT) + lane; i < chunk; i += 32) part += cta[i];
+#pragma unroll
+    for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
+    return part;
+}
+
+/* geometry of one chunk on the byte grid */
+struct TailGeom {
+    const uint32_t *slot;
+    uint32_t T, nw;             /* bits and words of the chunk stream */
+    uint32_t prev32;            /* the 32 bits in front of the chunk's bit 0 */
+    int d;                      /* local bit offset of the first owned byte: -(g0 & 7) */
+    unsigned long long bA;      /* index of the first owned byte in the un-stuffed stream */
+    uint32_t nB;                /* owned bytes */
+    uint32_t pad;               /* 1-bits completing the final byte (last chunk of the last band) */
+    /* 32 bits of the stream at local bit offset L >= -32; bits at or beyond T read 0, the pad 1 */
+    __device__ __forceinline__ uint32_t get32(int L) const
+    {
+        const int w = L >> 5; /* arithmetic: -1 for L < 0 */
+        const uint32_t sh = (uint32_t)L & 31u;
+        const uint32_t hi = (w < 0) ? prev32 : ((uint32_t)w < nw ? be32(slot[w]) : 0u);
+        const uint32_t lo = ((uint32_t)(w + 1) < nw) ? be32(slot[w + 1]) : 0u;
+        uint32_t v = sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+        if (pad) {
+            const int lo_j = (int)T - L, hi_j = (int)(T + pad) - L; /* window bits [lo_j, hi_j) are pad */
+            if (hi_j > 0 && lo_j < 32) {
+                const uint32_t m_lo = lo_j <= 0 ? 0xffffffffu : (0xffffffffu >> lo_j);
+                const uint32_t m_hi = hi_j >= 32 ? 0u : (0xffffffffu >> hi_j);
+                v |= m_lo & ~m_hi;
+            }
+        }
+        return v;
+    }
+};
+
+__device__ __forceinline__ TailGeom tail_geom(const TailParams &q, long long chunk, int lane)
+{
+    TailGeom g;
+    const unsigned long long g0 = (unsigned long long)q.bit_phase + tail_prefix(q.cta_bits, q.super_bits, chunk, lane);
+    g.T = q.cta_bits[chunk];
+    g.nw = (g.T + 31u) >> 5;
+    g.slot = q.tmp + chunk * q.slot_words;
+    if (chunk == 0) {
+        g.prev32 = q.carry;
+    } else {
+        /* the previous chunk is a full one (>= 64 MCUs x 12 bits): its last 32 bits exist */
+        const uint32_t Tp = q.cta_bits[chunk - 1];
+        const uint32_t *ps = q.tmp + (chunk - 1) * q.slot_words;
+        const uint32_t L = Tp - 32u, w = L >> 5, sh = L & 31u;
+        const uint32_t hi = be32(ps[w]);
+        g.prev32 = sh ? ((hi << sh) | (be32(ps[w + 1]) >> (32u - sh))) : hi;
+    }
+    g.d = -(int)(g0 & 7ull);
+    g.bA = g0 >> 3;
+    const unsigned long long end = g0 + g.T;
+    unsigned long long bB = end >> 3;
+    g.pad = 0;
+    if (chunk == q.n_chunks - 1 && q.is_last_band && (end & 7ull)) {
+        g.pad = 8u - (uint32_t)(end & 7ull);
+        bB += 1;
+    }
+    g.nB = (uint32_t)(bB - g.bA);
+    return g;
+}
+
+/* 0xff per byte of v that is 0xFF, restricted to its first (most significant) nvalid bytes */
+__device__ __forceinline__ uint32_t ff_mask(uint32_t v, int nvalid)
+{
+    uint32_t m = __vcmpeq4(v, 0xffffffffu);
+    if (nvalid < 4) m &= nvalid <= 0 ? 0u : (0xffffffffu << (8 * (4 - nvalid)));
+    return m;
+}
+
+/* ---- KF ---- */
+__global__ void __launch_bounds__(TAIL_THREADS) k_count_ff(const TailParams q)
+{
+    const int lane = threadIdx.x & 31;
+    const long long chunk = (long long)blockIdx.x * TAIL_WARPS + (threadIdx.x >> 5);
+    if (chunk >= q.n_chunks) return;
+    const TailGeom g = tail_geom(q, chunk, lane);
+    const uint32_t groups = (g.nB + 3u) >> 2;
+    uint32_t c = 0;
+    for (uint32_t i = lane; i < groups; i += 32) {
+        const uint32_t v = g.get32(g.d + 32 * (int)i);
+        const int left = (int)(g.nB - 4u * i);
+        c += (uint32_t)__popc(ff_mask(v, left >= 4 ? 4 : left)) >> 3;
+    }
+#pragma unroll
+    for (int dd = 16; dd > 0; dd >>= 1) c += __shfl_xor_sync(0xffffffffu, c, dd);
+    if (lane == 0) {
+        q.cta_ff[chunk] = c;
+        if (c) atomicAdd(&q.super_ff[chunk >> EC_SUPER_SHIFT], c);
+    }
+}
+
+/* ---- KS ---- */
+__global__ void __launch_bounds__(TAIL_THREADS) k_scatter(const TailParams q)
+{
+    const int lane = threadIdx.x & 31;
+    const long long chunk = (long long)blockIdx.x * TAIL_WARPS + (threadIdx.x >> 5);
+    if (chunk >= q.n_chunks) return;
+    const TailGeom g = tail_geom(q, chunk, lane);
+    const unsigned long long ff_before = tail_prefix(q.cta_ff, q.super_ff, chunk, lane);
+    const uint32_t my_ff = q.cta_ff[chunk];
+    const unsigned long long trailer = q.write_eoi ? 2ull : 0ull;
+    unsigned long long P = (unsigned long long)q.header_len + g.bA + ff_before;
+    const bool fits = P + g.nB + my_ff + trailer <= q.cap;
+    const bool last = (chunk == q.n_chunks - 1);
+    if (chunk == 0 && (unsigned long long)q.header_len <= q.cap)
+        for (int i = lane; i < q.header_len; i += 32) q.out[i] = q.header[i];
+    if (fits) {
+        const uint32_t groups = (g.nB + 3u) >> 2;
+        for (uint32_t base = 0; base < groups; base += 32) {
+            const uint32_t i = base + lane;
+            uint32_t v = 0;
+            int nvalid = 0;
+            if (i < groups) {
+                v = g.get32(g.d + 32 * (int)i);
+                const int left = (int)(g.nB - 4u * i);
+                nvalid = left >= 4 ? 4 : left;
+            }
+            const uint32_t m = ff_mask(v, nvalid);
+            const uint32_t n_out = (uint32_t)nvalid + ((uint32_t)__popc(m) >> 3);
+            uint32_t inc = n_out;
+#pragma unroll
+            for (int dd = 1; dd < 32; dd <<= 1) {
+                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, dd);
+                if (lane >= dd) inc += t;
+            }
+            const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+            uint8_t *dst = q.out + P + (inc - n_out);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                if (k < nvalid) {
+                    const uint32_t byte = (v >> (24 - 8 * k)) & 0xffu;
+                    *dst++ = (uint8_t)byte;
+                    if (byte == 0xffu) *dst++ = 0;
+                }
+            }
+            P += total;
+        }
+    }
+    if (last && lane == 0) {
+        const unsigned long long nbytes = g.bA + g.nB;
+        const unsigned long long total_ff = ff_before + my_ff;
+        const unsigned long long out_len = (unsigned long long)q.header_len + nbytes + total_ff + trailer;
+        const bool ok = out_len <= q.cap;
+        if (ok && q.write_eoi) {
+            q.out[out_len - 2] = 0xFF;
+            q.out[out_len - 1] = 0xD9; /* EOI */
+        }
+        EncState *st = q.st;
+        st->nbytes = nbytes;
+        st->total_ff = total_ff;
+        st->out_len = out_len;
+        st->error = ok ? 0 : 1;
+        if (q.len_out) *q.len_out = ok ? out_len : 0ull;
+    }
+}
+
+/* trailing partial byte of a band: the last r bits of its stream, left-aligned in a byte */
+__global__ void k_band_tail(const uint32_t *tmp, long long slot_words, long long n_chunks, const uint32_t *cta_bits,
+                            unsigned int r, unsigned long long *out_byte)
+{
+    const uint32_t T = cta_bits[n_chunks - 1];
+    const uint32_t *slot = tmp + (n_chunks - 1) * slot_words;
+    uint32_t byte = 0;
+    if (r && T >= r) {
+        const uint32_t L = T - r, w = L >> 5, sh = L & 31u, nw = (T + 31u) >> 5;
+        const uint32_t hi = be32(slot[w]);
+        const uint32_t lo = (w + 1 < nw) ? be32(slot[w + 1]) : 0u;
+        const uint32_t v = sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+        byte = (v >> 24) & (0xffu << (8u - r)) & 0xffu;
+    }
+    *out_byte = byte;
+}
+
+}  // namespace jpgb200
+#endif
