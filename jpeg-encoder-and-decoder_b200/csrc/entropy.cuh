@@ -420,6 +420,20 @@ __device__ __forceinline__ unsigned long long cs_lookback(volatile unsigned long
     return excl;
 }
 
+/* the last 32 bits of a stream of `total` bits (right-aligned; fewer if the stream is shorter) */
+__device__ __forceinline__ uint32_t stream_tail32(const uint32_t *words, uint32_t total, bool big_endian)
+{
+    if (total == 0u) return 0u;
+    const uint32_t L = total > 32u ? total - 32u : 0u, w = L >> 5, sh = L & 31u, nw = (total + 31u) >> 5;
+    uint32_t hi = words[w], lo = (w + 1u < nw) ? words[w + 1u] : 0u;
+    if (big_endian) {
+        hi = __byte_perm(hi, 0, 0x0123);
+        lo = __byte_perm(lo, 0, 0x0123);
+    }
+    const uint32_t v = sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+    return total >= 32u ? v : (v >> (32u - total));
+}
+
 /* ---- bit writer into a thread-private region: numeric (MSB-first) 32-bit words; words past
  * the region are dropped but still counted, so the bit length is always right */
 struct PrivSink {
@@ -470,6 +484,7 @@ struct KeParams {
     uint32_t *tmp;         /* [n_chunks][slot_words] chunk-local streams, big-endian words */
     long long slot_words;
     uint32_t *cta_bits;    /* [n_chunks] */
+    uint32_t *cta_tail;    /* [n_chunks] the chunk stream's last 32 bits: the next chunk's leading bits (KF, KS) */
     uint32_t *super_bits;  /* [n_chunks / 64 + 1], cleared by K1 */
     uint32_t *local_off;   /* optional parity tap: [n_mcu*BPM] offset of every block in its chunk */
 };
@@ -572,6 +587,7 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k_encode_chunks(const KePara
         }
         __syncthreads();
         for (uint32_t i = tid; i < nwords; i += NT) slot[i] = __byte_perm(sS[i], 0, 0x0123);
+        if (tid == 0) q.cta_tail[chunk] = stream_tail32(sS, total, false);
         return;
     }
     /* rare: straight into the slot */
@@ -588,6 +604,8 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k_encode_chunks(const KePara
         ec_pack_block(sC[tid], diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
         s.finish();
     }
+    __syncthreads();
+    if (tid == 0) q.cta_tail[chunk] = stream_tail32(slot, total, true);
 }
 
 }  // namespace jpgb200

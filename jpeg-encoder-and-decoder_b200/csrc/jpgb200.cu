@@ -63,7 +63,8 @@ struct jpgb200_ctx {
     size_t n_super_bits, n_super_ff;
     unsigned long long *d_cta_base;
     size_t cta_cap;
-    uint32_t *d_cta_ff; /* [n_chunks] 0xFF bytes owned by every chunk (KF) */
+    uint32_t *d_cta_ff;   /* [n_chunks] 0xFF bytes owned by every chunk (KF) */
+    uint32_t *d_cta_tail; /* [n_chunks] last 32 bits of every chunk stream (KE) */
     uint32_t *d_tmp; /* chunk-local streams written by KE, one slot per chunk */
     size_t tmp_cap;
     unsigned long long *d_bit_state, *d_ff_state;
@@ -342,7 +343,7 @@ extern "C" void jpgb200_destroy(jpgb200_ctx *ctx)
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
     void *ptrs[] = {ctx->d_huff,     ctx->d_hbits, ctx->d_scan_order, ctx->d_planes[0], ctx->d_planes[1], ctx->d_zz,   ctx->d_local_off,
-                    ctx->d_cta_bits, ctx->d_super, ctx->d_cta_base,   ctx->d_cta_ff,    ctx->d_tmp,
+                    ctx->d_cta_bits, ctx->d_super, ctx->d_cta_base,   ctx->d_cta_ff,    ctx->d_cta_tail,  ctx->d_tmp,
                     ctx->d_state,    ctx->d_bit_state, ctx->d_ff_state, ctx->d_header,     ctx->d_out[0],    ctx->d_out[1],    ctx->d_len,  ctx->d_dc,
                     ctx->d_tile_sum, ctx->d_freq};
     for (void *p : ptrs)
@@ -537,9 +538,12 @@ static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_
         if ((rc = grow(ctx, &ctx->d_cta_bits, &c1, nc * 4))) return rc;
         if ((rc = grow(ctx, &ctx->d_cta_base, &c2, nc * 8))) return rc;
         if (ctx->d_cta_ff) CK(cudaFree(ctx->d_cta_ff));
+        if (ctx->d_cta_tail) CK(cudaFree(ctx->d_cta_tail));
         ctx->d_cta_ff = NULL;
-        size_t c3 = 0;
+        ctx->d_cta_tail = NULL;
+        size_t c3 = 0, c4 = 0;
         if ((rc = grow(ctx, &ctx->d_cta_ff, &c3, nc * 4))) return rc;
+        if ((rc = grow(ctx, &ctx->d_cta_tail, &c4, nc * 4))) return rc;
         ctx->cta_cap = nc * 8;
     }
     if (ctx->chain_cap < nc || !ctx->d_bit_state) {
@@ -695,6 +699,7 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     e.tmp = ctx->d_tmp;
     e.slot_words = slot_words(n);
     e.cta_bits = ctx->d_cta_bits;
+    e.cta_tail = ctx->d_cta_tail;
     e.super_bits = ctx->d_super;
     e.local_off = ctx->d_local_off;
     const unsigned nc = (unsigned)n_chunks(n);
@@ -726,6 +731,8 @@ static int launch_tail(jpgb200_ctx *ctx, const long long n[3], unsigned bit_phas
     q.cta_bits = ctx->d_cta_bits;
     q.super_bits = ctx->d_super;
     q.cta_ff = ctx->d_cta_ff;
+    q.cta_tail = ctx->d_cta_tail;
+    q.cta_base = ctx->d_cta_base;
     q.super_ff = ctx->d_super + ctx->n_super_bits;
     q.bit_phase = bit_phase;
     q.carry = carry;

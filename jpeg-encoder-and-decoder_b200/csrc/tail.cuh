@@ -35,8 +35,9 @@ namespace jpgb200 {
 struct TailParams {
     const uint32_t *tmp; /* [n_chunks][slot_words] chunk streams, big-endian words (KE) */
     long long slot_words, n_chunks;
-    const uint32_t *cta_bits, *super_bits;
+    const uint32_t *cta_bits, *super_bits, *cta_tail;
     uint32_t *cta_ff, *super_ff;
+    unsigned long long *cta_base; /* [n_chunks] global bit offset of every chunk: written by KF, read by KS */
     unsigned int bit_phase; /* global bit offset of chunk 0, 0..7 */
     unsigned int carry;     /* its low bit_phase bits precede the band's first bit */
     int is_last_band;
@@ -66,22 +67,41 @@ __device__ __forceinline__ unsigned long long tail_prefix(const uint32_t *cta, c
 
 /* geometry of one chunk on the byte grid */
 struct TailGeom {
-    const uint32_t *slot;
     uint32_t T, nw;             /* bits and words of the chunk stream */
-    uint32_t prev32;            /* the 32 bits in front of the chunk's bit 0 */
     int d;                      /* local bit offset of the first owned byte: -(g0 & 7) */
     unsigned long long bA;      /* index of the first owned byte in the un-stuffed stream */
     uint32_t nB;                /* owned bytes */
     uint32_t pad;               /* 1-bits completing the final byte (last chunk of the last band) */
-    /* 32 bits of the stream at local bit offset L >= -32; bits at or beyond T read 0, the pad 1 */
-    __device__ __forceinline__ uint32_t get32(int L) const
+    __device__ __forceinline__ TailGeom(const TailParams &q, long long chunk, unsigned long long g0, uint32_t T_)
     {
-        const int w = L >> 5; /* arithmetic: -1 for L < 0 */
-        const uint32_t sh = (uint32_t)L & 31u;
-        const uint32_t hi = (w < 0) ? prev32 : ((uint32_t)w < nw ? be32(slot[w]) : 0u);
-        const uint32_t lo = ((uint32_t)(w + 1) < nw) ? be32(slot[w + 1]) : 0u;
-        uint32_t v = sh ? ((hi << sh) | (lo >> (32u - sh))) : hi;
+        T = T_;
+        nw = (T + 31u) >> 5;
+        d = -(int)(g0 & 7ull);
+        bA = g0 >> 3;
+        const unsigned long long end = g0 + T;
+        unsigned long long bB = end >> 3;
+        pad = 0;
+        if (chunk == q.n_chunks - 1 && q.is_last_band && (end & 7ull)) {
+            pad = 8u - (uint32_t)(end & 7ull);
+            bB += 1;
+        }
+        nB = (uint32_t)(bB - bA);
+    }
+    /* Owned bytes 4i..4i+3 = the 32 stream bits at local offset d + 32 i, assembled from the raw
+     * (big-endian) words i-1 and i of the slot -- word -1 being the 32 bits in front of the chunk.
+     * Bits at or beyond T read 0, the pad 1.  The words can be fetched before g0 is known: only the
+     * shift depends on it. */
+    __device__ __forceinline__ uint32_t group(uint32_t i, uint32_t raw_prev, uint32_t raw_cur) const
+    {
+        const uint32_t wc = i < nw ? be32(raw_cur) : 0u;
+        uint32_t v = wc;
+        if (d) {
+            const uint32_t wp = (i == 0u) ? raw_prev : ((i - 1u) < nw ? be32(raw_prev) : 0u);
+            const uint32_t sh = 32u + (uint32_t)d;
+            v = (wp << sh) | (wc >> (32u - sh));
+        }
         if (pad) {
+            const int L = d + 32 * (int)i;
             const int lo_j = (int)T - L, hi_j = (int)(T + pad) - L; /* window bits [lo_j, hi_j) are pad */
             if (hi_j > 0 && lo_j < 32) {
                 const uint32_t m_lo = lo_j <= 0 ? 0xffffffffu : (0xffffffffu >> lo_j);
@@ -93,34 +113,24 @@ struct TailGeom {
     }
 };
 
-__device__ __forceinline__ TailGeom tail_geom(const TailParams &q, long long chunk, int lane)
+/* Batched fetch: TAIL_BATCH rounds of 32 consecutive raw words, all requested before any is used.
+ * Word i-1 of group i is the neighbouring lane's word (shuffle); for lane 0 it is the last word
+ * of the previous round, or, in front of the chunk, the previous chunk's last 32 bits (numeric). */
+#define TAIL_BATCH 4
+__device__ __forceinline__ void tail_fetch(const TailParams &q, const uint32_t *slot, uint32_t base, int lane,
+                                           uint32_t (&rc)[TAIL_BATCH])
 {
-    TailGeom g;
-    const unsigned long long g0 = (unsigned long long)q.bit_phase + tail_prefix(q.cta_bits, q.super_bits, chunk, lane);
-    g.T = q.cta_bits[chunk];
-    g.nw = (g.T + 31u) >> 5;
-    g.slot = q.tmp + chunk * q.slot_words;
-    if (chunk == 0) {
-        g.prev32 = q.carry;
-    } else {
-        /* the previous chunk is a full one (>= 64 MCUs x 12 bits): its last 32 bits exist */
-        const uint32_t Tp = q.cta_bits[chunk - 1];
-        const uint32_t *ps = q.tmp + (chunk - 1) * q.slot_words;
-        const uint32_t L = Tp - 32u, w = L >> 5, sh = L & 31u;
-        const uint32_t hi = be32(ps[w]);
-        g.prev32 = sh ? ((hi << sh) | (be32(ps[w + 1]) >> (32u - sh))) : hi;
+#pragma unroll
+    for (int r = 0; r < TAIL_BATCH; r++) {
+        const uint32_t i = base + 32u * (uint32_t)r + (uint32_t)lane;
+        rc[r] = (long long)i < q.slot_words ? slot[i] : 0u;
     }
-    g.d = -(int)(g0 & 7ull);
-    g.bA = g0 >> 3;
-    const unsigned long long end = g0 + g.T;
-    unsigned long long bB = end >> 3;
-    g.pad = 0;
-    if (chunk == q.n_chunks - 1 && q.is_last_band && (end & 7ull)) {
-        g.pad = 8u - (uint32_t)(end & 7ull);
-        bB += 1;
-    }
-    g.nB = (uint32_t)(bB - g.bA);
-    return g;
+}
+/* raw_prev of this lane for round r; `carry_word` = word (base + 32 r - 1), maintained by the caller */
+__device__ __forceinline__ uint32_t tail_prev(uint32_t cur, uint32_t carry_word, int lane)
+{
+    const uint32_t up = __shfl_up_sync(0xffffffffu, cur, 1);
+    return lane == 0 ? carry_word : up;
 }
 
 /* 0xff per byte of v that is 0xFF, restricted to its first (most significant) nvalid bytes */
@@ -137,18 +147,35 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_count_ff(const TailParams q)
     const int lane = threadIdx.x & 31;
     const long long chunk = (long long)blockIdx.x * TAIL_WARPS + (threadIdx.x >> 5);
     if (chunk >= q.n_chunks) return;
-    const TailGeom g = tail_geom(q, chunk, lane);
+    const uint32_t *slot = q.tmp + chunk * q.slot_words;
+    /* everything this warp needs is requested before anything is waited for */
+    uint32_t rc[TAIL_BATCH];
+    tail_fetch(q, slot, 0u, lane, rc);
+    uint32_t carry_word = chunk == 0 ? q.carry : q.cta_tail[chunk - 1];
+    const uint32_t T = q.cta_bits[chunk];
+    const unsigned long long g0 = (unsigned long long)q.bit_phase + tail_prefix(q.cta_bits, q.super_bits, chunk, lane);
+    const TailGeom g(q, chunk, g0, T);
     const uint32_t groups = (g.nB + 3u) >> 2;
     uint32_t c = 0;
-    for (uint32_t i = lane; i < groups; i += 32) {
-        const uint32_t v = g.get32(g.d + 32 * (int)i);
-        const int left = (int)(g.nB - 4u * i);
-        c += (uint32_t)__popc(ff_mask(v, left >= 4 ? 4 : left)) >> 3;
+    for (uint32_t base = 0; base < groups; base += 32u * TAIL_BATCH) {
+        if (base) tail_fetch(q, slot, base, lane, rc);
+#pragma unroll
+        for (int r = 0; r < TAIL_BATCH; r++) {
+            const uint32_t i = base + 32u * (uint32_t)r + (uint32_t)lane;
+            const uint32_t rp = tail_prev(rc[r], carry_word, lane);
+            carry_word = __shfl_sync(0xffffffffu, rc[r], 31);
+            if (i < groups) {
+                const uint32_t v = g.group(i, rp, rc[r]);
+                const int left = (int)(g.nB - 4u * i);
+                c += (uint32_t)__popc(ff_mask(v, left >= 4 ? 4 : left)) >> 3;
+            }
+        }
     }
 #pragma unroll
     for (int dd = 16; dd > 0; dd >>= 1) c += __shfl_xor_sync(0xffffffffu, c, dd);
     if (lane == 0) {
         q.cta_ff[chunk] = c;
+        q.cta_base[chunk] = g0;
         if (c) atomicAdd(&q.super_ff[chunk >> EC_SUPER_SHIFT], c);
     }
 }
@@ -159,9 +186,15 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_scatter(const TailParams q)
     const int lane = threadIdx.x & 31;
     const long long chunk = (long long)blockIdx.x * TAIL_WARPS + (threadIdx.x >> 5);
     if (chunk >= q.n_chunks) return;
-    const TailGeom g = tail_geom(q, chunk, lane);
-    const unsigned long long ff_before = tail_prefix(q.cta_ff, q.super_ff, chunk, lane);
+    const uint32_t *slot = q.tmp + chunk * q.slot_words;
+    uint32_t rc[TAIL_BATCH];
+    tail_fetch(q, slot, 0u, lane, rc);
+    uint32_t carry_word = chunk == 0 ? q.carry : q.cta_tail[chunk - 1];
+    const uint32_t T = q.cta_bits[chunk];
+    const unsigned long long g0 = q.cta_base[chunk];
     const uint32_t my_ff = q.cta_ff[chunk];
+    const unsigned long long ff_before = tail_prefix(q.cta_ff, q.super_ff, chunk, lane);
+    const TailGeom g(q, chunk, g0, T);
     const unsigned long long trailer = q.write_eoi ? 2ull : 0ull;
     unsigned long long P = (unsigned long long)q.header_len + g.bA + ff_before;
     const bool fits = P + g.nB + my_ff + trailer <= q.cap;
@@ -170,34 +203,41 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_scatter(const TailParams q)
         for (int i = lane; i < q.header_len; i += 32) q.out[i] = q.header[i];
     if (fits) {
         const uint32_t groups = (g.nB + 3u) >> 2;
-        for (uint32_t base = 0; base < groups; base += 32) {
-            const uint32_t i = base + lane;
-            uint32_t v = 0;
-            int nvalid = 0;
-            if (i < groups) {
-                v = g.get32(g.d + 32 * (int)i);
-                const int left = (int)(g.nB - 4u * i);
-                nvalid = left >= 4 ? 4 : left;
-            }
-            const uint32_t m = ff_mask(v, nvalid);
-            const uint32_t n_out = (uint32_t)nvalid + ((uint32_t)__popc(m) >> 3);
-            uint32_t inc = n_out;
+        for (uint32_t base = 0; base < groups; base += 32u * TAIL_BATCH) {
+            if (base) tail_fetch(q, slot, base, lane, rc);
 #pragma unroll
-            for (int dd = 1; dd < 32; dd <<= 1) {
-                const uint32_t t = __shfl_up_sync(0xffffffffu, inc, dd);
-                if (lane >= dd) inc += t;
-            }
-            const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
-            uint8_t *dst = q.out + P + (inc - n_out);
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                if (k < nvalid) {
-                    const uint32_t byte = (v >> (24 - 8 * k)) & 0xffu;
-                    *dst++ = (uint8_t)byte;
-                    if (byte == 0xffu) *dst++ = 0;
+            for (int r = 0; r < TAIL_BATCH; r++) {
+                const uint32_t i = base + 32u * (uint32_t)r + (uint32_t)lane;
+                if (base + 32u * (uint32_t)r >= groups) break; /* warp-uniform */
+                const uint32_t rp = tail_prev(rc[r], carry_word, lane);
+                carry_word = __shfl_sync(0xffffffffu, rc[r], 31);
+                uint32_t v = 0;
+                int nvalid = 0;
+                if (i < groups) {
+                    v = g.group(i, rp, rc[r]);
+                    const int left = (int)(g.nB - 4u * i);
+                    nvalid = left >= 4 ? 4 : left;
                 }
+                const uint32_t m = ff_mask(v, nvalid);
+                const uint32_t n_out = (uint32_t)nvalid + ((uint32_t)__popc(m) >> 3);
+                uint32_t inc = n_out;
+#pragma unroll
+                for (int dd = 1; dd < 32; dd <<= 1) {
+                    const uint32_t t = __shfl_up_sync(0xffffffffu, inc, dd);
+                    if (lane >= dd) inc += t;
+                }
+                const uint32_t total = __shfl_sync(0xffffffffu, inc, 31);
+                uint8_t *dst = q.out + P + (inc - n_out);
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    if (k < nvalid) {
+                        const uint32_t byte = (v >> (24 - 8 * k)) & 0xffu;
+                        *dst++ = (uint8_t)byte;
+                        if (byte == 0xffu) *dst++ = 0;
+                    }
+                }
+                P += total;
             }
-            P += total;
         }
     }
     if (last && lane == 0) {
