@@ -30,6 +30,12 @@ struct HuffDev {
     uint32_t ac[2][256]; /* (code << 8) | code_length ; [lum|chr][(run<<4)|size] */
     uint32_t dc[2][16];  /* (code << 8) | code_length ; [lum|chr][category]     */
 };
+/* KE's pack tables: ((code << category) << 5) | (code_length + category): the code already
+ * shifted to make room for the additional bits, and the total length, in one word */
+struct HuffPack {
+    uint32_t ac[2][256];
+    uint32_t dc[2][16];
+};
 /* count tables: total bits of one symbol incl. its additional bits; the AC table is
  * extended to runs of up to 62 zeros, folding in the ZRL codes a long run needs */
 struct HuffBits {
@@ -118,10 +124,10 @@ __device__ __forceinline__ void cp_async_wait_all()
 /* asynchronous fill of the chunk's coefficient rows.  Rows are component-major (EcMap) and a
  * component's blocks of the chunk are contiguous in HBM, so each component is one linear run of
  * 16-byte chunks: chunk i -> row i/8, column i%8 (rows padded to 144 B in shared memory) */
-template <int RATIO>
+template <int RATIO, int NTH = EcCfg<RATIO>::NT>
 __device__ __forceinline__ void ec_fill(uint4 (*sC)[EC_ROW_CHUNKS], const EcParams &p, long long m0, int tid)
 {
-    constexpr int NT = EcCfg<RATIO>::NT;
+    constexpr int NT = NTH;
     const long long left = p.n_mcu - m0;
     const int nv = left < EC_MCUS ? (int)left : EC_MCUS; /* valid MCUs of this chunk */
     const uint4 *z = reinterpret_cast<const uint4 *>(p.zz);
@@ -129,7 +135,7 @@ __device__ __forceinline__ void ec_fill(uint4 (*sC)[EC_ROW_CHUNKS], const EcPara
         const int n0 = (RATIO == 0 ? nv : 2 * nv) * 8;
         const uint4 *src = z + (RATIO == 0 ? m0 : 2 * m0) * 8;
 #pragma unroll
-        for (int k = 0; k < (RATIO == 0 ? 3 : 4); k++) {
+        for (int k = 0; k < ((RATIO == 0 ? 64 : 128) * 8 + NT - 1) / NT; k++) {
             const int i = k * NT + tid;
             if (i < n0) cp_async16(&sC[i >> 3][i & 7], src + i);
         }
@@ -138,7 +144,7 @@ __device__ __forceinline__ void ec_fill(uint4 (*sC)[EC_ROW_CHUNKS], const EcPara
         const int n1 = nv * 8, r1 = (RATIO == 0 ? 64 : 128);
         const uint4 *s1 = z + (p.coff1 + m0) * 8, *s2 = z + (p.coff2 + m0) * 8;
 #pragma unroll
-        for (int k = 0; k < (RATIO == 0 ? 3 : 2); k++) {
+        for (int k = 0; k < (64 * 8 + NT - 1) / NT; k++) {
             const int i = k * NT + tid;
             if (i < n1) {
                 cp_async16(&sC[r1 + (i >> 3)][i & 7], s1 + i);
@@ -321,6 +327,94 @@ __device__ __forceinline__ void ec_pack_block(const uint4 *row, int diff, const 
     }
 }
 
+/* ---- block coder in two parts ---------------------------------------------------------------
+ * A luma block carries about three times the non-zero coefficients of a chroma block, and a
+ * thread's coding loop runs as long as its block is busy; so KE codes a luma block with TWO
+ * threads.  Both see the same non-zero mask M (bit k = coefficient k != 0, k = 1..63) and derive
+ * the same split position S from it: part 0 codes the DC difference and the coefficients 1..S,
+ * part 1 the coefficients S+1..63 and the end-of-block code -- its first run length starts at
+ * the last non-zero of part 0.  The two bit strings simply follow each other in the stream.
+ * S is the first of a few fixed positions that gives part 0 at least half of the non-zeros. */
+__device__ __forceinline__ int ec_split(unsigned long long M)
+{
+    const int n = __popcll(M);
+    if (n < 4) return 63; /* not worth splitting: part 0 codes everything */
+    const int half = (n + 1) >> 1;
+    if (__popcll(M & 0x3eull) >= half) return 5;
+    if (__popcll(M & 0x3feull) >= half) return 9;
+    if (__popcll(M & 0x7ffeull) >= half) return 14;
+    if (__popcll(M & 0xffffffeull) >= half) return 27;
+    return 40;
+}
+
+/* WHOLE = true: one thread codes the entire block (chroma); otherwise part 0 or 1 of a split block,
+ * coded by two ADJACENT lanes which each build one half of the non-zero mask and swap them.
+ * Tables are HuffPack words. */
+template <bool WHOLE, class Sink>
+__device__ __forceinline__ void ec_pack_part(const uint4 *row, int diff, int part, const uint32_t *sAc, const uint32_t *sDc,
+                                             Sink &s)
+{
+    uint32_t mm[2];
+    int prev = 0;
+    bool eob = true;
+    if (WHOLE) {
+        ec_nz_masks(row, mm[0], mm[1]);
+    } else {
+        const uint32_t mine_half = part == 0 ? ((nz_mask16(row[0], row[1]) | (nz_mask16(row[2], row[3]) << 16)) & ~1u)
+                                             : (nz_mask16(row[4], row[5]) | (nz_mask16(row[6], row[7]) << 16));
+        const uint32_t other_half = __shfl_xor_sync(__activemask(), mine_half, 1);
+        const unsigned long long M = part == 0 ? ((unsigned long long)mine_half | ((unsigned long long)other_half << 32))
+                                               : ((unsigned long long)other_half | ((unsigned long long)mine_half << 32));
+        const int S = ec_split(M);
+        const unsigned long long lowmask = S >= 63 ? ~0ull : ((2ull << S) - 1ull);
+        unsigned long long mine;
+        if (part == 0) {
+            mine = M & lowmask;
+            eob = (S >= 63);
+        } else {
+            mine = M & ~lowmask;
+            const unsigned long long before = M & lowmask;
+            prev = before ? 63 - __clzll((long long)before) : 0;
+            if (S >= 63) return; /* part 0 coded the whole block */
+        }
+        mm[0] = (uint32_t)mine;
+        mm[1] = (uint32_t)(mine >> 32);
+    }
+    if (WHOLE || part == 0) {
+        const int cat = diff == 0 ? 0 : msb_index((uint32_t)abs(diff)) + 1;
+        const uint32_t e = sDc[cat];
+        const uint32_t extra = (uint32_t)(diff - (diff < 0 ? 1 : 0)) & ((1u << cat) - 1u);
+        s.put((e >> 5) | extra, (int)(e & 31u));
+    }
+#pragma unroll
+    for (int half = 0; half < 2; half++) {
+        uint32_t mr = __brev(mm[half]); /* bit 31 = position 0: one FLO per coefficient, no BREV */
+        while (mr) {
+            const int pos = __clz((int)mr);
+            mr ^= 0x80000000u >> pos;
+            const int k = half * 32 + pos;
+            const int v = ec_coef(row, k);
+            int run = k - prev - 1;
+            prev = k;
+            if (run > 15) { /* rare: one ZRL code per 16 zeros */
+                const uint32_t zrl = sAc[0xF0];
+                do {
+                    s.put(zrl >> 5, (int)(zrl & 31u));
+                    run -= 16;
+                } while (run > 15);
+            }
+            const int cat = msb_index((uint32_t)abs(v)) + 1;
+            const uint32_t e = sAc[(run << 4) | cat];
+            const uint32_t extra = (uint32_t)(v - (v < 0 ? 1 : 0)) & ((1u << cat) - 1u);
+            s.put((e >> 5) | extra, (int)(e & 31u));
+        }
+    }
+    if (eob && prev != 63) {
+        const uint32_t eobc = sAc[0x00];
+        s.put(eobc >> 5, (int)(eobc & 31u));
+    }
+}
+
 /* exclusive scan of one uint32 per thread over the CTA; returns this thread's offset and
  * the CTA total through `total` */
 template <int NT>
@@ -489,31 +583,83 @@ struct KeParams {
     uint32_t *local_off;   /* optional parity tap: [n_mcu*BPM] offset of every block in its chunk */
 };
 
+/* KE's threads: "entries" in component-major order -- two per luma block (part 0, part 1), one per
+ * chroma block -- so that warps are component-pure; e_local is the entry's position in stream
+ * order inside the chunk (4:4:4: Y.0 Y.1 Cb Cr per MCU; 4:2:2: Y0.0 Y0.1 Y1.0 Y1.1 Cb Cr). */
 template <int RATIO>
-struct KeSmem {
-    static const int NT = EcCfg<RATIO>::NT;
-    static const int PRIV = (RATIO == 0) ? 16 : 12;  /* words of private stream per block */
-    static const int PSTRIDE = PRIV + 1;             /* odd: lanes hit distinct banks */
-    static const int ROW_BYTES = NT * EC_ROW_CHUNKS * 16;
-    static const int STAGE_WORDS = ROW_BYTES / 4;    /* the chunk stream reuses the coefficient rows */
+struct KeCfg {
+    static const int ROWS = EcCfg<RATIO>::NT;            /* coefficient rows (blocks) per chunk */
+    static const int NY = (RATIO == 0) ? 64 : 128;       /* luma blocks per chunk */
+    static const int NT = 2 * NY + 128;                  /* threads = entries: 256 / 384 */
+    static const int EPM = (RATIO == 0) ? 4 : 6;         /* entries per MCU */
+    static const int PRIV = 12;                          /* words of private stream per entry */
+    static const int PSTRIDE = PRIV + 1;                 /* odd: lanes hit distinct banks */
+    static const int ROW_BYTES = ROWS * EC_ROW_CHUNKS * 16;
+    static const int STAGE_WORDS = ROW_BYTES / 4;        /* the chunk stream reuses the coefficient rows */
     static const int OFF_PRIV = ROW_BYTES;
     static const int OFF_H = OFF_PRIV + NT * PSTRIDE * 4;
-    static const int OFF_OFF = OFF_H + (int)sizeof(HuffDev);
+    static const int OFF_OFF = OFF_H + (int)sizeof(HuffPack);
     static const int OFF_WARP = OFF_OFF + NT * 4;
     static const int OFF_FLAG = OFF_WARP + (NT / 32) * 4;
     static const int BYTES = OFF_FLAG + 16;
 };
+template <int RATIO>
+using KeSmem = KeCfg<RATIO>;
 
 template <int RATIO>
-__global__ void __launch_bounds__(EcCfg<RATIO>::NT) k_encode_chunks(const KeParams q, const HuffDev *huff)
+struct KeMap {
+    int row, part, comp, e_local, blk_local; /* blk_local: the block's position in scan order, -1 for part 1 */
+    bool valid, first_of_comp, luma;
+    long long gabs; /* block index inside zz */
+    __device__ __forceinline__ KeMap(const EcParams &p, long long m0, int tid)
+    {
+        constexpr int NY = KeCfg<RATIO>::NY;
+        if (tid < 2 * NY) {
+            luma = true;
+            comp = 0;
+            row = tid >> 1;
+            part = tid & 1;
+            const int m = (RATIO == 0) ? row : (row >> 1);
+            e_local = (RATIO == 0) ? 4 * m + part : 6 * m + 2 * (row & 1) + part;
+            blk_local = part ? -1 : ((RATIO == 0) ? 3 * m : 4 * m + (row & 1));
+            gabs = ((RATIO == 0) ? m0 : 2 * m0) + row;
+            valid = (m0 + m) < p.n_mcu;
+            first_of_comp = (row == 0);
+        } else {
+            luma = false;
+            part = 0;
+            const int c = (tid - 2 * NY) >> 6, m = (tid - 2 * NY) & 63;
+            comp = 1 + c;
+            row = NY + 64 * c + m;
+            e_local = (RATIO == 0) ? 4 * m + 2 + c : 6 * m + 4 + c;
+            blk_local = (RATIO == 0) ? 3 * m + 1 + c : 4 * m + 2 + c;
+            gabs = m0 + m + (c == 0 ? p.coff1 : p.coff2);
+            valid = (m0 + m) < p.n_mcu;
+            first_of_comp = (m == 0);
+        }
+    }
+};
+
+template <int RATIO, class Sink>
+__device__ __forceinline__ void ke_code(const uint4 (*sC)[EC_ROW_CHUNKS], const KeMap<RATIO> &mp, int diff, const HuffPack &sH,
+                                        Sink &s)
 {
-    constexpr int BPM = EcCfg<RATIO>::BPM, NT = EcCfg<RATIO>::NT;
-    typedef KeSmem<RATIO> L;
+    if (mp.luma)
+        ec_pack_part<false>(sC[mp.row], diff, mp.part, sH.ac[0], sH.dc[0], s);
+    else
+        ec_pack_part<true>(sC[mp.row], diff, 0, sH.ac[1], sH.dc[1], s);
+}
+
+template <int RATIO>
+__global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KeParams q, const HuffPack *huff)
+{
+    constexpr int BPM = EcCfg<RATIO>::BPM, NT = KeCfg<RATIO>::NT;
+    typedef KeCfg<RATIO> L;
     extern __shared__ __align__(16) unsigned char ke_smem[];
     uint4(*sC)[EC_ROW_CHUNKS] = reinterpret_cast<uint4(*)[EC_ROW_CHUNKS]>(ke_smem);
     uint32_t *sS = reinterpret_cast<uint32_t *>(ke_smem); /* chunk stream, over the rows */
     uint32_t *sP = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_PRIV);
-    HuffDev &sH = *reinterpret_cast<HuffDev *>(ke_smem + L::OFF_H);
+    HuffPack &sH = *reinterpret_cast<HuffPack *>(ke_smem + L::OFF_H);
     uint32_t *sOff = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_OFF);
     uint32_t *sWarp = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_WARP);
     uint32_t *sFlag = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_FLAG);
@@ -530,39 +676,48 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k_encode_chunks(const KePara
     p.dc_pred[1] = q.dc_pred[1];
     p.dc_pred[2] = q.dc_pred[2];
 
-    ec_fill<RATIO>(sC, p, m0, tid);
+    ec_fill<RATIO, NT>(sC, p, m0, tid);
     ec_load_table(&sH, huff, tid);
-    const EcMap<RATIO> mp(p, m0, tid);
+    const KeMap<RATIO> mp(p, m0, tid);
     if (tid == 0) *sFlag = 0u;
     cp_async_wait_all();
     __syncthreads();
 
-    /* code every block once, privately */
+    /* code every entry once, privately */
     uint32_t nbits = 0;
     int diff = 0;
     uint32_t *priv = sP + tid * L::PSTRIDE;
     if (mp.valid) {
-        const int pred = ec_dc_pred<RATIO>(sC, p, m0, tid, mp);
-        diff = (int)(short)(sC[tid][0].x & 0xffffu) - pred;
+        if (mp.part == 0) {
+            int pred;
+            if (!mp.first_of_comp)
+                pred = (int)(short)(sC[mp.row - 1][0].x & 0xffffu);
+            else if (m0 == 0)
+                pred = p.dc_pred[mp.comp];
+            else
+                pred = (int)p.zz[(mp.gabs - 1) * 64];
+            diff = (int)(short)(sC[mp.row][0].x & 0xffffu) - pred;
+        }
         PrivSink s;
         s.acc = 0;
         s.nacc = 0;
         s.wp = priv;
         s.end = priv + L::PRIV;
         s.nwords = 0;
-        ec_pack_block(sC[tid], diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
+        ke_code<RATIO>(sC, mp, diff, sH, s);
         nbits = s.finish();
         if (nbits > (uint32_t)L::PRIV * 32u) *sFlag = 1u;
     }
-    sOff[mp.s_local] = nbits; /* scan (MCU-interleaved) order */
+    sOff[mp.e_local] = nbits; /* stream order */
     __syncthreads();
     uint32_t total;
     {
         const uint32_t ex = cta_exclusive_scan<NT>(sOff[tid], sWarp, tid, total);
         __syncthreads();
         sOff[tid] = ex;
-        if (q.local_off && m0 * BPM + tid < q.n_mcu * BPM) q.local_off[m0 * BPM + tid] = ex;
     }
+    __syncthreads();
+    if (q.local_off && mp.valid && mp.blk_local >= 0) q.local_off[m0 * BPM + mp.blk_local] = sOff[mp.e_local];
     if (tid == 0) {
         q.cta_bits[chunk] = total;
         atomicAdd(&q.super_bits[chunk >> EC_SUPER_SHIFT], total);
@@ -570,12 +725,13 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k_encode_chunks(const KePara
     const uint32_t nwords = (total + 31u) >> 5;
     const bool staged = (*sFlag == 0u) && nwords < (uint32_t)L::STAGE_WORDS; /* word [nwords] may receive an empty OR */
     uint32_t *slot = q.tmp + chunk * q.slot_words;
+    const uint32_t loff = sOff[mp.e_local];
     if (staged) {
-        /* the coefficient rows are dead (every block is coded): the chunk stream takes their place */
+        /* the coefficient rows are dead (every entry is coded): the chunk stream takes their place */
+        __syncthreads();
         for (uint32_t i = tid; i < nwords + 1u; i += NT) sS[i] = 0u;
         __syncthreads();
         if (mp.valid) {
-            const uint32_t loff = sOff[mp.s_local];
             const uint32_t sh = loff & 31u, nw = (nbits + 31u) >> 5;
             uint32_t *dst = sS + (loff >> 5);
             for (uint32_t i = 0; i < nw; i++) {
@@ -591,17 +747,15 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k_encode_chunks(const KePara
         return;
     }
     /* rare: straight into the slot */
-    __syncthreads();
     for (uint32_t i = tid; i < nwords; i += NT) slot[i] = 0u;
     __syncthreads();
     if (mp.valid) {
-        const uint32_t loff = sOff[mp.s_local];
         PackSink<false> s;
         s.acc = 0;
         s.nacc = (int)(loff & 31u);
         s.wp = slot + (loff >> 5);
         s.first = true;
-        ec_pack_block(sC[tid], diff, sH.ac[mp.comp ? 1 : 0], sH.dc[mp.comp ? 1 : 0], s);
+        ke_code<RATIO>(sC, mp, diff, sH, s);
         s.finish();
     }
     __syncthreads();

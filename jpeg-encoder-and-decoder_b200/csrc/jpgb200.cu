@@ -48,6 +48,7 @@ struct jpgb200_ctx {
     int sm_count;
     cudaStream_t own_stream, stream, copy_in, copy_out;
     HuffDev *d_huff;
+    HuffPack *d_hpack;
     HuffBits *d_hbits;
     int *d_scan_order;
     uint8_t oob[24];
@@ -185,6 +186,23 @@ static void build_huff(HuffDev *h)
     }
 }
 
+/* KE's tables: code pre-shifted by the category, total length in the low 5 bits */
+static void build_huff_pack(const HuffDev *h, HuffPack *k)
+{
+    memset(k, 0, sizeof *k);
+    for (int t = 0; t < 2; t++) {
+        for (int c = 0; c < 16; c++) {
+            const uint32_t e = h->dc[t][c], len = e & 0xff;
+            if (len) k->dc[t][c] = (((e >> 8) << c) << 5) | (len + (uint32_t)c);
+        }
+        for (int sym = 0; sym < 256; sym++) {
+            const uint32_t e = h->ac[t][sym], len = e & 0xff;
+            const uint32_t c = (sym == 0xF0) ? 0u : (uint32_t)(sym & 15);
+            if (len) k->ac[t][sym] = (((e >> 8) << c) << 5) | (len + c);
+        }
+    }
+}
+
 /* total bits per symbol (code + additional bits), AC extended to runs of 0..62 zeros */
 static void build_huff_bits(const HuffDev *h, HuffBits *b)
 {
@@ -309,6 +327,8 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
     HuffBits hb;
     build_huff(&hh);
     build_huff_bits(&hh, &hb);
+    HuffPack hp;
+    build_huff_pack(&hh, &hp);
     int rc = [&]() -> int {
         CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
@@ -316,6 +336,8 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         ctx->stream = ctx->own_stream;
         CK(cudaMalloc(&ctx->d_huff, sizeof(HuffDev)));
         CK(cudaMemcpy(ctx->d_huff, &hh, sizeof hh, cudaMemcpyHostToDevice));
+        CK(cudaMalloc(&ctx->d_hpack, sizeof(HuffPack)));
+        CK(cudaMemcpy(ctx->d_hpack, &hp, sizeof hp, cudaMemcpyHostToDevice));
         CK(cudaMalloc(&ctx->d_hbits, sizeof(HuffBits)));
         CK(cudaMemcpy(ctx->d_hbits, &hb, sizeof hb, cudaMemcpyHostToDevice));
         CK(cudaMalloc(&ctx->d_scan_order, 64 * sizeof(int)));
@@ -342,7 +364,7 @@ extern "C" void jpgb200_destroy(jpgb200_ctx *ctx)
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
-    void *ptrs[] = {ctx->d_huff,     ctx->d_hbits, ctx->d_scan_order, ctx->d_planes[0], ctx->d_planes[1], ctx->d_zz,   ctx->d_local_off,
+    void *ptrs[] = {ctx->d_huff,     ctx->d_hpack, ctx->d_hbits, ctx->d_scan_order, ctx->d_planes[0], ctx->d_planes[1], ctx->d_zz,   ctx->d_local_off,
                     ctx->d_cta_bits, ctx->d_super, ctx->d_cta_base,   ctx->d_cta_ff,    ctx->d_cta_tail,  ctx->d_tmp,
                     ctx->d_state,    ctx->d_bit_state, ctx->d_ff_state, ctx->d_header,     ctx->d_out[0],    ctx->d_out[1],    ctx->d_len,  ctx->d_dc,
                     ctx->d_tile_sum, ctx->d_freq};
@@ -711,9 +733,9 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     {
         LaunchScope ls(ctx, KI_KE);
         if (ratio == 0)
-            k_encode_chunks<0><<<nc, EcCfg<0>::NT, KeSmem<0>::BYTES, ctx->stream>>>(e, ctx->d_huff);
+            k_encode_chunks<0><<<nc, KeCfg<0>::NT, KeSmem<0>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
         else
-            k_encode_chunks<1><<<nc, EcCfg<1>::NT, KeSmem<1>::BYTES, ctx->stream>>>(e, ctx->d_huff);
+            k_encode_chunks<1><<<nc, KeCfg<1>::NT, KeSmem<1>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
     }
     CK(cudaGetLastError());
     ctx->have_bits = true;
