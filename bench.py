@@ -4,8 +4,8 @@ configuration: a batch of 8K (7680x4320) RGB frames, 4:4:4, quality 75, one imag
 GPU (configs[3]); frames are independent, so ranks shard the batch with no collective
 ("scaling": "weak": every GPU encodes FRAMES frames per step).
 
-A step = one pass of the whole hot path (K1 transform, K3 bit lengths, K4 scan, K5 pack,
-K6 stuffing -> complete JFIF streams) over one batch of synthetic frames.
+A step = one pass of the whole hot path (K1 transform, KE chunk encode, KF 0xFF count, KS stuffed
+scatter -> complete JFIF streams) over one batch of synthetic frames.
   value : frames are resident in HBM when the timed region starts (device-resident encode)
   e2e   : the same batch through the C-ABI host-buffer call (jpgb200_encode_batch_host):
           pinned host frames in, JFIF bytes out, H2D and D2H inside the timed region
@@ -306,7 +306,7 @@ def run_b200(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k1_transform<0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k1_transform_ws<0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": 9 * NPX, "avg_launch_us": k1_avg_s * 1e6,
                 "kernel_ms_per_step": {k: v[0] / args.steps for k, v in ktimes.items()}}
