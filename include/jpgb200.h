@@ -69,6 +69,16 @@ int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on);
  * width % 16 == 8); 2 = the earlier TMA kernel whose phases are separated by CTA barriers.
  * Identical results. */
 int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on);
+/* Huffman tables: 0 (default) = the standard Annex-K tables the reference carries in
+ * src/headers/tables.h:37-72; 1 = per-image optimal tables built from the image's own symbol
+ * histograms by T.81 Annex K.2 -- what construct_huffman_table (src/huffman.c:76-180) sets out to
+ * do and never finishes.  Costs one host synchronisation per image
+ * (histograms to the host, tables and DHT segments back); streams are 10-15 % smaller and decode
+ * to the same pixels. */
+int jpgb200_set_optimized_huffman(jpgb200_ctx *ctx, int on);
+/* BITS (nr[t][1..16]) and HUFFVAL of the tables used by the last encode; t = 0 DC lum, 1 DC chr,
+ * 2 AC lum, 3 AC chr */
+int jpgb200_huffman_specs(const jpgb200_ctx *ctx, uint8_t nr[4][17], uint8_t vals[4][256], int nvals[4]);
 /* The 8 bytes the reference reads in front of each plane buffer for block W/8-1
  * (src/preprocess.c:159,206-210): oob[0..7]=r, [8..15]=g, [16..23]=b.
  * Default: zeros. */

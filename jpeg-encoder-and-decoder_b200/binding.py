@@ -33,6 +33,8 @@ _SIGS = {
     "jpgb200_set_oob_bytes": (C.c_int, [_vp, _vp]),
     "jpgb200_set_staged_entropy": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_plain_transform": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_set_optimized_huffman": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_huffman_specs": (C.c_int, [_vp, _vp, _vp, _vp]),
     "jpgb200_encode_planar": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "jpgb200_encode_rgb": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "jpgb200_encode_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
@@ -161,6 +163,17 @@ class Encoder:
 
     def set_staged_entropy(self, on):
         self._ck(lib().jpgb200_set_staged_entropy(self._h, 1 if on else 0))
+
+    def set_optimized_huffman(self, on):
+        self._ck(lib().jpgb200_set_optimized_huffman(self._h, 1 if on else 0))
+
+    def huffman_specs(self):
+        """(nr[4][17], vals[4][256], nvals[4]) of the tables the last encode used"""
+        nr = np.zeros((4, 17), dtype=np.uint8)
+        vals = np.zeros((4, 256), dtype=np.uint8)
+        nv = np.zeros(4, dtype=np.int32)
+        self._ck(lib().jpgb200_huffman_specs(self._h, nr.ctypes.data, vals.ctypes.data, nv.ctypes.data))
+        return nr, vals, nv
 
     def set_plain_transform(self, on):
         self._ck(lib().jpgb200_set_plain_transform(self._h, int(on)))

@@ -34,6 +34,12 @@
 
 using namespace jpgb200;
 
+struct HuffSpecs {
+    uint8_t nr[4][17];
+    uint8_t vals[4][256];
+    int nvals[4];
+};
+
 enum { KI_K1 = 0, KI_K35, KI_KE, KI_KF, KI_KS };
 static const char *kKernelNames[JPGB200_NUM_KERNELS] = {"k1_transform", "k35_entropy", "k_encode_chunks", "k_count_ff",
                                                         "k_scatter"};
@@ -93,6 +99,11 @@ struct jpgb200_ctx {
     unsigned long long band_bits;
     int band_phase, band_last, band_ratio, band_pred[3];
     long long band_n[3];
+    bool opt_huff;       /* per-image optimal Huffman tables (T.81 K.2) instead of the tables.h ones */
+    HuffSpecs specs;     /* tables in use: DHT segments and code tables derive from them */
+    HuffDev std_huff;    /* the tables.h tables, kept for switching back */
+    HuffBits std_hbits;
+    HuffPack std_hpack;
     bool legacy_entropy; /* staged K3/K4/K5/K6 pipeline instead of the fused K35 (tests) */
     /* quantiser cache */
     int q_cached;
@@ -163,12 +174,82 @@ extern "C" long long jpgb200_num_blocks(int w, int h, int ratio, long long n[3])
     return ny + 2 * nc;
 }
 
-/* canonical codes from the tables.h specs (T.81 Annex C) */
-static void build_huff(HuffDev *h)
+/* BITS / HUFFVAL of the four tables (0 DC lum, 1 DC chr, 2 AC lum, 3 AC chr) */
+static void standard_specs(HuffSpecs *sp)
+{
+    memset(sp, 0, sizeof *sp);
+    for (int t = 0; t < 4; t++) {
+        HuffSpec s = huff_spec(t);
+        memcpy(sp->nr[t], s.nr, 17);
+        memcpy(sp->vals[t], s.vals, (size_t)s.nvals);
+        sp->nvals[t] = s.nvals;
+    }
+}
+
+/* Per-image optimal table: T.81 Annex K.2 (figures K.1-K.4), the procedure the reference's
+ * construct_huffman_table sets out to follow and never finishes (src/huffman.c:76-180,
+ * SURVEY.md F2).  freq[257], freq[256] = 1 reserves the all-ones code (src/huffman.c:54). */
+static void optimal_spec(const int32_t *freq_in, uint8_t nr[17], uint8_t vals[256], int *nvals)
+{
+    long long freq[257];
+    int size[257], next[257], bits[34];
+    for (int i = 0; i < 257; i++) {
+        freq[i] = freq_in[i];
+        size[i] = 0;
+        next[i] = -1;
+    }
+    freq[256] = 1;
+    for (;;) {
+        int a = -1, b = -1; /* the two least frequent values; on ties the larger value */
+        for (int i = 0; i < 257; i++)
+            if (freq[i] > 0 && (a < 0 || freq[i] <= freq[a])) a = i;
+        for (int i = 0; i < 257; i++)
+            if (i != a && freq[i] > 0 && (b < 0 || freq[i] <= freq[b])) b = i;
+        if (b < 0) break;
+        freq[a] += freq[b];
+        freq[b] = 0;
+        for (size[a]++; next[a] >= 0;) {
+            a = next[a];
+            size[a]++;
+        }
+        next[a] = b;
+        for (size[b]++; next[b] >= 0;) {
+            b = next[b];
+            size[b]++;
+        }
+    }
+    memset(bits, 0, sizeof bits);
+    for (int i = 0; i < 257; i++)
+        if (size[i] > 0) bits[size[i] > 32 ? 32 : size[i]]++;
+    int i = 32;
+    for (; i > 16; i--)
+        while (bits[i] > 0) { /* K.3: no code longer than 16 bits */
+            int j = i - 2;
+            while (bits[j] == 0) j--;
+            bits[i] -= 2;
+            bits[i - 1] += 1;
+            bits[j + 1] += 2;
+            bits[j] -= 1;
+        }
+    while (bits[i] == 0) i--;
+    bits[i]--; /* drop the reserved code point */
+    memset(nr, 0, 17);
+    for (int l = 1; l <= 16; l++) nr[l] = (uint8_t)bits[l];
+    int k = 0;
+    for (int l = 1; l <= 32; l++)
+        for (int j = 0; j < 256; j++)
+            if (size[j] == l) vals[k++] = (uint8_t)j;
+    *nvals = k;
+}
+
+/* canonical codes from the specs (T.81 Annex C) */
+static void build_huff(const HuffSpecs *specs, HuffDev *h)
 {
     memset(h, 0, sizeof *h);
     for (int t = 0; t < 4; t++) {
-        HuffSpec sp = huff_spec(t);
+        struct {
+            const uint8_t *nr, *vals;
+        } sp = {specs->nr[t], specs->vals[t]};
         unsigned code = 0;
         int k = 0;
         for (int l = 1; l <= 16; l++) {
@@ -229,7 +310,16 @@ static size_t put16(uint8_t *o, size_t p, unsigned v)
 
 /* JFIF marker segments SOI..SOS (T.81 Annex B).  The DQT carries, at zig-zag
  * position of (v,u), the divisor the reference actually applies there: T'[u][v]. */
+static int jfif_header_specs(int w, int h, int quality, int ratio, const HuffSpecs *specs, uint8_t *o, size_t cap, size_t *len);
+
 extern "C" int jpgb200_jfif_header(int w, int h, int quality, int ratio, uint8_t *o, size_t cap, size_t *len)
+{
+    HuffSpecs sp;
+    standard_specs(&sp);
+    return jfif_header_specs(w, h, quality, ratio, &sp, o, cap, len);
+}
+
+static int jfif_header_specs(int w, int h, int quality, int ratio, const HuffSpecs *specs, uint8_t *o, size_t cap, size_t *len)
 {
     int lum[64], chr[64];
     if (jpgb200_num_blocks(w, h, ratio, NULL) < 0) return JPGB200_ERR_BAD_DIMS;
@@ -270,14 +360,14 @@ extern "C" int jpgb200_jfif_header(int w, int h, int quality, int ratio, uint8_t
     static const int order[4] = {0, 2, 1, 3};
     static const uint8_t tcth[4] = {0x00, 0x10, 0x01, 0x11};
     for (int i = 0; i < 4; i++) {
-        HuffSpec sp = huff_spec(order[i]);
+        const int t = order[i];
         p = put16(o, p, 0xFFC4);
-        p = put16(o, p, (unsigned)(2 + 1 + 16 + sp.nvals));
+        p = put16(o, p, (unsigned)(2 + 1 + 16 + specs->nvals[t]));
         o[p++] = tcth[i];
-        memcpy(o + p, sp.nr + 1, 16);
+        memcpy(o + p, specs->nr[t] + 1, 16);
         p += 16;
-        memcpy(o + p, sp.vals, (size_t)sp.nvals);
-        p += (size_t)sp.nvals;
+        memcpy(o + p, specs->vals[t], (size_t)specs->nvals[t]);
+        p += (size_t)specs->nvals[t];
     }
     p = put16(o, p, 0xFFDA);
     p = put16(o, p, 12);
@@ -323,12 +413,16 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         return JPGB200_ERR_NO_DEVICE;
     }
     ctx->sm_count = prop.multiProcessorCount;
+    standard_specs(&ctx->specs);
     HuffDev hh;
     HuffBits hb;
-    build_huff(&hh);
+    build_huff(&ctx->specs, &hh);
     build_huff_bits(&hh, &hb);
     HuffPack hp;
     build_huff_pack(&hh, &hp);
+    ctx->std_huff = hh;
+    ctx->std_hbits = hb;
+    ctx->std_hpack = hp;
     int rc = [&]() -> int {
         CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
@@ -411,6 +505,32 @@ extern "C" int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;
     ctx->legacy_entropy = on != 0;
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_set_optimized_huffman(jpgb200_ctx *ctx, int on)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const bool was = ctx->opt_huff;
+    ctx->opt_huff = on != 0;
+    if (was && !ctx->opt_huff) { /* back to the tables.h tables */
+        standard_specs(&ctx->specs);
+        CK(cudaMemcpyAsync(ctx->d_huff, &ctx->std_huff, sizeof(HuffDev), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_hbits, &ctx->std_hbits, sizeof(HuffBits), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaMemcpyAsync(ctx->d_hpack, &ctx->std_hpack, sizeof(HuffPack), cudaMemcpyHostToDevice, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        ctx->hdr_w = -1;
+    }
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_huffman_specs(const jpgb200_ctx *ctx, uint8_t nr[4][17], uint8_t vals[4][256], int nvals[4])
+{
+    if (!ctx || !nr || !vals || !nvals) return JPGB200_ERR_BAD_ARG;
+    memcpy(nr, ctx->specs.nr, sizeof ctx->specs.nr);
+    memcpy(vals, ctx->specs.vals, sizeof ctx->specs.vals);
+    memcpy(nvals, ctx->specs.nvals, sizeof ctx->specs.nvals);
     return JPGB200_OK;
 }
 
@@ -614,7 +734,7 @@ static int ensure_tables(jpgb200_ctx *ctx, int w, int h, int quality, int ratio)
     if (ctx->hdr_w != w || ctx->hdr_h != h || ctx->hdr_q != quality || ctx->hdr_ratio != ratio) {
         uint8_t hdr[1024];
         size_t len = 0;
-        int rc = jpgb200_jfif_header(w, h, quality, ratio, hdr, sizeof hdr, &len);
+        int rc = jfif_header_specs(w, h, quality, ratio, &ctx->specs, hdr, sizeof hdr, &len);
         if (rc) return rc;
         CK(cudaMemcpyAsync(ctx->d_header, hdr, len, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream)); /* hdr is a stack buffer */
@@ -830,6 +950,38 @@ static int launch_fused(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lo
     return JPGB200_OK;
 }
 
+/* code tables and header of ctx->specs -> device (synchronises: the sources are stack buffers) */
+static int upload_tables(jpgb200_ctx *ctx)
+{
+    HuffDev hh;
+    HuffBits hb;
+    HuffPack hp;
+    build_huff(&ctx->specs, &hh);
+    build_huff_bits(&hh, &hb);
+    build_huff_pack(&hh, &hp);
+    CK(cudaMemcpyAsync(ctx->d_huff, &hh, sizeof hh, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_hbits, &hb, sizeof hb, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ctx->d_hpack, &hp, sizeof hp, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    ctx->hdr_w = -1; /* the cached header carries the old DHT segments */
+    return JPGB200_OK;
+}
+
+static int device_histograms(jpgb200_ctx *ctx, int dc_mode, int sym_mode, int32_t *freq);
+
+/* histograms of the coefficients just produced (KH) -> host-side T.81 K.2
+ * -> DHT segments + code tables for this image.  One host synchronisation per image. */
+static int optimise_tables(jpgb200_ctx *ctx, int w, int h, int quality, int ratio)
+{
+    int32_t freq[4 * 257];
+    int rc = device_histograms(ctx, JPGB200_DC_SPEC_DIFF, JPGB200_SYM_SPEC, freq);
+    if (rc) return rc;
+    static const int src[4] = {0, 2, 1, 3}; /* histogram order: lum_DC, lum_AC, chrom_DC, chrom_AC */
+    for (int t = 0; t < 4; t++) optimal_spec(freq + 257 * src[t], ctx->specs.nr[t], ctx->specs.vals[t], &ctx->specs.nvals[t]);
+    if ((rc = upload_tables(ctx))) return rc;
+    return ensure_tables(ctx, w, h, quality, ratio);
+}
+
 static int encode_core(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w, int h,
                        int quality, int ratio, uint8_t *d_out, size_t cap, unsigned long long *len_out)
 {
@@ -846,6 +998,10 @@ static int encode_core(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g,
     if ((rc = launch_k1(ctx, d_r, d_g, d_b, w, h, ratio, n, 1, 0, ctx->d_zz, 0, 0))) return rc;
     if (d_out) {
         ctx->have_bits = false;
+        if (ctx->opt_huff) {
+            if ((rc = optimise_tables(ctx, w, h, quality, ratio))) return rc;
+            /* the histogram kernels ran after K1 cleared the two-level sums: still clear */
+        }
         if (ctx->legacy_entropy) {
             if ((rc = launch_bits(ctx, ctx->d_zz, ratio, n))) return rc;
             return launch_pack(ctx, ctx->d_zz, ratio, n, d_out, cap, len_out);
@@ -1189,6 +1345,11 @@ extern "C" int jpgb200_histograms(jpgb200_ctx *ctx, int dc_mode, int sym_mode, i
     if (!ctx || !freq || (dc_mode != 0 && dc_mode != 1) || (sym_mode != 0 && sym_mode != 1)) return JPGB200_ERR_BAD_ARG;
     if (!ctx->d_zz || ctx->n[0] == 0) return JPGB200_ERR_BAD_ARG;
     CK(cudaSetDevice(ctx->device));
+    return device_histograms(ctx, dc_mode, sym_mode, freq);
+}
+
+static int device_histograms(jpgb200_ctx *ctx, int dc_mode, int sym_mode, int32_t *freq)
+{
     int rc = run_dc_sequence(ctx, dc_mode);
     if (rc) return rc;
     CK(cudaMemsetAsync(ctx->d_freq, 0, 4 * 257 * sizeof(int), ctx->stream));
@@ -1425,6 +1586,7 @@ extern "C" int jpgb200_encode_coefficients(jpgb200_ctx *ctx, const int16_t *zz, 
     ctx->ratio = ratio;
     memcpy(ctx->n, n, sizeof n);
     CK(cudaMemcpyAsync(ctx->d_zz, zz, (size_t)(n[0] + n[1] + n[2]) * 128, cudaMemcpyHostToDevice, ctx->stream));
+    if (ctx->opt_huff && (rc = optimise_tables(ctx, w, h, quality, ratio))) return rc;
     if (ctx->legacy_entropy) {
         if ((rc = launch_bits(ctx, ctx->d_zz, ratio, n, NULL, true))) return rc;
         if ((rc = launch_pack(ctx, ctx->d_zz, ratio, n, ctx->d_out[0], cap, ctx->d_len))) return rc;

@@ -22,6 +22,11 @@ jpgb200_ctx *host_ctx(void)
             fprintf(stderr, "jpgb200: %s\n", jpgb200_strerror(rc));
             g_ctx = NULL;
         } else {
+            /* JPGB200_OPTIMIZED_HUFFMAN=1: per-image optimal tables -- what the reference's
+             * construct_huffman_table (src/huffman.c:76-180) sets out to build -- instead of the
+             * standard tables of src/headers/tables.h */
+            const char *o = getenv("JPGB200_OPTIMIZED_HUFFMAN");
+            if (o && atoi(o) != 0) jpgb200_set_optimized_huffman(g_ctx, 1);
             atexit(release);
         }
     }

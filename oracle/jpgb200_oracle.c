@@ -438,6 +438,109 @@ static void huffset_init(HuffSet *h)
     for (int t = 0; t < 4; t++) orc_huffman_table(t, h->code[t], h->len[t]);
 }
 
+/* canonical codes (T.81 Annex C) of caller-supplied specs */
+static void huffset_from_specs(HuffSet *h, const OrcHuffSpecs *sp)
+{
+    memset(h, 0, sizeof *h);
+    for (int t = 0; t < 4; t++) {
+        unsigned c = 0;
+        int k = 0;
+        for (int l = 1; l <= 16; l++) {
+            for (int i = 0; i < sp->nr[t][l]; i++) {
+                h->code[t][sp->vals[t][k]] = (uint16_t)c;
+                h->len[t][sp->vals[t][k]] = (uint8_t)l;
+                c++;
+                k++;
+            }
+            c <<= 1;
+        }
+    }
+}
+
+void orc_specs_standard(OrcHuffSpecs *sp)
+{
+    memset(sp, 0, sizeof *sp);
+    for (int t = 0; t < 4; t++) {
+        const uint8_t *nr, *vals;
+        int nvals;
+        huff_spec(t, &nr, &vals, &nvals);
+        memcpy(sp->nr[t], nr, 17);
+        memcpy(sp->vals[t], vals, (size_t)nvals);
+        sp->nvals[t] = nvals;
+    }
+}
+
+/* ---- optimal tables: T.81 Annex K.2, the procedure construct_huffman_table
+ * (src/huffman.c:76-180) attempts and never finishes.  freq[257] with
+ * freq[256] = 1 reserving the all-ones code point (src/huffman.c:54); returns BITS (nr[1..16])
+ * and HUFFVAL.  Figures K.1 (code sizes), K.2 (count), K.3 (limit to 16 bits), K.4 (sort). */
+static void optimal_table(const int32_t freq_in[257], uint8_t nr[17], uint8_t vals[256], int *nvals)
+{
+    long freq[257];
+    int codesize[257], others[257], bits[34];
+    for (int i = 0; i < 257; i++) {
+        freq[i] = freq_in[i];
+        codesize[i] = 0;
+        others[i] = -1;
+    }
+    freq[256] = 1;
+    for (;;) {
+        /* least frequency > 0, ties -> largest value; then the next least */
+        int v1 = -1, v2 = -1;
+        for (int i = 0; i < 257; i++)
+            if (freq[i] > 0 && (v1 < 0 || freq[i] <= freq[v1])) v1 = i;
+        for (int i = 0; i < 257; i++)
+            if (i != v1 && freq[i] > 0 && (v2 < 0 || freq[i] <= freq[v2])) v2 = i;
+        if (v2 < 0) break;
+        freq[v1] += freq[v2];
+        freq[v2] = 0;
+        codesize[v1]++;
+        while (others[v1] >= 0) {
+            v1 = others[v1];
+            codesize[v1]++;
+        }
+        others[v1] = v2;
+        codesize[v2]++;
+        while (others[v2] >= 0) {
+            v2 = others[v2];
+            codesize[v2]++;
+        }
+    }
+    memset(bits, 0, sizeof bits);
+    for (int i = 0; i < 257; i++)
+        if (codesize[i] > 0) bits[codesize[i] > 32 ? 32 : codesize[i]]++;
+    int i = 32;
+    while (i > 16) {
+        while (bits[i] > 0) {
+            int j = i - 2;
+            while (bits[j] == 0) j--;
+            bits[i] -= 2;
+            bits[i - 1] += 1;
+            bits[j + 1] += 2;
+            bits[j] -= 1;
+        }
+        i--;
+    }
+    while (bits[i] == 0) i--;
+    bits[i]--; /* the reserved code point */
+    memset(nr, 0, 17);
+    for (int l = 1; l <= 16; l++) nr[l] = (uint8_t)bits[l];
+    int k = 0;
+    for (int l = 1; l <= 32; l++)
+        for (int j = 0; j < 256; j++)
+            if (codesize[j] == l) vals[k++] = (uint8_t)j;
+    *nvals = k;
+}
+
+/* freq[4][257] in the order lum_DC, lum_AC, chrom_DC, chrom_AC (orc_histograms, SPEC modes);
+ * specs in the order 0 DC lum, 1 DC chr, 2 AC lum, 3 AC chr */
+void orc_specs_optimal(const int32_t *freq, OrcHuffSpecs *sp)
+{
+    static const int src[4] = {0, 2, 1, 3};
+    memset(sp, 0, sizeof *sp);
+    for (int t = 0; t < 4; t++) optimal_table(freq + 257 * src[t], sp->nr[t], sp->vals[t], &sp->nvals[t]);
+}
+
 /* additional bits: v>0 -> low cat bits of v; v<0 -> low cat bits of v-1 (T.81 F.1.2.1) */
 static inline uint32_t extra_bits(int v, int cat) { return (uint32_t)(v < 0 ? v - 1 : v) & ((1u << cat) - 1u); }
 
@@ -484,11 +587,20 @@ static uint32_t encode_block(BitW *w, const HuffSet *h, const int16_t *zz, int p
 
 /* Walk blocks in interleaved MCU order (T.81 A.2): 4:4:4 -> Y Cb Cr per MCU;
  * 4:2:2 -> Y(2m) Y(2m+1) Cb(m) Cr(m). */
+static uint64_t walk_scan_h(BitW *w, const HuffSet *hs, const int16_t *zz, int wpx, int hpx, int sample_ratio,
+                            uint32_t *bits_out);
 static uint64_t walk_scan(BitW *w, const int16_t *zz, int wpx, int hpx, int sample_ratio, uint32_t *bits_out)
 {
     HuffSet h;
-    long n[3];
     huffset_init(&h);
+    return walk_scan_h(w, &h, zz, wpx, hpx, sample_ratio, bits_out);
+}
+
+static uint64_t walk_scan_h(BitW *w, const HuffSet *hs, const int16_t *zz, int wpx, int hpx, int sample_ratio,
+                            uint32_t *bits_out)
+{
+    const HuffSet h = *hs;
+    long n[3];
     if (orc_block_counts(wpx, hpx, sample_ratio, n)) return 0;
     const int16_t *zy = zz, *zcb = zz + n[0] * 64, *zcr = zz + (n[0] + n[1]) * 64;
     int pred[3] = {0, 0, 0};
@@ -535,6 +647,18 @@ size_t orc_encode_scan(const int16_t *zz, int w, int h, int sample_ratio, uint8_
     return bw.overflow ? 0 : bw.pos;
 }
 
+size_t orc_encode_scan_specs(const int16_t *zz, int w, int h, int sample_ratio, const OrcHuffSpecs *sp, uint8_t *out,
+                             size_t cap, uint64_t *total_bits)
+{
+    HuffSet hs;
+    huffset_from_specs(&hs, sp);
+    BitW bw = {out, cap, 0, 0, 0, 0, 0, 0};
+    uint64_t t = walk_scan_h(&bw, &hs, zz, w, h, sample_ratio, NULL);
+    bw_flush(&bw);
+    if (total_bits) *total_bits = t;
+    return bw.overflow ? 0 : bw.pos;
+}
+
 /* The same bit string without byte stuffing and without 1-padding (a trailing partial byte
  * is zero-filled): what the GPU's un-stuffed buffer holds; used by the band-partition tests. */
 size_t orc_encode_scan_raw(const int16_t *zz, int w, int h, int sample_ratio, uint8_t *out, size_t cap,
@@ -565,6 +689,13 @@ static size_t put16(uint8_t *o, size_t p, unsigned v)
 }
 
 size_t orc_jfif_header(int w, int h, int quality, int sample_ratio, uint8_t *o, size_t cap)
+{
+    OrcHuffSpecs sp;
+    orc_specs_standard(&sp);
+    return orc_jfif_header_specs(w, h, quality, sample_ratio, &sp, o, cap);
+}
+
+size_t orc_jfif_header_specs(int w, int h, int quality, int sample_ratio, const OrcHuffSpecs *sp, uint8_t *o, size_t cap)
 {
     int lum[64], chr[64];
     size_t p = 0;
@@ -616,9 +747,8 @@ size_t orc_jfif_header(int w, int h, int quality, int sample_ratio, uint8_t *o, 
     static const int order[4] = {0, 2, 1, 3};
     static const uint8_t tcth[4] = {0x00, 0x10, 0x01, 0x11};
     for (int i = 0; i < 4; i++) {
-        const uint8_t *nr, *vals;
-        int nvals;
-        huff_spec(order[i], &nr, &vals, &nvals);
+        const uint8_t *nr = sp->nr[order[i]], *vals = sp->vals[order[i]];
+        const int nvals = sp->nvals[order[i]];
         p = put16(o, p, 0xFFC4);
         p = put16(o, p, (unsigned)(2 + 1 + 16 + nvals));
         o[p++] = tcth[i];

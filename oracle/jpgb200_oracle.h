@@ -68,6 +68,22 @@ void orc_histograms(const int16_t *zz, const long n[3], int dc_mode, int sym_mod
  * 3 AC chr.  code[256], len[256] (len 0 = symbol absent). */
 void orc_huffman_table(int table, uint16_t code[256], uint8_t len[256]);
 
+/* Huffman table specifications (BITS = nr[1..16], HUFFVAL = vals) in the order 0 DC lum,
+ * 1 DC chr, 2 AC lum, 3 AC chr: the standard ones of src/headers/tables.h, or per-image optimal
+ * ones built by T.81 Annex K.2 from the SPEC-mode histograms (freq[4][257] in orc_histograms'
+ * order) -- what construct_huffman_table (src/huffman.c:76-180) set out to do. */
+typedef struct {
+    uint8_t nr[4][17];
+    uint8_t vals[4][256];
+    int nvals[4];
+} OrcHuffSpecs;
+void orc_specs_standard(OrcHuffSpecs *sp);
+void orc_specs_optimal(const int32_t *freq, OrcHuffSpecs *sp);
+size_t orc_encode_scan_specs(const int16_t *zz, int w, int h, int sample_ratio, const OrcHuffSpecs *sp, uint8_t *out,
+                             size_t cap, uint64_t *total_bits);
+size_t orc_jfif_header_specs(int w, int h, int quality, int sample_ratio, const OrcHuffSpecs *sp, uint8_t *out,
+                             size_t cap);
+
 /* Entropy-coded segment only (SPEC DC + SPEC symbols, interleaved MCUs, 1-padding,
  * 0xFF00 stuffing).  Returns bytes written, or 0 if cap is too small.
  * If total_bits != NULL it receives the un-stuffed, un-padded bit count. */

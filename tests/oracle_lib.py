@@ -52,6 +52,13 @@ def lib():
         L.orc_block_bits.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p]
         L.orc_jfif_header.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_size_t]
         L.orc_jfif_header.restype = C.c_size_t
+        L.orc_specs_standard.argtypes = [C.c_void_p]
+        L.orc_specs_optimal.argtypes = [C.c_void_p, C.c_void_p]
+        L.orc_encode_scan_specs.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.POINTER(C.c_uint64)]
+        L.orc_encode_scan_specs.restype = C.c_size_t
+        L.orc_jfif_header_specs.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t]
+        L.orc_jfif_header_specs.restype = C.c_size_t
         L.orc_encode_jfif.argtypes = [u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_void_p, C.c_size_t]
         L.orc_encode_jfif.restype = C.c_size_t
         L.orc_bmp_load.argtypes = [C.c_char_p, C.POINTER(u8p), C.POINTER(u8p), C.POINTER(u8p), C.POINTER(C.c_int), C.POINTER(C.c_int)]
@@ -159,6 +166,48 @@ def jfif_header(w, h, quality, ratio):
     n = lib().orc_jfif_header(w, h, quality, ratio, out.ctypes.data, 1024)
     assert n > 0
     return out[:n].copy()
+
+
+class HuffSpecs(C.Structure):
+    """OrcHuffSpecs: BITS/HUFFVAL of the four tables (0 DC lum, 1 DC chr, 2 AC lum, 3 AC chr)."""
+    _fields_ = [("nr", (C.c_uint8 * 17) * 4), ("vals", (C.c_uint8 * 256) * 4), ("nvals", C.c_int * 4)]
+
+    def lengths(self, t):
+        """code length per symbol of table t (0 = absent)"""
+        ln = np.zeros(256, dtype=np.int32)
+        k = 0
+        for l in range(1, 17):
+            for _ in range(self.nr[t][l]):
+                ln[self.vals[t][k]] = l
+                k += 1
+        return ln
+
+
+def specs_standard():
+    sp = HuffSpecs()
+    lib().orc_specs_standard(C.byref(sp))
+    return sp
+
+
+def specs_optimal(freq):
+    """T.81 K.2 tables from SPEC-mode histograms freq[4][257] (lum_DC, lum_AC, chrom_DC, chrom_AC)."""
+    f = np.ascontiguousarray(freq, dtype=np.int32)
+    sp = HuffSpecs()
+    lib().orc_specs_optimal(f.ctypes.data, C.byref(sp))
+    return sp
+
+
+def encode_jfif_specs(zz, w, h, quality, ratio, sp):
+    """header (with sp's DHT) + scan coded with sp + EOI"""
+    zz = np.ascontiguousarray(zz, dtype=np.int16)
+    hdr = np.zeros(1024, dtype=np.uint8)
+    n = lib().orc_jfif_header_specs(w, h, quality, ratio, C.byref(sp), hdr.ctypes.data, 1024)
+    assert n > 0
+    cap = zz.size * 4 + 1024
+    out = np.zeros(cap, dtype=np.uint8)
+    m = lib().orc_encode_scan_specs(zz.ctypes.data, w, h, ratio, C.byref(sp), out.ctypes.data, cap, None)
+    assert m > 0
+    return np.concatenate([hdr[:n], out[:m], np.array([0xFF, 0xD9], np.uint8)])
 
 
 def encode_jfif(r, g, b, w, h, quality, ratio=0, oob=None):

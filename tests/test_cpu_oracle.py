@@ -191,3 +191,33 @@ def test_fp32_block_math_within_tolerance_on_cpu(tmp_path):
     s = np.zeros((48, 64), np.uint8)
     L.hm_synth_plane(s.ctypes.data, 64, 48, 77, 3, 1, 0)
     assert (s == O.synth_plane(64, 48, 77, 3, 1, 0)).all()
+
+
+@pytest.mark.parametrize("w,h,q,ratio,kind", [(256, 128, 75, 0, 0), (320, 240, 90, 1, 0), (128, 64, 50, 0, 1)])
+def test_optimal_huffman_tables_oracle(w, h, q, ratio, kind):
+    """T.81 K.2 tables (what src/huffman.c:76-180 attempts): prefix-free, at most 16 bits, the
+    all-ones code left free; the stream coded with them decodes (PIL) to exactly the pixels of
+    the standard-table stream and is smaller.  Coding with the standard specs reproduces
+    orc_encode_jfif byte for byte."""
+    import io
+
+    from PIL import Image
+
+    r, g, b = O.synth_planes(w, h, 77, 0, kind)
+    zz = O.coefficients(r, g, b, w, h, q, ratio)
+    freq = O.histograms(zz, O.block_counts(w, h, ratio), 1, 1)
+    std, opt = O.specs_standard(), O.specs_optimal(freq)
+    a = O.encode_jfif_specs(zz, w, h, q, ratio, std)
+    ref = O.encode_jfif(r, g, b, w, h, q, ratio)
+    assert a.shape == ref.shape and (a == ref).all()
+    o = O.encode_jfif_specs(zz, w, h, q, ratio, opt)
+    assert o.size < a.size
+    src = [0, 2, 1, 3]  # histogram row of table t
+    for t in range(4):
+        ln = opt.lengths(t)
+        used = freq[src[t]][:256] > 0
+        assert (ln[used] > 0).all() and ln.max() <= 16
+        assert sum(2.0 ** -int(l) for l in ln if l > 0) < 1.0  # Kraft, strict: the reserved code point
+    ia = np.asarray(Image.open(io.BytesIO(a.tobytes())).convert("RGB"))
+    io_ = np.asarray(Image.open(io.BytesIO(o.tobytes())).convert("RGB"))
+    assert (ia == io_).all()

@@ -405,3 +405,36 @@ def test_tma_and_plain_transform_agree(enc, w, h, q, ratio, seed):
     assert (a == p).all()
     assert (a == c).all()
     assert_coeff_close(a, O.coefficients(r, g, b, w, h, q, ratio, oob=oob), "tma")
+
+
+@pytest.mark.parametrize("w,h,q,ratio,kind,seed", [(256, 128, 75, 0, 0, 51), (320, 240, 90, 1, 0, 52), (128, 64, 50, 0, 1, 53),
+                                                   (1920, 1080, 75, 0, 0, 54)])
+def test_optimized_huffman_tables(enc, w, h, q, ratio, kind, seed):
+    """per-image optimal tables (T.81 K.2, the goal of the reference's
+    construct_huffman_table, src/huffman.c:76-180).  Histograms on the GPU, K.2 on the host: the
+    tables equal the oracle's, the stream equals the oracle's stream coded with them byte for byte,
+    it is smaller than the standard-table stream and decodes to the same pixels."""
+    from PIL import Image
+
+    r, g, b = O.synth_planes(w, h, seed, 0, kind)
+    std = enc.encode_planar(r, g, b, w, h, q, ratio)
+    enc.set_optimized_huffman(True)
+    try:
+        opt = enc.encode_planar(r, g, b, w, h, q, ratio)
+        nr, vals, nv = enc.huffman_specs()
+        zz = enc.coefficients(r, g, b, w, h, q, ratio)
+    finally:
+        enc.set_optimized_huffman(False)
+    again = enc.encode_planar(r, g, b, w, h, q, ratio)
+    assert again.shape == std.shape and (again == std).all()  # switching back restores the standard tables
+    sp = O.specs_optimal(O.histograms(zz, O.block_counts(w, h, ratio), 1, 1))
+    for t in range(4):
+        assert nv[t] == sp.nvals[t]
+        assert (nr[t] == np.frombuffer(bytes(sp.nr[t]), np.uint8)).all()
+        assert (vals[t][:nv[t]] == np.frombuffer(bytes(sp.vals[t]), np.uint8)[:nv[t]]).all()
+    want = O.encode_jfif_specs(zz, w, h, q, ratio, sp)
+    assert opt.shape == want.shape and (opt == want).all()
+    assert opt.size < std.size
+    a = np.asarray(Image.open(io.BytesIO(std.tobytes())).convert("RGB"))
+    o = np.asarray(Image.open(io.BytesIO(opt.tobytes())).convert("RGB"))
+    assert (a == o).all()
