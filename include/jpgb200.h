@@ -69,6 +69,11 @@ int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on);
  * width % 16 == 8); 2 = the earlier TMA kernel whose phases are separated by CTA barriers.
  * Identical results. */
 int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on);
+/* Arithmetic of the transform: 0 (default) = bug-compatible with the reference (its Cb sign slip,
+ * src/preprocess.c:161, and the last block column read one pixel row higher, :199-211); 1 =
+ * standards-conforming (textbook Cb, no shift) -- the "robust front door" of SURVEY.md 8(f) rank 4:
+ * its streams decode to the source colours in any JPEG decoder. */
+int jpgb200_set_standard_mode(jpgb200_ctx *ctx, int on);
 /* Huffman tables: 0 (default) = the standard Annex-K tables the reference carries in
  * src/headers/tables.h:37-72; 1 = per-image optimal tables built from the image's own symbol
  * histograms by T.81 Annex K.2 -- what construct_huffman_table (src/huffman.c:76-180) sets out to
@@ -89,6 +94,12 @@ int jpgb200_set_oob_bytes(jpgb200_ctx *ctx, const uint8_t oob[24]);
  * host planes in, complete JFIF byte stream out (host).  H2D + kernels + D2H. */
 int jpgb200_encode_planar(jpgb200_ctx *ctx, const uint8_t *r, const uint8_t *g, const uint8_t *b, int width,
                           int height, int quality, int sample_ratio, uint8_t *out, size_t cap, size_t *len);
+/* Any width and height (1..65535): the reference's padding path is broken
+ * (src/preprocess.c:83-98,131-152: determine_resolutions adds w%8 instead of 8-w%8); here the
+ * planes are extended to whole MCUs by edge replication on the device and SOF0 carries the true
+ * size.  Works in either arithmetic mode. */
+int jpgb200_encode_planar_any(jpgb200_ctx *ctx, const uint8_t *r, const uint8_t *g, const uint8_t *b, int width,
+                              int height, int quality, int sample_ratio, uint8_t *out, size_t cap, size_t *len);
 /* Same from interleaved RGB24: the body encode_rgb_to_jpeg (src/headers/jpg_encode.h:99,
  * declared but never defined, and lacking width/height) would need. */
 int jpgb200_encode_rgb(jpgb200_ctx *ctx, const uint8_t *rgb, int width, int height, int quality, int sample_ratio,

@@ -34,8 +34,10 @@ _SIGS = {
     "jpgb200_set_staged_entropy": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_plain_transform": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_optimized_huffman": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_set_standard_mode": (C.c_int, [_vp, C.c_int]),
     "jpgb200_huffman_specs": (C.c_int, [_vp, _vp, _vp, _vp]),
     "jpgb200_encode_planar": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "jpgb200_encode_planar_any": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "jpgb200_encode_rgb": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "jpgb200_encode_device": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
     "jpgb200_encode_batch_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, _vp]),
@@ -192,6 +194,19 @@ class Encoder:
         self._ck(lib().jpgb200_encode_planar(self._h, r.ctypes.data, g.ctypes.data, b.ctypes.data, w, h, quality, ratio,
                                             out.ctypes.data, cap, C.byref(n)))
         return out[: n.value].copy()
+
+    def encode_planar_any(self, r, g, b, w, h, quality, ratio=0, cap=None):
+        """any width/height: edge replication to whole MCUs on the device, SOF0 with the true size"""
+        r, g, b = _c(r), _c(g), _c(b)
+        cap = cap or ((w + 16) * (h + 8) * 3 + 65536)
+        out = np.empty(cap, np.uint8)
+        n = C.c_size_t(0)
+        self._ck(lib().jpgb200_encode_planar_any(self._h, r.ctypes.data, g.ctypes.data, b.ctypes.data, w, h, quality, ratio,
+                                                out.ctypes.data, cap, C.byref(n)))
+        return out[: n.value].copy()
+
+    def set_standard_mode(self, on):
+        self._ck(lib().jpgb200_set_standard_mode(self._h, 1 if on else 0))
 
     def encode_rgb(self, rgb, w, h, quality, ratio=0, cap=None):
         rgb = _c(rgb)

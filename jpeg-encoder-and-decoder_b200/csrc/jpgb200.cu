@@ -99,6 +99,8 @@ struct jpgb200_ctx {
     unsigned long long band_bits;
     int band_phase, band_last, band_ratio, band_pred[3];
     long long band_n[3];
+    bool std_mode;       /* standards-conforming K1: textbook Cb, no last-column shift */
+    int sof_w, sof_h;    /* true image size for SOF0 when the planes were padded (0: same as the planes) */
     bool opt_huff;       /* per-image optimal Huffman tables (T.81 K.2) instead of the tables.h ones */
     HuffSpecs specs;     /* tables in use: DHT segments and code tables derive from them */
     HuffDev std_huff;    /* the tables.h tables, kept for switching back */
@@ -310,7 +312,8 @@ static size_t put16(uint8_t *o, size_t p, unsigned v)
 
 /* JFIF marker segments SOI..SOS (T.81 Annex B).  The DQT carries, at zig-zag
  * position of (v,u), the divisor the reference actually applies there: T'[u][v]. */
-static int jfif_header_specs(int w, int h, int quality, int ratio, const HuffSpecs *specs, uint8_t *o, size_t cap, size_t *len);
+static int jfif_header_specs(int w, int h, int quality, int ratio, const HuffSpecs *specs, uint8_t *o, size_t cap, size_t *len,
+                             bool check_dims = true);
 
 extern "C" int jpgb200_jfif_header(int w, int h, int quality, int ratio, uint8_t *o, size_t cap, size_t *len)
 {
@@ -319,11 +322,12 @@ extern "C" int jpgb200_jfif_header(int w, int h, int quality, int ratio, uint8_t
     return jfif_header_specs(w, h, quality, ratio, &sp, o, cap, len);
 }
 
-static int jfif_header_specs(int w, int h, int quality, int ratio, const HuffSpecs *specs, uint8_t *o, size_t cap, size_t *len)
+static int jfif_header_specs(int w, int h, int quality, int ratio, const HuffSpecs *specs, uint8_t *o, size_t cap, size_t *len,
+                             bool check_dims)
 {
     int lum[64], chr[64];
-    if (jpgb200_num_blocks(w, h, ratio, NULL) < 0) return JPGB200_ERR_BAD_DIMS;
-    if (w > 65535 || h > 65535) return JPGB200_ERR_BAD_DIMS;
+    if (check_dims && jpgb200_num_blocks(w, h, ratio, NULL) < 0) return JPGB200_ERR_BAD_DIMS;
+    if (w < 1 || h < 1 || w > 65535 || h > 65535 || (ratio != 0 && ratio != 1)) return JPGB200_ERR_BAD_DIMS;
     if (quality < 24 || quality > 97 || jpgb200_quant_tables(quality, lum, chr)) return JPGB200_ERR_BAD_QUALITY;
     if (cap < 640) return JPGB200_ERR_OUT_TOO_SMALL;
     size_t p = 0;
@@ -505,6 +509,13 @@ extern "C" int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;
     ctx->legacy_entropy = on != 0;
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_set_standard_mode(jpgb200_ctx *ctx, int on)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    ctx->std_mode = on != 0;
     return JPGB200_OK;
 }
 
@@ -724,6 +735,11 @@ static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_
 
 static int ensure_tables(jpgb200_ctx *ctx, int w, int h, int quality, int ratio)
 {
+    const bool padded = ctx->sof_w > 0;
+    if (padded) { /* SOF0 carries the true size, the planes hold whole MCUs */
+        w = ctx->sof_w;
+        h = ctx->sof_h;
+    }
     if (ctx->q_cached != quality) {
         int lum[64], chr[64];
         if (jpgb200_quant_tables(quality, lum, chr)) return JPGB200_ERR_BAD_QUALITY;
@@ -734,7 +750,7 @@ static int ensure_tables(jpgb200_ctx *ctx, int w, int h, int quality, int ratio)
     if (ctx->hdr_w != w || ctx->hdr_h != h || ctx->hdr_q != quality || ctx->hdr_ratio != ratio) {
         uint8_t hdr[1024];
         size_t len = 0;
-        int rc = jfif_header_specs(w, h, quality, ratio, &ctx->specs, hdr, sizeof hdr, &len);
+        int rc = jfif_header_specs(w, h, quality, ratio, &ctx->specs, hdr, sizeof hdr, &len, !padded);
         if (rc) return rc;
         CK(cudaMemcpyAsync(ctx->d_header, hdr, len, cudaMemcpyHostToDevice, ctx->stream));
         CK(cudaStreamSynchronize(ctx->stream)); /* hdr is a stack buffer */
@@ -781,20 +797,27 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
     }
     const bool aligned16 = (w % 16 == 0) && (((uintptr_t)d_r | (uintptr_t)d_g | (uintptr_t)d_b) % 16 == 0) &&
                            (plane_stride % 16 == 0);
-    if (aligned16 && !ctx->k1_plain && !ctx->k1_cta) {
+    if (aligned16 && !ctx->k1_plain && (!ctx->k1_cta || ctx->std_mode)) {
         /* persistent CTAs of four autonomous warps fed by TMA bulk copies (k1_warp.cuh) */
         if (!ctx->k1_attr_set) {
             CK(cudaFuncSetAttribute(k1_transform_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemTma)));
             CK(cudaFuncSetAttribute(k1_transform_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemTma)));
             CK(cudaFuncSetAttribute(k1_transform_ws<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1WSmem)));
             CK(cudaFuncSetAttribute(k1_transform_ws<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1WSmem)));
+            CK(cudaFuncSetAttribute((k1_transform_ws<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1WSmem)));
+            CK(cudaFuncSetAttribute((k1_transform_ws<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1WSmem)));
             ctx->k1_attr_set = true;
         }
         const long long n_tiles = (long long)p.tiles_per_row * (h / 8) * nframes;
         const long long resident = (long long)ctx->sm_count * K1W_MIN_CTAS;
         const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
         LaunchScope ls(ctx, KI_K1);
-        if (ratio == 0)
+        if (ctx->std_mode) {
+            if (ratio == 0)
+                k1_transform_ws<0, true><<<grid, K1_THREADS, sizeof(K1WSmem), ctx->stream>>>(p, n_tiles);
+            else
+                k1_transform_ws<1, true><<<grid, K1_THREADS, sizeof(K1WSmem), ctx->stream>>>(p, n_tiles);
+        } else if (ratio == 0)
             k1_transform_ws<0><<<grid, K1_THREADS, sizeof(K1WSmem), ctx->stream>>>(p, n_tiles);
         else
             k1_transform_ws<1><<<grid, K1_THREADS, sizeof(K1WSmem), ctx->stream>>>(p, n_tiles);
@@ -818,7 +841,12 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
     } else {
         dim3 grid((unsigned)p.tiles_per_row, (unsigned)(h / 8), (unsigned)nframes);
         LaunchScope ls(ctx, KI_K1);
-        if (ratio == 0)
+        if (ctx->std_mode) {
+            if (ratio == 0)
+                k1_transform<0, true><<<grid, K1_THREADS, 0, ctx->stream>>>(p);
+            else
+                k1_transform<1, true><<<grid, K1_THREADS, 0, ctx->stream>>>(p);
+        } else if (ratio == 0)
             k1_transform<0><<<grid, K1_THREADS, 0, ctx->stream>>>(p);
         else
             k1_transform<1><<<grid, K1_THREADS, 0, ctx->stream>>>(p);
@@ -1085,6 +1113,39 @@ extern "C" int jpgb200_encode_planar(jpgb200_ctx *ctx, const uint8_t *r, const u
     CK(cudaMemcpyAsync(dp + npx, g, npx, cudaMemcpyHostToDevice, ctx->stream));
     CK(cudaMemcpyAsync(dp + 2 * npx, b, npx, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = encode_core(ctx, dp, dp + npx, dp + 2 * npx, w, h, quality, ratio, ctx->d_out[0], cap, ctx->d_len))) return rc;
+    return finish_host(ctx, ctx->d_out[0], out, cap, len);
+}
+
+/* any width/height: the planes are extended to whole MCUs by edge replication on the device
+ * (T.81 A.2.4 leaves the padding samples to the encoder); SOF0 carries the true size */
+extern "C" int jpgb200_encode_planar_any(jpgb200_ctx *ctx, const uint8_t *r, const uint8_t *g, const uint8_t *b, int w, int h,
+                                         int quality, int ratio, uint8_t *out, size_t cap, size_t *len)
+{
+    if (!ctx || !r || !g || !b || !out) return JPGB200_ERR_BAD_ARG;
+    if (w < 1 || h < 1 || w > 65535 || h > 65535 || (ratio != 0 && ratio != 1)) return JPGB200_ERR_BAD_DIMS;
+    if (quality < 24 || quality > 97) return JPGB200_ERR_BAD_QUALITY;
+    const int mw = ratio ? 16 : 8;
+    const int pw = (w + mw - 1) / mw * mw, ph = (h + 7) / 8 * 8;
+    CK(cudaSetDevice(ctx->device));
+    const size_t npx = (size_t)w * h, pnpx = (size_t)pw * ph;
+    int rc;
+    if (ctx->planes_cap < 3 * pnpx || ctx->out_cap < cap || !ctx->d_planes[1] || !ctx->d_out[1]) {
+        if ((rc = ensure_io(ctx, pnpx, cap, 2))) return rc;
+    }
+    uint8_t *ds = ctx->d_planes[1], *dp = ctx->d_planes[0];
+    CK(cudaMemcpyAsync(ds, r, npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ds + npx, g, npx, cudaMemcpyHostToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(ds + 2 * npx, b, npx, cudaMemcpyHostToDevice, ctx->stream));
+    ks_pad_planes<<<(unsigned)ctx->sm_count * 8, 256, 0, ctx->stream>>>(ds, dp, w, h, pw, ph);
+    ctx->launch_total++;
+    CK(cudaGetLastError());
+    ctx->sof_w = w;
+    ctx->sof_h = h;
+    ctx->hdr_w = -1;
+    rc = encode_core(ctx, dp, dp + pnpx, dp + 2 * pnpx, pw, ph, quality, ratio, ctx->d_out[0], cap, ctx->d_len);
+    ctx->sof_w = ctx->sof_h = 0;
+    ctx->hdr_w = -1; /* the cached header carries the true size, not the plane size */
+    if (rc) return rc;
     return finish_host(ctx, ctx->d_out[0], out, cap, len);
 }
 

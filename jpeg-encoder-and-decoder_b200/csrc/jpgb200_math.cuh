@@ -118,6 +118,15 @@ __device__ __forceinline__ f32x2 colour_cb_p(f32x2 r, f32x2 g, f32x2 b)
 {
     return p_fma(p_bc(-0.5f), b, p_fma(p_bc(0.331264f), g, p_mul(p_bc(-0.168736f), r)));
 }
+/* the textbook Cb (JFIF): -0.168736 r - 0.331264 g + 0.5 b, for the standards-conforming front door */
+__device__ __forceinline__ f32x2 colour_cb_std_p(f32x2 r, f32x2 g, f32x2 b)
+{
+    return p_fma(p_bc(0.5f), b, p_fma(p_bc(-0.331264f), g, p_mul(p_bc(-0.168736f), r)));
+}
+__device__ __forceinline__ f32x2 colour_cb2_std_p(f32x2 rs, f32x2 gs, f32x2 bs)
+{
+    return p_fma(p_bc(0.25f), bs, p_fma(p_bc(-0.165632f), gs, p_mul(p_bc(-0.084368f), rs)));
+}
 __device__ __forceinline__ f32x2 colour_cr_p(f32x2 r, f32x2 g, f32x2 b)
 {
     return p_fma(p_bc(-0.081312f), b, p_fma(p_bc(-0.418688f), g, p_mul(p_bc(0.5f), r)));

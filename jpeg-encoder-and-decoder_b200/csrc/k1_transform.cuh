@@ -116,7 +116,7 @@ __device__ __forceinline__ void k1_store_pairs(K1F &F, int k, int slot, const f3
 
 /* phase 1, full-resolution components: thread (k, j) converts rows k and 7-k of block j.
  * ra/rb etc. = the 8 bytes of row k / row 7-k of the three planes. */
-template <int RATIO>
+template <int RATIO, bool STD = false>
 __device__ __forceinline__ void k1_convert_full(K1F *sF, int k, int j, const uint2 (&pa)[3], const uint2 (&pb)[3])
 {
     f32x2 r[8], g[8], b[8], o[8];
@@ -128,7 +128,7 @@ __device__ __forceinline__ void k1_convert_full(K1F *sF, int k, int j, const uin
     k1_store_pairs(sF[0], k, j, o);
     if (RATIO == 0) {
 #pragma unroll
-        for (int x = 0; x < 8; x++) o[x] = colour_cb_p(r[x], g[x], b[x]);
+        for (int x = 0; x < 8; x++) o[x] = STD ? colour_cb_std_p(r[x], g[x], b[x]) : colour_cb_p(r[x], g[x], b[x]);
         k1_store_pairs(sF[1], k, j, o);
 #pragma unroll
         for (int x = 0; x < 8; x++) o[x] = colour_cr_p(r[x], g[x], b[x]);
@@ -138,6 +138,7 @@ __device__ __forceinline__ void k1_convert_full(K1F *sF, int k, int j, const uin
 
 /* phase 1, 4:2:2 chroma: thread (k, lane) with lane = which*16 + jc averages the 16 pixels of
  * rows k and 7-k under chroma block jc and stores Cb (which = 0, slot jc) or Cr (slot 16+jc) */
+template <bool STD = false>
 __device__ __forceinline__ void k1_convert_chroma422(K1F *sF, int k, int lane, const uint4 (&pa)[3], const uint4 (&pb)[3])
 {
     f32x2 r[8], g[8], b[8], o[8];
@@ -146,7 +147,7 @@ __device__ __forceinline__ void k1_convert_chroma422(K1F *sF, int k, int lane, c
     k1_pairsums16(pa[2], pb[2], b);
     if (lane < 16) {
 #pragma unroll
-        for (int x = 0; x < 8; x++) o[x] = colour_cb2_p(r[x], g[x], b[x]);
+        for (int x = 0; x < 8; x++) o[x] = STD ? colour_cb2_std_p(r[x], g[x], b[x]) : colour_cb2_p(r[x], g[x], b[x]);
     } else {
 #pragma unroll
         for (int x = 0; x < 8; x++) o[x] = colour_cr2_p(r[x], g[x], b[x]);
@@ -224,7 +225,9 @@ __device__ __forceinline__ void k1_phase3(const K1Out *sOut, const K1Params &p, 
 /* ---------------------------------------------------------------------------------------------
  * k1_transform: one CTA per tile, direct 8-byte global loads (any width % 8 == 0)
  * --------------------------------------------------------------------------------------------- */
-template <int RATIO>
+/* STD = the standards-conforming front door (jpgb200_encode_planar_std): textbook Cb and no
+ * shift of the last block column -- the reference's two coefficient-path bugs left out */
+template <int RATIO, bool STD = false>
 __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform(const K1Params p)
 {
     __shared__ K1F sF[3];
@@ -248,7 +251,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform(const K1Params p)
         /* 8 bytes of image row by*8+rr of block column bx (one row higher for the last column) */
         auto ld8 = [&](int c, int rr, int bx) -> uint2 {
             if (bx >= p.BW) return make_uint2(0u, 0u);
-            const long long row = (long long)by * 8 + rr - (bx == p.BW - 1 ? 1 : 0);
+            const long long row = (long long)by * 8 + rr - ((!STD && bx == p.BW - 1) ? 1 : 0);
             if (row >= 0 || p.has_halo) return __ldg(reinterpret_cast<const uint2 *>(pl[c] + row * p.W + (long long)bx * 8));
             return ld_oob(p.oob + 8 * c);
         };
@@ -258,7 +261,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform(const K1Params p)
             pa[c] = ld8(c, k, tb0 + lane);
             pb2[c] = ld8(c, 7 - k, tb0 + lane);
         }
-        k1_convert_full<RATIO>(sF, k, lane, pa, pb2);
+        k1_convert_full<RATIO, STD>(sF, k, lane, pa, pb2);
         if (RATIO == 1) {
             const int jc = lane & 15;
             uint4 ca[3], cb[3];
@@ -269,7 +272,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform(const K1Params p)
                 ca[c] = make_uint4(l0.x, l0.y, l1.x, l1.y);
                 cb[c] = make_uint4(h0.x, h0.y, h1.x, h1.y);
             }
-            k1_convert_chroma422(sF, k, lane, ca, cb);
+            k1_convert_chroma422<STD>(sF, k, lane, ca, cb);
         }
     }
     __syncthreads();

@@ -66,6 +66,7 @@ __device__ __forceinline__ void cp_async8(void *smem, const void *gmem)
  * each plane, asynchronously (LDGSTS: no registers, completion by cp.async group).  The block of
  * column BW-1 is fetched one pixel row higher; row -1 of an image without halo
  * is left alone -- phase 1 substitutes the caller's out-of-bounds bytes for it. */
+template <bool STD>
 __device__ __forceinline__ void k1w_fetch(const K1Params &p, K1WRaw &raw, long long t, int w, int lane)
 {
     const K1Tile tl = k1_tile(p, t);
@@ -74,7 +75,7 @@ __device__ __forceinline__ void k1w_fetch(const K1Params &p, K1WRaw &raw, long l
     if (bx < p.BW) {
         const long long row = (long long)tl.by * 8 + y;
         const long long off = (long long)tl.frame * p.plane_stride + row * p.W + (long long)bx * 8;
-        const int jl = p.BW - 1 - bx; /* 0 or 1: the chunk holds the last block column */
+        const int jl = STD ? -1 : p.BW - 1 - bx; /* 0 or 1: the chunk holds the last block column */
         const uint8_t *src[3] = {p.r + off, p.g + off, p.b + off};
         if (jl == 0 || jl == 1) {
             const bool up_ok = (row - 1 >= 0) || p.has_halo;
@@ -91,7 +92,7 @@ __device__ __forceinline__ void k1w_fetch(const K1Params &p, K1WRaw &raw, long l
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
 
-template <int RATIO>
+template <int RATIO, bool STD = false>
 __global__ void __launch_bounds__(K1_THREADS, K1W_MIN_CTAS) k1_transform_ws(const K1Params p, long long n_tiles)
 {
     extern __shared__ __align__(128) unsigned char k1_smem[];
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1W_MIN_CTAS) k1_transform_ws(cons
     for (int s = 0; s < K1W_STAGES - 1; s++) {
         const long long t = (long long)blockIdx.x + (long long)s * gridDim.x;
         if (t < n_tiles)
-            k1w_fetch(p, S.raw[w][s], t, w, lane);
+            k1w_fetch<STD>(p, S.raw[w][s], t, w, lane);
         else
             asm volatile("cp.async.commit_group;\n" ::: "memory");
     }
@@ -126,7 +127,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1W_MIN_CTAS) k1_transform_ws(cons
             /* the slot consumed in the previous iteration is refilled with the strip two tiles ahead */
             const long long tn = t + (long long)(K1W_STAGES - 1) * gridDim.x;
             if (tn < n_tiles)
-                k1w_fetch(p, S.raw[w][(it + K1W_STAGES - 1) % K1W_STAGES], tn, w, lane);
+                k1w_fetch<STD>(p, S.raw[w][(it + K1W_STAGES - 1) % K1W_STAGES], tn, w, lane);
             else
                 asm volatile("cp.async.commit_group;\n" ::: "memory");
         }
@@ -136,7 +137,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1W_MIN_CTAS) k1_transform_ws(cons
         /* ---- phase 1 ---- */
         {
             const K1WRaw &raw = S.raw[w][s];
-            const int jl = p.BW - 1 - tl.tb0 - 8 * w; /* strip-local index of block column BW-1 */
+            const int jl = STD ? -1 : p.BW - 1 - tl.tb0 - 8 * w; /* strip-local index of block column BW-1 */
             const bool top_oob = (tl.by == 0 && !p.has_halo);
             auto ld8 = [&](int c, int rr, int j) -> uint2 {
                 if (RATIO == 1 && top_oob && rr == 0 && j == jl) return ld_oob(p.oob + 8 * c);
@@ -158,7 +159,8 @@ __global__ void __launch_bounds__(K1_THREADS, K1W_MIN_CTAS) k1_transform_ws(cons
             for (int x = 0; x < 8; x++) F[k1w_idx(0, k, x, jj)] = colour_y_p(r[x], g[x], b[x]);
             if (RATIO == 0) {
 #pragma unroll
-                for (int x = 0; x < 8; x++) F[k1w_idx(1, k, x, jj)] = colour_cb_p(r[x], g[x], b[x]);
+                for (int x = 0; x < 8; x++)
+                    F[k1w_idx(1, k, x, jj)] = STD ? colour_cb_std_p(r[x], g[x], b[x]) : colour_cb_p(r[x], g[x], b[x]);
 #pragma unroll
                 for (int x = 0; x < 8; x++) F[k1w_idx(2, k, x, jj)] = colour_cr_p(r[x], g[x], b[x]);
             } else {
@@ -177,7 +179,8 @@ __global__ void __launch_bounds__(K1_THREADS, K1W_MIN_CTAS) k1_transform_ws(cons
                 k1_pairsums16(ca[2], cb[2], b);
                 if (which == 0) {
 #pragma unroll
-                    for (int x = 0; x < 8; x++) F[k1w_idx(1, k, x, jj)] = colour_cb2_p(r[x], g[x], b[x]);
+                    for (int x = 0; x < 8; x++)
+                        F[k1w_idx(1, k, x, jj)] = STD ? colour_cb2_std_p(r[x], g[x], b[x]) : colour_cb2_p(r[x], g[x], b[x]);
                 } else {
 #pragma unroll
                     for (int x = 0; x < 8; x++) F[k1w_idx(1, k, x, jj)] = colour_cr2_p(r[x], g[x], b[x]);

@@ -380,5 +380,18 @@ __global__ void __launch_bounds__(256) ks_deinterleave(const uint8_t *rgb, uint8
     }
 }
 
+/* three tight planes w x h -> three planes pw x ph, edge samples replicated to the right and below */
+__global__ void __launch_bounds__(256) ks_pad_planes(const uint8_t *src, uint8_t *dst, int w, int h, int pw, int ph)
+{
+    const long long per = (long long)pw * ph, total = 3 * per;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c = (int)(i / per);
+        const long long rem = i - c * per;
+        const int y = (int)(rem / pw), x = (int)(rem - (long long)y * pw);
+        const int sy = y < h ? y : h - 1, sx = x < w ? x : w - 1;
+        dst[i] = src[(long long)c * w * h + (long long)sy * w + sx];
+    }
+}
+
 }  // namespace jpgb200
 #endif

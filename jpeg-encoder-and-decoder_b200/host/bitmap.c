@@ -81,6 +81,71 @@ BmpImage bmp_OpenBitmap(const char *file)
     return b;
 }
 
+/* Strict parsing of an uncompressed 24-bit BMP -- what the reference's README lists under "current
+ * issues" (README.md:16-24): the pixel-data offset is honoured, rows are 4-byte aligned,
+ * bottom-up files (positive height) are flipped, and the B,G,R bytes go to the planes they name.
+ * The accessors then return true red / green / blue, top-down. */
+BmpImage bmp_OpenBitmapStrict(const char *file)
+{
+    BmpImage b = (BmpImage)calloc(1, sizeof(struct _bitmap));
+    if (!b) return NULL;
+    strncpy(b->filename, file, NAME_MAX_LEN - 1);
+    FILE *fp = fopen(file, "rb");
+    if (!fp) {
+        b->error = BMP_FILE_DOESNT_EXIST;
+        return b;
+    }
+    fseek(fp, 0, SEEK_END);
+    const long fs = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    Byte *buf = (fs >= 54 && fs < 0x7fffffffL) ? (Byte *)malloc((size_t)fs) : NULL;
+    if (!buf || fread(buf, 1, (size_t)fs, fp) != (size_t)fs) {
+        b->error = BMP_READ_FAILED;
+        fclose(fp);
+        free(buf);
+        return b;
+    }
+    fclose(fp);
+    int compression = 0, hgt = 0;
+    b->fileSize = (int)fs;
+    memcpy(&b->offsetRGB, buf + 10, 4);
+    memcpy(&b->width, buf + 18, 4);
+    memcpy(&hgt, buf + 22, 4);
+    memcpy(&b->bitDepth, buf + 28, 2);
+    memcpy(&compression, buf + 30, 4);
+    const int top_down = hgt < 0;
+    b->height = top_down ? -hgt : hgt;
+    b->numPixels = b->width * b->height;
+    const long pitch = ((long)b->width * 3 + 3) & ~3L;
+    if (buf[0] != 'B' || buf[1] != 'M' || b->bitDepth != 24 || compression != 0 || b->width <= 0 || b->height <= 0 ||
+        b->offsetRGB < 54 || (long)b->offsetRGB + pitch * b->height > fs) {
+        b->error = BMP_READ_FAILED;
+        free(buf);
+        return b;
+    }
+    const long np = (long)b->width * b->height;
+    b->red = (Byte *)malloc((size_t)np);
+    b->green = (Byte *)malloc((size_t)np);
+    b->blue = (Byte *)malloc((size_t)np);
+    if (!b->red || !b->green || !b->blue) {
+        b->error = BMP_FAILED_ALLOCATE_BUFFER;
+        free(buf);
+        return b;
+    }
+    for (int y = 0; y < b->height; y++) {
+        const Byte *px = buf + b->offsetRGB + pitch * (top_down ? y : b->height - 1 - y);
+        Byte *r = b->red + (long)y * b->width, *g = b->green + (long)y * b->width, *bl = b->blue + (long)y * b->width;
+        for (int x = 0; x < b->width; x++, px += 3) {
+            bl[x] = px[0];
+            g[x] = px[1];
+            r[x] = px[2];
+        }
+    }
+    b->error = BMP_SUCCESS;
+    free(buf);
+    return b;
+}
+
 Byte *bmp_GetRed(BmpImage b) { return b->red; }
 Byte *bmp_GetGreen(BmpImage b) { return b->green; }
 Byte *bmp_GetBlue(BmpImage b) { return b->blue; }

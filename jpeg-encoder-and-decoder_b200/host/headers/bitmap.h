@@ -29,5 +29,8 @@ void bmp_DestroyBitmap(BmpImage b);
 
 /* not in the reference: the stored error code (the reference only prints it) */
 int bmp_GetErrorCode(BmpImage b);
+/* not in the reference: strict parsing of a 24-bit BMP (pixel-data offset, 4-byte row pitch,
+ * bottom-up rows, B,G,R order): the accessors return true red/green/blue, top-down */
+BmpImage bmp_OpenBitmapStrict(const char *file);
 
 #endif

@@ -60,4 +60,8 @@ int encode_rgb_to_jpeg_ex(const Byte *rgb, int width, int height, const char *ou
 /* Same as encode_bmp_to_jpeg with a status code (0 = ok, negative = JPGB200_ERR_*, positive = BMP_* error). */
 int encode_bmp_to_jpeg_status(const char *input_filename, const char *output_filename, int quality, int sample_ratio);
 
+/* Not in the reference: strict BMP parsing, any size, standards-conforming arithmetic (no
+ * bug-compatible quirks) -- same status codes as encode_bmp_to_jpeg_status. */
+int encode_bmp_to_jpeg_robust(const char *input_filename, const char *output_filename, int quality, int sample_ratio);
+
 #endif

@@ -3,7 +3,7 @@
  * known-answer walk (the Wikipedia 8x8 example through dct_block, quantise_lum and
  * zig_zag_block, src/jpg_driver.c:54-150) -- every stage on the GPU -- and prints it in the
  * same format; with arguments it encodes a file:
- *     jpg <in.bmp> <out.jpg> [quality=50] [sample_ratio=0] [--staged]
+ *     jpg <in.bmp> <out.jpg> [quality=50] [sample_ratio=0] [--staged | --robust]
  */
 #include <stdio.h>
 #include <stdlib.h>
@@ -54,5 +54,6 @@ int main(int argc, char **argv)
         printf("%dx%d blocks Y/Cb/Cr %d/%d/%d\n", j->width, j->height, j->num_blocks_Y, j->num_blocks_Cb, j->num_blocks_Cr);
         return 0;
     }
+    if (argc > 5 && !strcmp(argv[5], "--robust")) return encode_bmp_to_jpeg_robust(argv[1], argv[2], quality, ratio) == 0 ? 0 : 1;
     return encode_bmp_to_jpeg_status(argv[1], argv[2], quality, ratio) == 0 ? 0 : 1;
 }

@@ -49,6 +49,38 @@ int encode_bmp_to_jpeg_status(const char *input, const char *output, int quality
     return rc;
 }
 
+/* The robust front door (the reference's README.md:16-24 "current issues"):
+ * strict BMP parsing, any width and height, standards-conforming arithmetic -- the file decodes to
+ * the picture in the BMP in any JPEG decoder. */
+int encode_bmp_to_jpeg_robust(const char *input, const char *output, int quality, int sample_ratio)
+{
+    jpgb200_ctx *ctx = host_ctx();
+    if (!ctx) return JPGB200_ERR_NO_DEVICE;
+    BmpImage bmp = bmp_OpenBitmapStrict(input);
+    if (!bmp) return BMP_FAILED_ALLOCATE_BUFFER;
+    if (bmp_GetErrorCode(bmp) != BMP_SUCCESS) {
+        const int e = bmp_GetErrorCode(bmp);
+        bmp_GetLastError(bmp);
+        bmp_DestroyBitmap(bmp);
+        return e;
+    }
+    const int w = bmp_GetWidth(bmp), h = bmp_GetHeight(bmp);
+    const size_t cap = (size_t)(w + 16) * (h + 8) * 3 + 65536;
+    unsigned char *out = (unsigned char *)malloc(cap);
+    size_t len = 0;
+    int rc = out ? JPGB200_OK : JPGB200_ERR_NOMEM;
+    if (rc == JPGB200_OK) {
+        jpgb200_set_standard_mode(ctx, 1);
+        rc = jpgb200_encode_planar_any(ctx, bmp_GetRed(bmp), bmp_GetGreen(bmp), bmp_GetBlue(bmp), w, h, quality, sample_ratio,
+                                       out, cap, &len);
+        jpgb200_set_standard_mode(ctx, 0);
+    }
+    bmp_DestroyBitmap(bmp);
+    if (rc == JPGB200_OK) rc = write_file(output, out, len);
+    free(out);
+    return rc;
+}
+
 void encode_bmp_to_jpeg(const char *input, const char *output, int quality, int sample_ratio)
 {
     const int rc = encode_bmp_to_jpeg_status(input, output, quality, sample_ratio);

@@ -167,11 +167,16 @@ void orc_zigzag_block(const double values[64], int zz[64])
  * reproducing blockToCoords (:199-211): the last block column of every block
  * row reads one pixel row higher; row -1 of the top-right block comes from the
  * 8 bytes in front of the buffer. */
+/* standards-conforming arithmetic instead of the reference's two coefficient-path bugs: no
+ * last-column shift, textbook Cb (the product's "robust front door") */
+static int g_standard = 0;
+void orc_set_standard(int on) { g_standard = on != 0; }
+
 static inline int plane_sample(const uint8_t *p, int w, int bw, int bx, int by, int x, int y,
                                const uint8_t *oob)
 {
     long row = (long)by * 8 + y;
-    if (bx == bw - 1) row -= 1;
+    if (bx == bw - 1 && !g_standard) row -= 1;
     if (row < 0) return oob ? oob[x] : 0;
     return p[row * w + (long)bx * 8 + x];
 }
@@ -186,7 +191,8 @@ static void convert_block(const uint8_t *r, const uint8_t *g, const uint8_t *b, 
             int gv = plane_sample(g, w, bw, bx, by, x, y, oob ? oob + 8 : NULL);
             int bv = plane_sample(b, w, bw, bx, by, x, y, oob ? oob + 16 : NULL);
             double yv = 0.299 * rv + 0.587 * gv + 0.114 * bv;
-            double cb = 128 - (0.168736 * rv - 0.331264 * gv + 0.5 * bv);
+            double cb = g_standard ? 128 + (-0.168736 * rv - 0.331264 * gv + 0.5 * bv)
+                                   : 128 - (0.168736 * rv - 0.331264 * gv + 0.5 * bv);
             double cr = 128 + (0.5 * rv - 0.418688 * gv - 0.081312 * bv);
             Y[y * 8 + x] = yv - 128;
             Cb[y * 8 + x] = cb - 128;

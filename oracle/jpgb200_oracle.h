@@ -50,6 +50,9 @@ int orc_coefficients(const uint8_t *r, const uint8_t *g, const uint8_t *b, int w
 
 /* worker threads used by orc_coefficients (default 1: the reference is single-threaded) */
 void orc_set_threads(int t);
+/* 1: standards-conforming arithmetic (textbook Cb, no last-column shift) for the checks of the
+ * product's standard mode; 0 (default): the reference's behaviour */
+void orc_set_standard(int on);
 
 /* single-block entry points mirroring dct_block / quantise_lum|chr / zig_zag_block */
 void orc_dct_block(double values[64]);

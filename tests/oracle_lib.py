@@ -39,6 +39,7 @@ def lib():
         L.orc_block_counts.argtypes = [C.c_int, C.c_int, C.c_int, C.POINTER(C.c_long)]
         L.orc_coefficients.argtypes = [u8p, u8p, u8p, C.c_int, C.c_int, C.c_int, C.c_int, u8p, C.c_void_p, C.c_void_p]
         L.orc_set_threads.argtypes = [C.c_int]
+        L.orc_set_standard.argtypes = [C.c_int]
         L.orc_dct_block.argtypes = [C.c_void_p]
         L.orc_quantise_block.argtypes = [C.c_void_p, C.c_void_p]
         L.orc_zigzag_block.argtypes = [C.c_void_p, C.c_void_p]
@@ -109,6 +110,19 @@ def coefficients(r, g, b, w, h, quality, ratio=0, oob=None, want_dct=False, thre
     if rc:
         raise ValueError("orc_coefficients rc=%d" % rc)
     return (zz, dct) if want_dct else zz
+
+
+def set_standard(on):
+    """standards-conforming arithmetic (textbook Cb, no last-column shift) on/off"""
+    lib().orc_set_standard(1 if on else 0)
+
+
+def pad_planes(r, g, b, w, h, ratio):
+    """edge replication to whole MCUs, as jpgb200_encode_planar_any does on the device"""
+    mw = 16 if ratio else 8
+    pw, ph = (w + mw - 1) // mw * mw, (h + 7) // 8 * 8
+    out = [np.pad(np.asarray(p, np.uint8).reshape(h, w), ((0, ph - h), (0, pw - w)), mode="edge").reshape(-1) for p in (r, g, b)]
+    return out[0], out[1], out[2], pw, ph
 
 
 def dc_sequence(zz_comp, mode):

@@ -130,3 +130,29 @@ def test_encode_coefficients_is_byte_exact_given_equal_coefficients(enc):
             got = enc.encode_coefficients(zz, w, h, q, ratio)
             assert got.shape == want.shape and (got == want).all()
         enc.set_staged_entropy(True)
+
+
+def test_driver_robust_front_door(tmp_path):
+    """jpg <in.bmp> <out.jpg> q ratio --robust: strict BMP parsing (data offset, 4-byte row pitch,
+    bottom-up rows, B,G,R order), any size, standards-conforming arithmetic: PIL reads the BMP and
+    the JPEG made from it as (nearly) the same picture -- for a width that is neither a multiple
+    of 4 bytes per row nor of 8 pixels."""
+    from PIL import Image
+
+    w, h = 150, 101
+    yy, xx = np.mgrid[0:h, 0:w]
+    rng = np.random.default_rng(5)
+    rgb = np.stack([xx * 255 // (w - 1), yy * 255 // (h - 1), 255 - (xx + yy) * 255 // (w + h - 2)], axis=-1)
+    rgb = np.clip(rgb + rng.integers(-5, 6, size=rgb.shape), 0, 255).astype(np.uint8)
+    bmp = str(tmp_path / "in.bmp")
+    Image.fromarray(rgb, "RGB").save(bmp)  # bottom-up, rows padded to 452 bytes
+    exe = os.path.join(PKG, "jpg")
+    for ratio in (0, 1):
+        outp = str(tmp_path / ("out%d.jpg" % ratio))
+        r = subprocess.run([exe, bmp, outp, "90", str(ratio), "--robust"], capture_output=True, text=True, timeout=120)
+        assert r.returncode == 0, r.stderr + r.stdout
+        im = Image.open(outp)
+        assert im.size == (w, h)
+        dec = np.asarray(im.convert("RGB")).astype(np.float64)
+        mse = float(((dec - rgb.astype(np.float64)) ** 2).mean())
+        assert 10 * np.log10(255.0 ** 2 / mse) > 32.0
