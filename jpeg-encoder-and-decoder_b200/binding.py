@@ -352,7 +352,7 @@ class Encoder:
 
     # ---- measurement
     def set_profiling(self, on):
-        self._ck(lib().jpgb200_set_profiling(self._h, 1 if on else 0))
+        self._ck(lib().jpgb200_set_profiling(self._h, int(on)))
 
     def reset_profile(self):
         self._ck(lib().jpgb200_reset_profile(self._h))

@@ -111,7 +111,7 @@ struct jpgb200_ctx {
     int q_cached;
     float mul[2][64];
     /* profiling */
-    bool profiling;
+    int profiling; /* 0 off, 1 every kernel, 2 only K1 (the roofline kernel: fewer event records in a timed region) */
     std::vector<EvPair> pending;
     std::vector<cudaEvent_t> free_events;
     double ms[JPGB200_NUM_KERNELS];
@@ -570,9 +570,11 @@ struct LaunchScope {
     jpgb200_ctx *ctx;
     int k;
     cudaEvent_t a, b;
+    bool on;
     LaunchScope(jpgb200_ctx *c, int kk) : ctx(c), k(kk)
     {
-        if (ctx->profiling) {
+        on = ctx->profiling == 1 || (ctx->profiling == 2 && kk == KI_K1);
+        if (on) {
             a = get_event(ctx);
             b = get_event(ctx);
             cudaEventRecord(a, ctx->stream);
@@ -582,7 +584,7 @@ struct LaunchScope {
     {
         ctx->launch_total++;
         ctx->launches[k]++;
-        if (ctx->profiling) {
+        if (on) {
             cudaEventRecord(b, ctx->stream);
             ctx->pending.push_back({k, a, b});
         }
@@ -608,7 +610,7 @@ extern "C" int jpgb200_set_profiling(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;
     int rc = resolve_profile(ctx);
-    ctx->profiling = on != 0;
+    ctx->profiling = on < 0 ? 0 : (on > 2 ? 1 : on);
     return rc;
 }
 
