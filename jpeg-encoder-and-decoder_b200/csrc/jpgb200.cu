@@ -29,6 +29,7 @@
 #include "jpgb200_tables.h"
 #include "k1_transform.cuh"
 #include "k1_warp.cuh"
+#include "k1_pipe.cuh"
 #include "tail.cuh"
 #include "taps.cuh"
 
@@ -76,8 +77,9 @@ struct jpgb200_ctx {
     size_t tmp_cap;
     unsigned long long *d_bit_state, *d_ff_state;
     size_t chain_cap;
-    bool fused_attr_set, k1_attr_set, ke_attr_set;
+    bool fused_attr_set, k1_attr_set, ke_attr_set, k1p_attr_set;
     bool k1_plain; /* force the non-TMA K1 (tests) */
+    bool k1_pipe;  /* the software-pipelined K1 (k1_pipe.cuh) */
     bool k1_cta;   /* force the CTA-barrier TMA K1 instead of the warp-autonomous one (tests, A/B runs) */
     EncState *d_state;
     uint8_t *d_header;
@@ -408,6 +410,8 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         const char *k = getenv("JPGB200_K1"); /* "plain" | "tma" */
         if (k && !strcmp(k, "plain")) ctx->k1_plain = true;
         if (k && !strcmp(k, "cta")) ctx->k1_cta = true;
+        if (k && !strcmp(k, "pipe")) ctx->k1_pipe = true;
+        if (k && !strcmp(k, "ws")) ctx->k1_pipe = false;
     }
     ctx->hdr_w = -1;
     ctx->err[0] = 0;
@@ -502,6 +506,7 @@ extern "C" int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on)
     if (!ctx) return JPGB200_ERR_BAD_ARG;
     ctx->k1_plain = (on == 1);
     ctx->k1_cta = (on == 2);
+    ctx->k1_pipe = (on == 3);
     return JPGB200_OK;
 }
 
@@ -799,7 +804,29 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
     }
     const bool aligned16 = (w % 16 == 0) && (((uintptr_t)d_r | (uintptr_t)d_g | (uintptr_t)d_b) % 16 == 0) &&
                            (plane_stride % 16 == 0);
-    if (aligned16 && !ctx->k1_plain && (!ctx->k1_cta || ctx->std_mode)) {
+    if (aligned16 && ctx->k1_pipe && !ctx->k1_plain) {
+        /* persistent CTAs, warps specialised and software-pipelined over tiles (k1_pipe.cuh) */
+        if (!ctx->k1p_attr_set) {
+            CK(cudaFuncSetAttribute((k1_transform_pipe<0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1PSmem)));
+            CK(cudaFuncSetAttribute((k1_transform_pipe<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1PSmem)));
+            CK(cudaFuncSetAttribute((k1_transform_pipe<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1PSmem)));
+            CK(cudaFuncSetAttribute((k1_transform_pipe<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1PSmem)));
+            ctx->k1p_attr_set = true;
+        }
+        const long long n_tiles = (long long)p.tiles_per_row * (h / 8) * nframes;
+        const long long resident = (long long)ctx->sm_count * K1P_MIN_CTAS;
+        const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+        LaunchScope ls(ctx, KI_K1);
+        if (ctx->std_mode) {
+            if (ratio == 0)
+                k1_transform_pipe<0, true><<<grid, K1_THREADS, sizeof(K1PSmem), ctx->stream>>>(p, n_tiles);
+            else
+                k1_transform_pipe<1, true><<<grid, K1_THREADS, sizeof(K1PSmem), ctx->stream>>>(p, n_tiles);
+        } else if (ratio == 0)
+            k1_transform_pipe<0, false><<<grid, K1_THREADS, sizeof(K1PSmem), ctx->stream>>>(p, n_tiles);
+        else
+            k1_transform_pipe<1, false><<<grid, K1_THREADS, sizeof(K1PSmem), ctx->stream>>>(p, n_tiles);
+    } else if (aligned16 && !ctx->k1_plain && (!ctx->k1_cta || ctx->std_mode)) {
         /* persistent CTAs of four autonomous warps fed by TMA bulk copies (k1_warp.cuh) */
         if (!ctx->k1_attr_set) {
             CK(cudaFuncSetAttribute(k1_transform_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1SmemTma)));
