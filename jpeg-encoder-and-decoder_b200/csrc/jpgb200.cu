@@ -80,6 +80,10 @@ struct jpgb200_ctx {
     bool fused_attr_set, k1_attr_set, ke_attr_set, k1p_attr_set;
     bool k1_plain; /* force the non-TMA K1 (tests) */
     bool k1_pipe;  /* the software-pipelined K1 (k1_pipe.cuh) */
+    bool no_tma_store; /* k1_pipe: copy the coefficients out with ordinary stores (A/B runs) */
+    CUtensorMap tm32, tm16; /* tensor maps of the coefficient buffer, cached */
+    int16_t *tm_ptr;
+    long long tm_rows;
     bool k1_cta;   /* force the CTA-barrier TMA K1 instead of the warp-autonomous one (tests, A/B runs) */
     EncState *d_state;
     uint8_t *d_header;
@@ -411,6 +415,7 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         if (k && !strcmp(k, "plain")) ctx->k1_plain = true;
         if (k && !strcmp(k, "cta")) ctx->k1_cta = true;
         if (k && !strcmp(k, "pipe")) ctx->k1_pipe = true;
+        if (k && !strcmp(k, "pipe_notma")) ctx->k1_pipe = ctx->no_tma_store = true;
         if (k && !strcmp(k, "ws")) ctx->k1_pipe = false;
     }
     ctx->hdr_w = -1;
@@ -772,6 +777,53 @@ static int ensure_tables(jpgb200_ctx *ctx, int w, int h, int quality, int ratio)
 
 /* ---- launch sequencing --------------------------------------------------------------------- */
 
+/* tensor maps of the coefficient buffer for K1's TMA stores (k1_pipe.cuh); cached per buffer */
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *, const cuuint64_t *,
+                                  const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static void make_store_maps(jpgb200_ctx *ctx, K1PStore *st, int16_t *zz, const long long n[3], long long zz_stride, int nframes)
+{
+    memset(st, 0, sizeof *st);
+    st->row_cb = n[0];
+    st->row_cr = n[0] + n[1];
+    st->rows_per_frame = zz_stride / 64;
+    const long long rows = (nframes > 1 ? (long long)(nframes - 1) * st->rows_per_frame : 0) + n[0] + n[1] + n[2];
+    if (ctx->no_tma_store || (zz_stride % 64) || rows >= (1ll << 31)) return;
+    if (ctx->tm_ptr == zz && ctx->tm_rows == rows) {
+        st->box32 = ctx->tm32;
+        st->box16 = ctx->tm16;
+        st->enabled = 1;
+        return;
+    }
+    static EncodeTiledFn fn = NULL;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *pfn = NULL;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &pfn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)pfn;
+    }
+    if (!fn) return;
+    const cuuint64_t gdim[2] = {64, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {128};
+    const cuuint32_t estr[2] = {1, 1};
+    const cuuint32_t box32[2] = {64, 32}, box16[2] = {64, 16};
+    if (fn(&ctx->tm32, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, zz, gdim, gstride, box32, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return;
+    if (fn(&ctx->tm16, CU_TENSOR_MAP_DATA_TYPE_UINT16, 2, zz, gdim, gstride, box16, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+           CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+        return;
+    ctx->tm_ptr = zz;
+    ctx->tm_rows = rows;
+    st->box32 = ctx->tm32;
+    st->box16 = ctx->tm16;
+    st->enabled = 1;
+}
+
 static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w, int h,
                      int ratio, const long long n[3], int nframes, long long plane_stride, int16_t *zz,
                      long long zz_stride, int has_halo)
@@ -807,25 +859,28 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
     if (aligned16 && ctx->k1_pipe && !ctx->k1_plain) {
         /* persistent CTAs, warps specialised and software-pipelined over tiles (k1_pipe.cuh) */
         if (!ctx->k1p_attr_set) {
-            CK(cudaFuncSetAttribute((k1_transform_pipe<0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1PSmem)));
-            CK(cudaFuncSetAttribute((k1_transform_pipe<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1PSmem)));
-            CK(cudaFuncSetAttribute((k1_transform_pipe<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1PSmem)));
-            CK(cudaFuncSetAttribute((k1_transform_pipe<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1PSmem)));
+            CK(cudaFuncSetAttribute((k1_transform_pipe<0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1PSmem) + 1024));
+            CK(cudaFuncSetAttribute((k1_transform_pipe<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1PSmem) + 1024));
+            CK(cudaFuncSetAttribute((k1_transform_pipe<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1PSmem) + 1024));
+            CK(cudaFuncSetAttribute((k1_transform_pipe<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1PSmem) + 1024));
             ctx->k1p_attr_set = true;
         }
         const long long n_tiles = (long long)p.tiles_per_row * (h / 8) * nframes;
         const long long resident = (long long)ctx->sm_count * K1P_MIN_CTAS;
         const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+        K1PStore st;
+        make_store_maps(ctx, &st, zz, n, zz_stride, nframes);
+        const size_t smem = sizeof(K1PSmem) + 1024;
         LaunchScope ls(ctx, KI_K1);
         if (ctx->std_mode) {
             if (ratio == 0)
-                k1_transform_pipe<0, true><<<grid, K1_THREADS, sizeof(K1PSmem), ctx->stream>>>(p, n_tiles);
+                k1_transform_pipe<0, true><<<grid, K1_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
             else
-                k1_transform_pipe<1, true><<<grid, K1_THREADS, sizeof(K1PSmem), ctx->stream>>>(p, n_tiles);
+                k1_transform_pipe<1, true><<<grid, K1_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
         } else if (ratio == 0)
-            k1_transform_pipe<0, false><<<grid, K1_THREADS, sizeof(K1PSmem), ctx->stream>>>(p, n_tiles);
+            k1_transform_pipe<0, false><<<grid, K1_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
         else
-            k1_transform_pipe<1, false><<<grid, K1_THREADS, sizeof(K1PSmem), ctx->stream>>>(p, n_tiles);
+            k1_transform_pipe<1, false><<<grid, K1_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
     } else if (aligned16 && !ctx->k1_plain && (!ctx->k1_cta || ctx->std_mode)) {
         /* persistent CTAs of four autonomous warps fed by TMA bulk copies (k1_warp.cuh) */
         if (!ctx->k1_attr_set) {

@@ -11,9 +11,9 @@
  *   -- barrier A --
  *   warps 0..2       phase 2 of tile i : warp c transforms the 32 blocks of component c, every
  *                    lane busy; results wait in registers
- *   warp 3           meanwhile: cp.async prefetch of tile i+1's raw rows, and phase 3 of tile
- *                    i-1 (its coefficients, still in shared memory, go out with coalesced 16-byte
- *                    stores)
+ *   warp 3           meanwhile: cp.async prefetch of tile i+2's raw rows into a three-slot ring,
+ *                    and phase 3 of tile i-1 (its coefficients, still in shared memory, go out
+ *                    with coalesced 16-byte stores)
  *   -- barrier C --  (named barrier: warp 3 arrives when tile i-1 has left shared memory)
  *   warps 0..2       store tile i's coefficients into shared memory
  *   -- barrier B --  (tile i+1's raw rows have landed)
@@ -23,20 +23,42 @@
 #ifndef JPGB200_K1_PIPE_CUH
 #define JPGB200_K1_PIPE_CUH
 
+#include <cuda.h>
+
 #include "k1_transform.cuh"
 #include "k1_warp.cuh"
 
 namespace jpgb200 {
 
-#define K1P_STAGES 2
+#ifndef K1P_STAGES
+#define K1P_STAGES 2 /* ring of raw tiles: prefetch distance K1P_STAGES-1 */
+#endif
 #define K1P_MIN_CTAS 4
 
 struct K1PSmem {
+    K1Out sOut[3]; /* first: the TMA store's 128-byte swizzle wants 1 KB alignment */
     uint8_t raw[K1P_STAGES][3][8][K1_ROW_BYTES]; /* [slot][plane][row][x] */
     K1F sF[3];
-    K1Out sOut[3];
     float mul[2][64];
 };
+
+/* The coefficients as a 2-D tensor [block][64 x int16] for TMA stores: a tile's component row
+ * (32 blocks x 128 B, or 16 for a 4:2:2 chroma half) leaves shared memory with ONE instruction.
+ * K1Out's XOR of the 16-byte chunk index with (row & 7) is exactly CU_TENSOR_MAP_SWIZZLE_128B. */
+struct K1PStore {
+    CUtensorMap box32, box16;
+    long long row_cb, row_cr; /* first Cb / Cr block (tensor row); Y starts at 0 */
+    long long rows_per_frame; /* zz_stride / 64 */
+    int enabled;
+};
+
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap *tm, const void *smem, int c0, int c1)
+{
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tm), "r"(c0), "r"(c1),
+                 "r"(sa)
+                 : "memory");
+}
 
 /* warp 3: asynchronous fetch of one tile's raw rows, 16 bytes per copy.  The block of column BW-1
  * is fetched one pixel row higher; row -1 of an image without halo is left alone. */
@@ -106,12 +128,46 @@ __device__ __forceinline__ void k1p_phase3(const K1Out *sOut, const K1Params &p,
     }
 }
 
-template <int RATIO, bool STD = false>
-__global__ void __launch_bounds__(K1_THREADS, K1P_MIN_CTAS) k1_transform_pipe(const K1Params p, long long n_tiles)
+/* warp 3: a whole tile with three (4:2:2: three smaller) TMA tensor stores; tiles cut short by the
+ * image's right edge take the manual path (a full box would spill into the next block row) */
+template <int RATIO>
+__device__ __forceinline__ void k1p_store(const K1Out *sOut, const K1Params &p, const K1PStore &st, const K1Tile &tl, int lane)
 {
-    extern __shared__ __align__(128) unsigned char k1_smem[];
+    const bool full = (tl.tb0 + K1_TILE_BLOCKS <= p.BW);
+    if (!st.enabled || !full) {
+        k1p_phase3<RATIO>(sOut, p, tl, lane);
+        return;
+    }
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* the transform warps' writes -> async proxy */
+    if (lane == 0) {
+        const long long f0 = (long long)tl.frame * st.rows_per_frame;
+        const long long ry = f0 + (long long)tl.by * p.BW + tl.tb0;
+        tma_store_2d(&st.box32, &sOut[0], 0, (int)ry);
+        if (RATIO == 0) {
+            tma_store_2d(&st.box32, &sOut[1], 0, (int)(st.row_cb + ry));
+            tma_store_2d(&st.box32, &sOut[2], 0, (int)(st.row_cr + ry));
+        } else {
+            const long long rc = f0 + (long long)tl.by * (p.BW >> 1) + (tl.tb0 >> 1);
+            tma_store_2d(&st.box16, &sOut[1][0], 0, (int)(st.row_cb + rc));
+            tma_store_2d(&st.box16, &sOut[1][16], 0, (int)(st.row_cr + rc));
+        }
+        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+        asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); /* shared memory has been read */
+    }
+    __syncwarp();
+}
+
+template <int RATIO, bool STD = false>
+__global__ void __launch_bounds__(K1_THREADS, K1P_MIN_CTAS) k1_transform_pipe(const K1Params p, long long n_tiles,
+                                                                              const __grid_constant__ K1PStore st)
+{
+    extern __shared__ unsigned char k1_smem_raw[];
+    /* 1 KB alignment for the swizzled TMA source */
+    unsigned char *k1_smem = k1_smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(k1_smem_raw) & 1023u)) & 1023u);
     K1PSmem &S = *reinterpret_cast<K1PSmem *>(k1_smem);
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    /* Warp w of every CTA runs on scheduler w % 4: rotate the roles with the CTA index so that the
+     * service role (and the idle transform role of 4:2:2) is spread over the SM's four schedulers */
+    const int tid = threadIdx.x, lane = tid & 31, w = ((tid >> 5) + (int)(blockIdx.x & 3u)) & 3;
     constexpr int NP2 = (RATIO == 0) ? 3 : 2; /* transform warps with work */
 
     S.mul[tid >> 6][tid & 63] = p.mul[tid >> 6][tid & 63];
@@ -119,14 +175,22 @@ __global__ void __launch_bounds__(K1_THREADS, K1P_MIN_CTAS) k1_transform_pipe(co
         for (int i = tid; i < p.clear_n; i += K1_THREADS) p.clear[i] = 0u;
     K1Tile tl = k1_tile(p, blockIdx.x), prev = tl;
     if (w == 3) {
-        k1p_fetch<STD>(p, S.raw[0], tl, lane);
-        cp_async_wait_all();
+        /* prologue: the first K1P_STAGES-1 tiles of the ring */
+#pragma unroll
+        for (int d = 0; d < K1P_STAGES - 1; d++) {
+            const long long td = (long long)blockIdx.x + (long long)d * gridDim.x;
+            if (td < n_tiles)
+                k1p_fetch<STD>(p, S.raw[d], k1_tile(p, td), lane);
+            else
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        asm volatile("cp.async.wait_group %0;\n" ::"n"(K1P_STAGES - 2) : "memory");
     }
     __syncthreads();
 
     int it = 0;
     for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
-        const int s = it & 1;
+        const int s = it % K1P_STAGES;
         /* ---- phase 1: warp k, lane j ---- */
         {
             const int k = w;
@@ -160,16 +224,17 @@ __global__ void __launch_bounds__(K1_THREADS, K1P_MIN_CTAS) k1_transform_pipe(co
 
         const long long tn = t + gridDim.x;
         if (w == 3) {
-            K1Tile nx = tl;
-            if (tn < n_tiles) {
-                nx = k1_tile(p, tn);
-                k1p_fetch<STD>(p, S.raw[s ^ 1], nx, lane);
-            }
-            if (it > 0) k1p_phase3<RATIO>(S.sOut, p, prev, lane);
+            /* the fetch of tile i+K1P_STAGES-1 first (its loads are in flight during the copy-out) */
+            const long long tn2 = t + (long long)(K1P_STAGES - 1) * gridDim.x;
+            if (tn2 < n_tiles)
+                k1p_fetch<STD>(p, S.raw[(it + K1P_STAGES - 1) % K1P_STAGES], k1_tile(p, tn2), lane);
+            else
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
+            if (it > 0) k1p_store<RATIO>(S.sOut, p, st, prev, lane);
             asm volatile("bar.arrive 1, 128;\n" ::: "memory"); /* C: tile i-1 has left shared memory */
-            cp_async_wait_all();
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(K1P_STAGES - 2) : "memory"); /* tile i+1's rows are in */
             prev = tl;
-            tl = nx;
+            if (tn < n_tiles) tl = k1_tile(p, tn);
         } else {
             /* ---- phase 2: warp c, lane = block ---- */
             uint32_t o[32];
@@ -206,7 +271,10 @@ __global__ void __launch_bounds__(K1_THREADS, K1P_MIN_CTAS) k1_transform_pipe(co
         }
         __syncthreads(); /* B: tile i's coefficients are in shared memory, tile i+1's raw rows have landed */
     }
-    if (w == 3 && it > 0) k1p_phase3<RATIO>(S.sOut, p, prev, lane);
+    if (w == 3 && it > 0) {
+        k1p_store<RATIO>(S.sOut, p, st, prev, lane);
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
 }
 
 }  // namespace jpgb200
