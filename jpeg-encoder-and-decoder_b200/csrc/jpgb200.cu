@@ -30,6 +30,7 @@
 #include "k1_transform.cuh"
 #include "k1_warp.cuh"
 #include "k1_pipe.cuh"
+#include "k1_pc.cuh"
 #include "tail.cuh"
 #include "taps.cuh"
 
@@ -80,6 +81,8 @@ struct jpgb200_ctx {
     bool fused_attr_set, k1_attr_set, ke_attr_set, k1p_attr_set;
     bool k1_plain; /* force the non-TMA K1 (tests) */
     bool k1_pipe;  /* the software-pipelined K1 (k1_pipe.cuh) */
+    bool k1_pc;    /* the producer/consumer K1 (k1_pc.cuh) */
+    bool k1c_attr_set;
     bool no_tma_store; /* k1_pipe: copy the coefficients out with ordinary stores (A/B runs) */
     CUtensorMap tm32, tm16; /* tensor maps of the coefficient buffer, cached */
     int16_t *tm_ptr;
@@ -416,6 +419,8 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         if (k && !strcmp(k, "cta")) ctx->k1_cta = true;
         if (k && !strcmp(k, "pipe")) ctx->k1_pipe = true;
         if (k && !strcmp(k, "pipe_notma")) ctx->k1_pipe = ctx->no_tma_store = true;
+        if (k && !strcmp(k, "pc")) ctx->k1_pc = true;
+        if (k && !strcmp(k, "pc_notma")) ctx->k1_pc = ctx->no_tma_store = true;
         if (k && !strcmp(k, "ws")) ctx->k1_pipe = false;
     }
     ctx->hdr_w = -1;
@@ -512,6 +517,7 @@ extern "C" int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on)
     ctx->k1_plain = (on == 1);
     ctx->k1_cta = (on == 2);
     ctx->k1_pipe = (on == 3);
+    ctx->k1_pc = (on == 4);
     return JPGB200_OK;
 }
 
@@ -856,7 +862,32 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
     }
     const bool aligned16 = (w % 16 == 0) && (((uintptr_t)d_r | (uintptr_t)d_g | (uintptr_t)d_b) % 16 == 0) &&
                            (plane_stride % 16 == 0);
-    if (aligned16 && ctx->k1_pipe && !ctx->k1_plain) {
+    if (aligned16 && ctx->k1_pc && !ctx->k1_plain) {
+        /* eight specialised warps per CTA handing tiles over through mbarriers (k1_pc.cuh) */
+        const size_t smem = sizeof(K1CSmem) + 1024;
+        if (!ctx->k1c_attr_set) {
+            CK(cudaFuncSetAttribute((k1_transform_pc<0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute((k1_transform_pc<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute((k1_transform_pc<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute((k1_transform_pc<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->k1c_attr_set = true;
+        }
+        const long long n_tiles = (long long)p.tiles_per_row * (h / 8) * nframes;
+        const long long resident = (long long)ctx->sm_count * K1C_MIN_CTAS;
+        const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+        K1PStore st;
+        make_store_maps(ctx, &st, zz, n, zz_stride, nframes);
+        LaunchScope ls(ctx, KI_K1);
+        if (ctx->std_mode) {
+            if (ratio == 0)
+                k1_transform_pc<0, true><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
+            else
+                k1_transform_pc<1, true><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
+        } else if (ratio == 0)
+            k1_transform_pc<0, false><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
+        else
+            k1_transform_pc<1, false><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
+    } else if (aligned16 && ctx->k1_pipe && !ctx->k1_plain) {
         /* persistent CTAs, warps specialised and software-pipelined over tiles (k1_pipe.cuh) */
         if (!ctx->k1p_attr_set) {
             CK(cudaFuncSetAttribute((k1_transform_pipe<0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(K1PSmem) + 1024));

@@ -1,0 +1,215 @@
+/*
+ * K1, producer/consumer form (k1_transform_pc): eight specialised warps per CTA, two CTAs per SM,
+ * no CTA-wide barrier -- every hand-over is an mbarrier.
+ *
+ *   convert warps 0..3  (k = warp)  fetch rows k and 7-k of the tile's 32 blocks two tiles ahead
+ *                       (cp.async, private ring), turn them into FP32 row pairs (PRMT + FADD2,
+ *                       FFMA2) and fill sample buffer b          -> arrive  samples_full[b]
+ *   transform warps 4..6 (c = warp - 4)  wait samples_full[b], pull their 32 blocks (one per
+ *                       lane, 64 samples) into registers          -> arrive  samples_free[b]
+ *                       packed FDCT, FFMA2 quantise, zig-zag pack; wait coef_free[o], store the
+ *                       rows (128-byte swizzle)                   -> arrive  coef_full[o]
+ *   store warp 7        wait coef_full[o], three TMA tensor stores (32 blocks x 128 B per
+ *                       component), wait until shared memory is read -> arrive  coef_free[o]
+ *
+ * Sample and coefficient buffers are double; because a transform warp copies its samples into
+ * registers before it computes, the convert warps run one to two tiles ahead and a transform warp
+ * goes from one tile's arithmetic straight into the next: the FMA pipes are the resource this
+ * form tries to keep busy (the CTA-barrier and warp-autonomous forms leave them idle 45 % of the
+ * time, profiles/README.md).
+ */
+#ifndef JPGB200_K1_PC_CUH
+#define JPGB200_K1_PC_CUH
+
+#include "k1_pipe.cuh"
+
+namespace jpgb200 {
+
+#define K1C_THREADS 256
+#define K1C_STAGES 3
+#define K1C_MIN_CTAS 2
+
+struct K1CSmem {
+    K1Out coef[2][3];                       /* 24 KB, 1 KB aligned (TMA swizzle) */
+    K1F samples[2][3];                      /* 48 KB */
+    uint8_t raw[4][K1C_STAGES][3][2][K1_ROW_BYTES]; /* [convert warp][slot][plane][row k | row 7-k][x]  18 KB */
+    float mul[2][64];
+    unsigned long long samples_full[2], samples_free[2], coef_full[2], coef_free[2];
+};
+
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
+{
+    const unsigned a = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
+}
+
+/* convert warp k: its two rows of one tile, 16 bytes per copy (3 per lane).  The block of column
+ * BW-1 is fetched one pixel row higher; row -1 of an image without halo is left
+ * alone and replaced by the caller's out-of-bounds bytes at conversion time. */
+template <bool STD>
+__device__ __forceinline__ void k1c_fetch(const K1Params &p, uint8_t (*raw)[2][K1_ROW_BYTES], const K1Tile &tl, int k, int lane)
+{
+    const int part = lane & 15, sel = lane >> 4;
+    const int y = sel ? 7 - k : k;
+    const int bx = tl.tb0 + 2 * part;
+    if (bx < p.BW) {
+        const long long row = (long long)tl.by * 8 + y;
+        const long long off = (long long)tl.frame * p.plane_stride + row * p.W + (long long)bx * 8;
+        const int jl = STD ? -1 : p.BW - 1 - bx;
+        if (jl == 0 || jl == 1) {
+            const bool up_ok = (row - 1 >= 0) || p.has_halo;
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                const uint8_t *src = (c == 0 ? p.r : (c == 1 ? p.g : p.b)) + off;
+                uint8_t *dst = &raw[c][sel][part * 16];
+                if (jl == 1) cp_async8(dst, src);
+                if (up_ok) cp_async8(dst + 8 * jl, src + 8 * jl - p.W);
+            }
+        } else {
+#pragma unroll
+            for (int c = 0; c < 3; c++)
+                cp_async16(&raw[c][sel][part * 16], (c == 0 ? p.r : (c == 1 ? p.g : p.b)) + off);
+        }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
+template <int RATIO, bool STD = false>
+__global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pc(const K1Params p, long long n_tiles,
+                                                                              const __grid_constant__ K1PStore st)
+{
+    extern __shared__ unsigned char k1_smem_raw[];
+    unsigned char *k1_smem = k1_smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(k1_smem_raw) & 1023u)) & 1023u);
+    K1CSmem &S = *reinterpret_cast<K1CSmem *>(k1_smem);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int NT = (RATIO == 0) ? 3 : 2; /* transform warps with work */
+
+    if (tid < 128) S.mul[tid >> 6][tid & 63] = p.mul[tid >> 6][tid & 63];
+    if (blockIdx.x == 0)
+        for (int i = tid; i < p.clear_n; i += K1C_THREADS) p.clear[i] = 0u;
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&S.samples_full[b], 4);
+            mbar_init(&S.samples_free[b], NT);
+            mbar_init(&S.coef_full[b], NT);
+            mbar_init(&S.coef_free[b], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (w < 4) {
+        /* ================= convert warp k ================= */
+        const int k = w;
+        uint8_t(*ring)[3][2][K1_ROW_BYTES] = S.raw[k];
+#pragma unroll
+        for (int d = 0; d < K1C_STAGES - 1; d++) {
+            const long long td = (long long)blockIdx.x + (long long)d * gridDim.x;
+            if (td < n_tiles)
+                k1c_fetch<STD>(p, ring[d], k1_tile(p, td), k, lane);
+            else
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        int it = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+            const int b = it & 1;
+            const unsigned use = (unsigned)(it >> 1);
+            const K1Tile tl = k1_tile(p, t);
+            {
+                const long long tn = t + (long long)(K1C_STAGES - 1) * gridDim.x;
+                if (tn < n_tiles)
+                    k1c_fetch<STD>(p, ring[(it + K1C_STAGES - 1) % K1C_STAGES], k1_tile(p, tn), k, lane);
+                else
+                    asm volatile("cp.async.commit_group;\n" ::: "memory");
+            }
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(K1C_STAGES - 1) : "memory");
+            __syncwarp();
+            const uint8_t(*raw)[2][K1_ROW_BYTES] = ring[it % K1C_STAGES];
+            const int jl = STD ? -1 : p.BW - 1 - tl.tb0;
+            const bool top_oob = (tl.by == 0 && !p.has_halo && k == 0);
+            auto ld8 = [&](int c, int sel, int j) -> uint2 {
+                if (top_oob && sel == 0 && j == jl) return ld_oob(p.oob + 8 * c);
+                return *reinterpret_cast<const uint2 *>(&raw[c][sel][j * 8]);
+            };
+            uint2 pa[3], pb[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                pa[c] = ld8(c, 0, lane);
+                pb[c] = ld8(c, 1, lane);
+            }
+            uint4 ca[3], cb[3];
+            if (RATIO == 1) {
+                const int jc = lane & 15;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const uint2 l0 = ld8(c, 0, 2 * jc), l1 = ld8(c, 0, 2 * jc + 1);
+                    const uint2 h0 = ld8(c, 1, 2 * jc), h1 = ld8(c, 1, 2 * jc + 1);
+                    ca[c] = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                    cb[c] = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                }
+            }
+            mbar_wait(&S.samples_free[b], (use & 1u) ^ 1u); /* the transform warps have taken tile it-2 */
+            k1_convert_full<RATIO, STD>(S.samples[b], k, lane, pa, pb);
+            if (RATIO == 1) k1_convert_chroma422<STD>(S.samples[b], k, lane, ca, cb);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.samples_full[b]);
+        }
+    } else if (w < 4 + NT) {
+        /* ================= transform warp c ================= */
+        const int c = w - 4;
+        const float4 *m4 = reinterpret_cast<const float4 *>(S.mul[c == 0 ? 0 : 1]);
+        int it = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+            const int b = it & 1;
+            const unsigned use = (unsigned)(it >> 1);
+            f32x2 P[4][8], Q[8][4];
+            mbar_wait(&S.samples_full[b], use & 1u);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int x = 0; x < 8; x++) P[k][x] = S.samples[b][c][k][x][lane];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.samples_free[b]);
+            fdct8x8_p(P, Q);
+            float f[64];
+#pragma unroll
+            for (int v = 0; v < 8; v++)
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const float4 m = m4[v * 2 + hh];
+                    const f32x2 q0 = p_fma(Q[v][2 * hh], make_float2(m.x, m.y), p_bc(JPGB_ROUND_MAGIC));
+                    const f32x2 q1 = p_fma(Q[v][2 * hh + 1], make_float2(m.z, m.w), p_bc(JPGB_ROUND_MAGIC));
+                    f[v * 8 + 4 * hh + 0] = q0.x;
+                    f[v * 8 + 4 * hh + 1] = q0.y;
+                    f[v * 8 + 4 * hh + 2] = q1.x;
+                    f[v * 8 + 4 * hh + 3] = q1.y;
+                }
+            uint32_t o[32];
+            zigzag_pack(f, o);
+            mbar_wait(&S.coef_free[b], (use & 1u) ^ 1u); /* tile it-2 has left the buffer */
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                S.coef[b][c][lane][j ^ (lane & 7)] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic writes -> the TMA's proxy */
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.coef_full[b]);
+        }
+    } else if (w == 7) {
+        /* ================= store warp ================= */
+        int it = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+            const int b = it & 1;
+            const unsigned use = (unsigned)(it >> 1);
+            const K1Tile tl = k1_tile(p, t);
+            mbar_wait(&S.coef_full[b], use & 1u);
+            k1p_store<RATIO>(S.coef[b], p, st, tl, lane); /* returns when shared memory has been read */
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.coef_free[b]);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
+}  // namespace jpgb200
+#endif

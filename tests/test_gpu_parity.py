@@ -401,12 +401,15 @@ def test_tma_and_plain_transform_agree(enc, w, h, q, ratio, seed):
         c = enc.coefficients(r, g, b, w, h, q, ratio)
         enc.set_plain_transform(3)
         d = enc.coefficients(r, g, b, w, h, q, ratio)
+        enc.set_plain_transform(4)
+        e = enc.coefficients(r, g, b, w, h, q, ratio)
     finally:
         enc.set_plain_transform(False)
         enc.set_oob_bytes(np.zeros(24, np.uint8))
     assert (a == p).all()
     assert (a == c).all()
     assert (a == d).all()
+    assert (a == e).all()
     assert_coeff_close(a, O.coefficients(r, g, b, w, h, q, ratio, oob=oob), "tma")
 
 
