@@ -64,10 +64,13 @@ int jpgb200_sync(jpgb200_ctx *ctx);
  * K3 (bit lengths) / K4 (scan) / K5 (pack) / K6 (stuffing) pipeline, kept for the MCU-row
  * partition and as a cross-check -- both produce identical bytes. */
 int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on);
-/* K1 selection: 0 (default) = persistent kernel of autonomous warps fed by TMA bulk copies
- * whenever width % 16 == 0; 1 = always the direct-load kernel (the only one for
- * width % 16 == 8); 2 = the earlier TMA kernel whose phases are separated by CTA barriers.
- * Identical results. */
+/* K1 selection (identical results; the alternatives are kept for A/B runs and as cross-checks):
+ *   0 (default) producer/consumer form: convert, transform and store warps hand tiles over through
+ *               mbarriers, TMA tensor stores (csrc/k1_pc.cuh); needs width % 16 == 0
+ *   1           one CTA per tile, direct loads (the only form for width % 16 == 8)
+ *   2           persistent CTAs, TMA bulk loads, phases separated by CTA barriers
+ *   3           software-pipelined CTA (csrc/k1_pipe.cuh)
+ *   4           autonomous warps, per-warp cp.async ring (csrc/k1_warp.cuh) */
 int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on);
 /* Arithmetic of the transform: 0 (default) = bug-compatible with the reference (its Cb sign slip,
  * src/preprocess.c:161, and the last block column read one pixel row higher, :199-211); 1 =

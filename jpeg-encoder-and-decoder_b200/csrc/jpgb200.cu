@@ -81,7 +81,8 @@ struct jpgb200_ctx {
     bool fused_attr_set, k1_attr_set, ke_attr_set, k1p_attr_set;
     bool k1_plain; /* force the non-TMA K1 (tests) */
     bool k1_pipe;  /* the software-pipelined K1 (k1_pipe.cuh) */
-    bool k1_pc;    /* the producer/consumer K1 (k1_pc.cuh) */
+    bool k1_pc;    /* the producer/consumer K1 (k1_pc.cuh): the default */
+    bool k1_ws;    /* the warp-autonomous K1 (k1_warp.cuh) */
     bool k1c_attr_set;
     bool no_tma_store; /* k1_pipe: copy the coefficients out with ordinary stores (A/B runs) */
     CUtensorMap tm32, tm16; /* tensor maps of the coefficient buffer, cached */
@@ -411,17 +412,17 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
     ctx->device = device;
     ctx->q_cached = -1;
     ctx->legacy_entropy = true; /* measured faster than the fused K35 so far */
+    ctx->k1_pc = true;          /* K1 default: the producer/consumer form (fastest measured) */
     {
         const char *e = getenv("JPGB200_ENTROPY"); /* "fused" | "staged": experiment switch for bench runs */
         if (e && !strcmp(e, "fused")) ctx->legacy_entropy = false;
         const char *k = getenv("JPGB200_K1"); /* "plain" | "tma" */
-        if (k && !strcmp(k, "plain")) ctx->k1_plain = true;
-        if (k && !strcmp(k, "cta")) ctx->k1_cta = true;
-        if (k && !strcmp(k, "pipe")) ctx->k1_pipe = true;
-        if (k && !strcmp(k, "pipe_notma")) ctx->k1_pipe = ctx->no_tma_store = true;
-        if (k && !strcmp(k, "pc")) ctx->k1_pc = true;
-        if (k && !strcmp(k, "pc_notma")) ctx->k1_pc = ctx->no_tma_store = true;
-        if (k && !strcmp(k, "ws")) ctx->k1_pipe = false;
+        if (k && !strcmp(k, "plain")) ctx->k1_plain = true, ctx->k1_pc = false;
+        if (k && !strcmp(k, "cta")) ctx->k1_cta = true, ctx->k1_pc = false;
+        if (k && !strcmp(k, "pipe")) ctx->k1_pipe = true, ctx->k1_pc = false;
+        if (k && !strcmp(k, "pipe_notma")) ctx->k1_pipe = ctx->no_tma_store = true, ctx->k1_pc = false;
+        if (k && !strcmp(k, "pc_notma")) ctx->no_tma_store = true;
+        if (k && !strcmp(k, "ws")) ctx->k1_ws = true, ctx->k1_pc = false;
     }
     ctx->hdr_w = -1;
     ctx->err[0] = 0;
@@ -514,10 +515,11 @@ extern "C" int jpgb200_sync(jpgb200_ctx *ctx)
 extern "C" int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;
+    ctx->k1_pc = (on == 0);
     ctx->k1_plain = (on == 1);
     ctx->k1_cta = (on == 2);
     ctx->k1_pipe = (on == 3);
-    ctx->k1_pc = (on == 4);
+    ctx->k1_ws = (on == 4);
     return JPGB200_OK;
 }
 

@@ -386,9 +386,10 @@ def test_staged_and_fused_entropy_agree(enc, w, h, q, ratio, kind, seed):
 @pytest.mark.parametrize("w,h,q,ratio,seed", [(272, 24, 75, 0, 31), (528, 40, 50, 0, 32), (544, 32, 90, 1, 33),
                                               (1920, 1080, 75, 0, 34), (256, 8, 75, 1, 35), (16, 16, 75, 0, 36)])
 def test_tma_and_plain_transform_agree(enc, w, h, q, ratio, seed):
-    """K1 has three forms (autonomous warps + TMA ring; CTA-barrier phases + TMA ring; one CTA per
-    tile + direct loads): bit-identical coefficients, including the shifted last block column
-    and ragged tiles."""
+    """K1 has five forms (producer/consumer with mbarriers and TMA stores -- the default;
+    one CTA per tile + direct loads; CTA-barrier phases + TMA bulk loads; software-pipelined CTA;
+    autonomous warps): bit-identical coefficients, including the shifted last block column and
+    ragged tiles."""
     r, g, b = O.synth_planes(w, h, seed, 0, 0)
     oob = np.arange(24, dtype=np.uint8) * 7 + 3
     enc.set_oob_bytes(oob)
