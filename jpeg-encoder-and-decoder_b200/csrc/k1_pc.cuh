@@ -16,7 +16,9 @@
  * registers before it computes, the convert warps run one to two tiles ahead and a transform warp
  * goes from one tile's arithmetic straight into the next: the FMA pipes are the resource this
  * form tries to keep busy (the CTA-barrier and warp-autonomous forms leave them idle 45 % of the
- * time, profiles/README.md).
+ * time, profiles/README.md).  Moving the FDCT's row pass (all of it: 79.7 us; its first twelve
+ * operations: 78.6 us) into the convert warps, which own whole rows, was measured against doing
+ * it all in the transform warps (76.5 us): both roles are already equally busy.
  */
 #ifndef JPGB200_K1_PC_CUH
 #define JPGB200_K1_PC_CUH
