@@ -313,7 +313,7 @@ def run_b200(args):
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    roofline = {"bound": "hbm", "kernel": "k1_transform_ws<0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+    roofline = {"bound": "hbm", "kernel": "k1_transform_pc<0>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                 "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": 9 * NPX, "avg_launch_us": k1_avg_s * 1e6,
                 "k1_ms_per_step": k1_ms / args.steps, "k1_share_of_step": k1_ms / args.steps / ms_per_step,
