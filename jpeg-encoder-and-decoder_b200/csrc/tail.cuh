@@ -57,9 +57,9 @@ __device__ __forceinline__ uint32_t be32(uint32_t w) { return __byte_perm(w, 0, 
 __device__ __forceinline__ unsigned long long tail_prefix(const uint32_t *cta, const uint32_t *sup, long long chunk, int lane)
 {
     unsigned long long part = 0ull;
-    const long long s = chunk >> EC_SUPER_SHIFT;
-    for (long long i = lane; i < s; i += 32) part += sup[i];
-    for (long long i = (s << EC_SUPER_SHIFT) + lane; i < chunk; i += 32) part += cta[i];
+    const int c = (int)chunk, s = c >> EC_SUPER_SHIFT; /* chunk counts stay far below 2^31 */
+    for (int i = lane; i < s; i += 32) part += sup[i];
+    for (int i = (s << EC_SUPER_SHIFT) + lane; i < c; i += 32) part += cta[i];
 #pragma unroll
     for (int d = 16; d > 0; d >>= 1) part += __shfl_xor_sync(0xffffffffu, part, d);
     return part;
@@ -219,6 +219,28 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_scatter(const TailParams q)
                     nvalid = left >= 4 ? 4 : left;
                 }
                 const uint32_t m = ff_mask(v, nvalid);
+                const uint32_t round0 = base + 32u * (uint32_t)r;
+                const bool full_round = (round0 + 32u) * 4u <= g.nB; /* warp-uniform: 128 owned bytes */
+                if (full_round && __ballot_sync(0xffffffffu, m != 0u) == 0u) {
+                    /* no 0xFF in these 128 bytes (the common case): they go out as they are, with
+                     * aligned 32-bit stores -- words straddling two lanes are assembled by shuffle */
+                    uint8_t *d = q.out + P;
+                    const unsigned a = (unsigned)((unsigned long long)(uintptr_t)d & 3ull);
+                    const uint32_t own = __byte_perm(v, 0, 0x0123); /* memory order */
+                    const uint32_t prv = __shfl_up_sync(0xffffffffu, own, 1);
+                    if (a == 0u) {
+                        reinterpret_cast<uint32_t *>(d)[lane] = own;
+                    } else {
+                        if (lane > 0)
+                            reinterpret_cast<uint32_t *>(d - a)[lane] = __funnelshift_r(prv, own, 8u * (4u - a));
+                        else
+                            for (unsigned t = 0; t < 4u - a; t++) d[t] = (uint8_t)(own >> (8u * t));
+                        if (lane == 31)
+                            for (unsigned t = 0; t < a; t++) d[128u - a + t] = (uint8_t)(own >> (8u * (4u - a + t)));
+                    }
+                    P += 128ull;
+                    continue;
+                }
                 const uint32_t n_out = (uint32_t)nvalid + ((uint32_t)__popc(m) >> 3);
                 uint32_t inc = n_out;
 #pragma unroll
