@@ -52,7 +52,8 @@ def nvcc_path():
 def build_cuda(force=False, verbose=False):
     srcs = _sources(CSRC, (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "jpgb200.h")]
     if force or _newer(LIB, srcs):
-        cmd = [nvcc_path()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "jpgb200.cu")]
+        extra = os.environ.get("JPGB200_NVCC_EXTRA", "").split()  # e.g. -DK1C_NC=2 for A/B builds of a kernel variant
+        cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "jpgb200.cu")]
         subprocess.check_call(cmd)
     return LIB
 
