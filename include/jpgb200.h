@@ -12,10 +12,15 @@
  * Conventions
  *   - r,g,b are the three u8 planes exactly as bmp_GetRed/Green/Blue deliver them
  *     (src/headers/bitmap.h:34-44; top-down raster, no row padding).
- *   - sample_ratio: 0 = NO_CHROMA_SUBSAMPLING (4:4:4), 1 = HORIZONTAL_SUBSAMPLING (4:2:2)
- *     (src/headers/jpg_encode.h:13-14).  4:2:0 is not built (src/downsample.c:29 is a stub).
- *   - width % 8 == 0 (4:4:4) or % 16 == 0 (4:2:2), height % 8 == 0: the reference's padding
- *     path is broken (src/preprocess.c:83-98,131-152), so other sizes are rejected.
+ *   - sample_ratio: 0 = NO_CHROMA_SUBSAMPLING (4:4:4), 1 = HORIZONTAL_SUBSAMPLING (4:2:2),
+ *     2 = HORIZONTAL_VERTICAL_SUBSAMPLING (4:2:0) (src/headers/jpg_encode.h:13-15).  The
+ *     reference's 4:2:2 and 4:2:0 are printf stubs (src/downsample.c:24-32): both are defined
+ *     here as box averages of the level-shifted chroma.  For 4:2:0 the luma blocks of the
+ *     coefficient layout are in MCU order (Y00 Y01 Y10 Y11 per 16x16 MCU); the MCU-row partition
+ *     (jpgb200_band_*) and the single-launch entropy kernel do not take it.
+ *   - width % 8 == 0 (4:4:4) or % 16 == 0 (4:2:2, 4:2:0), height % 8 == 0 (% 16 for 4:2:0): the
+ *     reference's padding path is broken (src/preprocess.c:83-98,131-152), so other sizes are
+ *     rejected -- jpgb200_encode_planar_any takes any size.
  *   - quality 24..97: outside it the reference's scale_table yields zero divisors or
  *     entries above 255 (src/quantise.c:81-83).
  *   - "device" pointers are CUDA device addresses on the context's GPU, passed as plain

@@ -65,7 +65,7 @@ struct EcParams {
 
 template <int RATIO>
 struct EcCfg {
-    static const int BPM = (RATIO == 0) ? 3 : 4;
+    static const int BPM = (RATIO == 0) ? 3 : (RATIO == 1 ? 4 : 6); /* 2 = 4:2:0: 4 luma blocks per MCU, stored in MCU order */
     static const int NT = EC_MCUS * BPM;
     static const int STAGE_WORDS = (RATIO == 0) ? 3072 : 1664; /* chunk stream staging (static smem <= 48 KB) */
 };
@@ -132,16 +132,17 @@ __device__ __forceinline__ void ec_fill(uint4 (*sC)[EC_ROW_CHUNKS], const EcPara
     const int nv = left < EC_MCUS ? (int)left : EC_MCUS; /* valid MCUs of this chunk */
     const uint4 *z = reinterpret_cast<const uint4 *>(p.zz);
     {
-        const int n0 = (RATIO == 0 ? nv : 2 * nv) * 8;
-        const uint4 *src = z + (RATIO == 0 ? m0 : 2 * m0) * 8;
+        constexpr int YPM = (RATIO == 0) ? 1 : (RATIO == 1 ? 2 : 4); /* luma blocks per MCU */
+        const int n0 = YPM * nv * 8;
+        const uint4 *src = z + YPM * m0 * 8;
 #pragma unroll
-        for (int k = 0; k < ((RATIO == 0 ? 64 : 128) * 8 + NT - 1) / NT; k++) {
+        for (int k = 0; k < (YPM * 64 * 8 + NT - 1) / NT; k++) {
             const int i = k * NT + tid;
             if (i < n0) cp_async16(&sC[i >> 3][i & 7], src + i);
         }
     }
     {
-        const int n1 = nv * 8, r1 = (RATIO == 0 ? 64 : 128);
+        const int n1 = nv * 8, r1 = (RATIO == 0 ? 64 : (RATIO == 1 ? 128 : 256));
         const uint4 *s1 = z + (p.coff1 + m0) * 8, *s2 = z + (p.coff2 + m0) * 8;
 #pragma unroll
         for (int k = 0; k < (64 * 8 + NT - 1) / NT; k++) {
@@ -588,9 +589,10 @@ struct KeParams {
  * order inside the chunk (4:4:4: Y.0 Y.1 Cb Cr per MCU; 4:2:2: Y0.0 Y0.1 Y1.0 Y1.1 Cb Cr). */
 template <int RATIO>
 struct KeCfg {
-    static const int ROWS = EcCfg<RATIO>::NT;            /* coefficient rows (blocks) per chunk */
-    static const int NY = (RATIO == 0) ? 64 : 128;       /* luma blocks per chunk */
-    static const int NT = 2 * NY + 128;                  /* threads = entries: 256 / 384 */
+    static const int NY = (RATIO == 0) ? 64 : (RATIO == 1 ? 128 : 256); /* luma blocks per chunk */
+    static const int ROWS = NY + 128;                    /* coefficient rows (blocks) per chunk */
+    static const bool SPLIT = (RATIO != 2);              /* two lanes per luma block (4:2:0 has four luma blocks per MCU already) */
+    static const int NT = (SPLIT ? 2 : 1) * NY + 128;    /* threads = entries: 256 / 384 / 384 */
     static const int EPM = (RATIO == 0) ? 4 : 6;         /* entries per MCU */
     static const int PRIV = 12;                          /* words of private stream per entry */
     static const int PSTRIDE = PRIV + 1;                 /* odd: lanes hit distinct banks */
@@ -614,7 +616,29 @@ struct KeMap {
     __device__ __forceinline__ KeMap(const EcParams &p, long long m0, int tid)
     {
         constexpr int NY = KeCfg<RATIO>::NY;
-        if (tid < 2 * NY) {
+        if (RATIO == 2) {
+            /* 4:2:0: one lane per block; luma rows are already in stream order (MCU-major) */
+            part = 0;
+            if (tid < NY) {
+                luma = true;
+                comp = 0;
+                row = tid;
+                const int m = row >> 2;
+                e_local = blk_local = 6 * m + (row & 3);
+                gabs = 4 * m0 + row;
+                valid = (m0 + m) < p.n_mcu;
+                first_of_comp = (row == 0);
+            } else {
+                luma = false;
+                const int c = (tid - NY) >> 6, m = (tid - NY) & 63;
+                comp = 1 + c;
+                row = NY + 64 * c + m;
+                e_local = blk_local = 6 * m + 4 + c;
+                gabs = m0 + m + (c == 0 ? p.coff1 : p.coff2);
+                valid = (m0 + m) < p.n_mcu;
+                first_of_comp = (m == 0);
+            }
+        } else if (tid < 2 * NY) {
             luma = true;
             comp = 0;
             row = tid >> 1;
@@ -644,10 +668,10 @@ template <int RATIO, class Sink>
 __device__ __forceinline__ void ke_code(const uint4 (*sC)[EC_ROW_CHUNKS], const KeMap<RATIO> &mp, int diff, const HuffPack &sH,
                                         Sink &s)
 {
-    if (mp.luma)
+    if (mp.luma && KeCfg<RATIO>::SPLIT)
         ec_pack_part<false>(sC[mp.row], diff, mp.part, sH.ac[0], sH.dc[0], s);
     else
-        ec_pack_part<true>(sC[mp.row], diff, 0, sH.ac[1], sH.dc[1], s);
+        ec_pack_part<true>(sC[mp.row], diff, 0, sH.ac[mp.luma ? 0 : 1], sH.dc[mp.luma ? 0 : 1], s);
 }
 
 template <int RATIO>

@@ -174,10 +174,10 @@ extern "C" int jpgb200_quant_tables(int quality, int lum[64], int chr[64])
 
 extern "C" long long jpgb200_num_blocks(int w, int h, int ratio, long long n[3])
 {
-    if (w <= 0 || h <= 0 || (h % 8) || (ratio != 0 && ratio != 1)) return JPGB200_ERR_BAD_DIMS;
+    if (w <= 0 || h <= 0 || (h % (ratio == 2 ? 16 : 8)) || ratio < 0 || ratio > 2) return JPGB200_ERR_BAD_DIMS;
     if (w % (ratio ? 16 : 8)) return JPGB200_ERR_BAD_DIMS;
     long long ny = (long long)(w / 8) * (h / 8);
-    long long nc = ratio ? ny / 2 : ny;
+    long long nc = ratio == 2 ? ny / 4 : (ratio ? ny / 2 : ny);
     if (n) {
         n[0] = ny;
         n[1] = nc;
@@ -337,7 +337,7 @@ static int jfif_header_specs(int w, int h, int quality, int ratio, const HuffSpe
 {
     int lum[64], chr[64];
     if (check_dims && jpgb200_num_blocks(w, h, ratio, NULL) < 0) return JPGB200_ERR_BAD_DIMS;
-    if (w < 1 || h < 1 || w > 65535 || h > 65535 || (ratio != 0 && ratio != 1)) return JPGB200_ERR_BAD_DIMS;
+    if (w < 1 || h < 1 || w > 65535 || h > 65535 || ratio < 0 || ratio > 2) return JPGB200_ERR_BAD_DIMS;
     if (quality < 24 || quality > 97 || jpgb200_quant_tables(quality, lum, chr)) return JPGB200_ERR_BAD_QUALITY;
     if (cap < 640) return JPGB200_ERR_OUT_TOO_SMALL;
     size_t p = 0;
@@ -368,7 +368,7 @@ static int jfif_header_specs(int w, int h, int quality, int ratio, const HuffSpe
     p = put16(o, p, (unsigned)h);
     p = put16(o, p, (unsigned)w);
     o[p++] = 3;
-    const uint8_t sof[9] = {1, (uint8_t)(ratio == 1 ? 0x21 : 0x11), 0, 2, 0x11, 1, 3, 0x11, 1};
+    const uint8_t sof[9] = {1, (uint8_t)(ratio == 1 ? 0x21 : (ratio == 2 ? 0x22 : 0x11)), 0, 2, 0x11, 1, 3, 0x11, 1};
     memcpy(o + p, sof, 9);
     p += 9;
     static const int order[4] = {0, 2, 1, 3};
@@ -688,7 +688,7 @@ static long long n_chunks(const long long n[3]) { return (n[1] + EC_MCUS - 1) / 
 /* words of one chunk's slot: worst case 1658 bits per block (20-bit DC + 63 x 26-bit AC), 16-byte multiple */
 static long long slot_words(const long long n[3])
 {
-    const long long bpm = (n[0] == n[1]) ? 3 : 4;
+    const long long bpm = n[0] / n[1] + 2; /* 3, 4 or 6 blocks per MCU */
     return (((long long)EC_MCUS * bpm * 1658 + 31) / 32 + 4) & ~3ll;
 }
 
@@ -864,7 +864,15 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
     }
     const bool aligned16 = (w % 16 == 0) && (((uintptr_t)d_r | (uintptr_t)d_g | (uintptr_t)d_b) % 16 == 0) &&
                            (plane_stride % 16 == 0);
-    if (aligned16 && ctx->k1_pc && !ctx->k1_plain) {
+    if (ratio == 2) {
+        /* 4:2:0: one CTA per tile of 16 MCUs (k1_transform420) */
+        dim3 grid((unsigned)p.tiles_per_row, (unsigned)(h / 16), (unsigned)nframes);
+        LaunchScope ls(ctx, KI_K1);
+        if (ctx->std_mode)
+            k1_transform420<true><<<grid, K1_THREADS, 0, ctx->stream>>>(p);
+        else
+            k1_transform420<false><<<grid, K1_THREADS, 0, ctx->stream>>>(p);
+    } else if (aligned16 && ctx->k1_pc && !ctx->k1_plain) {
         /* eight specialised warps per CTA handing tiles over through mbarriers (k1_pc.cuh) */
         const size_t smem = sizeof(K1CSmem) + 1024;
         if (!ctx->k1c_attr_set) {
@@ -993,14 +1001,17 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     if (!ctx->ke_attr_set) {
         CK(cudaFuncSetAttribute(k_encode_chunks<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<0>::BYTES));
         CK(cudaFuncSetAttribute(k_encode_chunks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<1>::BYTES));
+        CK(cudaFuncSetAttribute(k_encode_chunks<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<2>::BYTES));
         ctx->ke_attr_set = true;
     }
     {
         LaunchScope ls(ctx, KI_KE);
         if (ratio == 0)
             k_encode_chunks<0><<<nc, KeCfg<0>::NT, KeSmem<0>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
-        else
+        else if (ratio == 1)
             k_encode_chunks<1><<<nc, KeCfg<1>::NT, KeSmem<1>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
+        else
+            k_encode_chunks<2><<<nc, KeCfg<2>::NT, KeSmem<2>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
     }
     CK(cudaGetLastError());
     ctx->have_bits = true;
@@ -1147,7 +1158,7 @@ static int encode_core(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g,
             if ((rc = optimise_tables(ctx, w, h, quality, ratio))) return rc;
             /* the histogram kernels ran after K1 cleared the two-level sums: still clear */
         }
-        if (ctx->legacy_entropy) {
+        if (ctx->legacy_entropy || ratio == 2) { /* the single-launch K35 knows 4:4:4 and 4:2:2 only */
             if ((rc = launch_bits(ctx, ctx->d_zz, ratio, n))) return rc;
             return launch_pack(ctx, ctx->d_zz, ratio, n, d_out, cap, len_out);
         }
@@ -1239,10 +1250,10 @@ extern "C" int jpgb200_encode_planar_any(jpgb200_ctx *ctx, const uint8_t *r, con
                                          int quality, int ratio, uint8_t *out, size_t cap, size_t *len)
 {
     if (!ctx || !r || !g || !b || !out) return JPGB200_ERR_BAD_ARG;
-    if (w < 1 || h < 1 || w > 65535 || h > 65535 || (ratio != 0 && ratio != 1)) return JPGB200_ERR_BAD_DIMS;
+    if (w < 1 || h < 1 || w > 65535 || h > 65535 || ratio < 0 || ratio > 2) return JPGB200_ERR_BAD_DIMS;
     if (quality < 24 || quality > 97) return JPGB200_ERR_BAD_QUALITY;
-    const int mw = ratio ? 16 : 8;
-    const int pw = (w + mw - 1) / mw * mw, ph = (h + 7) / 8 * 8;
+    const int mw = ratio ? 16 : 8, mh = ratio == 2 ? 16 : 8;
+    const int pw = (w + mw - 1) / mw * mw, ph = (h + mh - 1) / mh * mh;
     CK(cudaSetDevice(ctx->device));
     const size_t npx = (size_t)w * h, pnpx = (size_t)pw * ph;
     int rc;
@@ -1361,6 +1372,7 @@ extern "C" int jpgb200_band_transform(jpgb200_ctx *ctx, const uint8_t *d_r, cons
                                       int w, int band_h, int has_halo, int quality, int ratio, int last_dc[3])
 {
     if (!ctx || !d_r || !d_g || !d_b || !last_dc) return JPGB200_ERR_BAD_ARG;
+    if (ratio == 2) return JPGB200_ERR_BAD_ARG; /* the MCU-row partition is built for 8-row MCUs */
     long long n[3];
     int rc = validate(w, band_h, quality, ratio, n);
     if (rc) return rc;
@@ -1550,7 +1562,7 @@ extern "C" int jpgb200_block_bit_offsets(jpgb200_ctx *ctx, unsigned long long *o
 {
     if (!ctx || !offsets || !ctx->have_bits) return JPGB200_ERR_BAD_ARG;
     CK(cudaSetDevice(ctx->device));
-    const int bpm = ctx->ratio ? 4 : 3;
+    const int bpm = ctx->ratio == 2 ? 6 : (ctx->ratio ? 4 : 3);
     const long long nb = ctx->n[1] * bpm, nc = n_chunks(ctx->n);
     std::vector<uint32_t> loc((size_t)nb), cbits((size_t)nc);
     CK(cudaMemcpyAsync(loc.data(), ctx->d_local_off, (size_t)nb * 4, cudaMemcpyDeviceToHost, ctx->stream));
@@ -1765,7 +1777,7 @@ extern "C" int jpgb200_encode_coefficients(jpgb200_ctx *ctx, const int16_t *zz, 
     memcpy(ctx->n, n, sizeof n);
     CK(cudaMemcpyAsync(ctx->d_zz, zz, (size_t)(n[0] + n[1] + n[2]) * 128, cudaMemcpyHostToDevice, ctx->stream));
     if (ctx->opt_huff && (rc = optimise_tables(ctx, w, h, quality, ratio))) return rc;
-    if (ctx->legacy_entropy) {
+    if (ctx->legacy_entropy || ratio == 2) {
         if ((rc = launch_bits(ctx, ctx->d_zz, ratio, n, NULL, true))) return rc;
         if ((rc = launch_pack(ctx, ctx->d_zz, ratio, n, ctx->d_out[0], cap, ctx->d_len))) return rc;
     } else {

@@ -140,6 +140,21 @@ __device__ __forceinline__ f32x2 colour_cr2_p(f32x2 rs, f32x2 gs, f32x2 bs)
     return p_fma(p_bc(-0.040656f), bs, p_fma(p_bc(-0.209344f), gs, p_mul(p_bc(0.25f), rs)));
 }
 
+/* 4:2:0: mean of a 2x2 group == formula applied to the (exact, integer) sums of four with
+ * quarter weights */
+__device__ __forceinline__ f32x2 colour_cb4_p(f32x2 rs, f32x2 gs, f32x2 bs)
+{
+    return p_fma(p_bc(-0.125f), bs, p_fma(p_bc(0.082816f), gs, p_mul(p_bc(-0.042184f), rs)));
+}
+__device__ __forceinline__ f32x2 colour_cb4_std_p(f32x2 rs, f32x2 gs, f32x2 bs)
+{
+    return p_fma(p_bc(0.125f), bs, p_fma(p_bc(-0.082816f), gs, p_mul(p_bc(-0.042184f), rs)));
+}
+__device__ __forceinline__ f32x2 colour_cr4_p(f32x2 rs, f32x2 gs, f32x2 bs)
+{
+    return p_fma(p_bc(-0.020328f), bs, p_fma(p_bc(-0.104672f), gs, p_mul(p_bc(0.125f), rs)));
+}
+
 /* fdct8 after its first butterfly stage (t0..t7 given) */
 __device__ __forceinline__ void fdct8_tail_p(f32x2 t0, f32x2 t1, f32x2 t2, f32x2 t3, f32x2 t4, f32x2 t5, f32x2 t6, f32x2 t7,
                                              f32x2 &d0, f32x2 &d1, f32x2 &d2, f32x2 &d3, f32x2 &d4, f32x2 &d5, f32x2 &d6,

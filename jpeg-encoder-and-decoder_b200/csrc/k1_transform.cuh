@@ -282,6 +282,130 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform(const K1Params p)
 }
 
 /* ---------------------------------------------------------------------------------------------
+ * k1_transform420: 4:2:0 (HORIZONTAL_VERTICAL_SUBSAMPLING, a printf stub in the reference,
+ * src/downsample.c:29-32).  One CTA per tile of 16 MCUs (32 x 2 luma
+ * blocks, 16 Cb, 16 Cr), direct loads.  Luma coefficients are stored in MCU order (Y00 Y01 Y10
+ * Y11 per MCU: the order of the scan), chroma one block per MCU.  Chroma = mean of each 2x2 group,
+ * computed from exact integer sums with quarter-weight colour coefficients.
+ * --------------------------------------------------------------------------------------------- */
+template <bool STD>
+__global__ void __launch_bounds__(K1_THREADS, 4) k1_transform420(const K1Params p)
+{
+    __shared__ K1F sF[3];      /* luma block row 0, luma block row 1, chroma (slots 0..15 Cb, 16..31 Cr) */
+    __shared__ K1Out sOut[3];
+    __shared__ float sMul[2][64];
+
+    const int tid = threadIdx.x, k = tid >> 5, lane = tid & 31;
+    const int my = blockIdx.y;                   /* MCU row */
+    const int tb0 = blockIdx.x * K1_TILE_BLOCKS; /* first luma block column of the tile */
+    const int frame = blockIdx.z;
+    const uint8_t *pl[3] = {p.r + (long long)frame * p.plane_stride, p.g + (long long)frame * p.plane_stride,
+                            p.b + (long long)frame * p.plane_stride};
+    sMul[tid >> 6][tid & 63] = p.mul[tid >> 6][tid & 63];
+    if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0)
+        for (int i = tid; i < p.clear_n; i += K1_THREADS) p.clear[i] = 0u;
+
+    /* 8 bytes of image row y of block column bx (one row higher for the last column) */
+    auto ld8 = [&](int c, long long y, int bx) -> uint2 {
+        if (bx >= p.BW) return make_uint2(0u, 0u);
+        const long long row = y - ((!STD && bx == p.BW - 1) ? 1 : 0);
+        if (row >= 0 || p.has_halo) return __ldg(reinterpret_cast<const uint2 *>(pl[c] + row * p.W + (long long)bx * 8));
+        return ld_oob(p.oob + 8 * c);
+    };
+    /* luma: rows k and 7-k of block (r, lane) */
+#pragma unroll
+    for (int r = 0; r < 2; r++) {
+        uint2 pa[3], pb[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            pa[c] = ld8(c, (long long)my * 16 + 8 * r + k, tb0 + lane);
+            pb[c] = ld8(c, (long long)my * 16 + 8 * r + 7 - k, tb0 + lane);
+        }
+        k1_convert_full<1, STD>(sF + r, k, lane, pa, pb); /* the luma half of the 4:2:2 converter */
+    }
+    /* chroma rows k and 7-k of MCU column jc = pixel rows (2k, 2k+1) and (14-2k, 15-2k), 16 wide */
+    {
+        const int jc = lane & 15;
+        f32x2 sum[3][8];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            f32x2 o0[8], o1[8];
+#pragma unroll
+            for (int d = 0; d < 2; d++) {
+                const long long ya = (long long)my * 16 + 2 * k + d, yb = (long long)my * 16 + 14 - 2 * k + d;
+                const uint2 a0 = ld8(c, ya, tb0 + 2 * jc), a1 = ld8(c, ya, tb0 + 2 * jc + 1);
+                const uint2 b0 = ld8(c, yb, tb0 + 2 * jc), b1 = ld8(c, yb, tb0 + 2 * jc + 1);
+                k1_pairsums16(make_uint4(a0.x, a0.y, a1.x, a1.y), make_uint4(b0.x, b0.y, b1.x, b1.y), d ? o1 : o0);
+            }
+#pragma unroll
+            for (int x = 0; x < 8; x++) sum[c][x] = p_add(o0[x], o1[x]);
+        }
+        f32x2 o[8];
+        if (lane < 16) {
+#pragma unroll
+            for (int x = 0; x < 8; x++)
+                o[x] = STD ? colour_cb4_std_p(sum[0][x], sum[1][x], sum[2][x]) : colour_cb4_p(sum[0][x], sum[1][x], sum[2][x]);
+        } else {
+#pragma unroll
+            for (int x = 0; x < 8; x++) o[x] = colour_cr4_p(sum[0][x], sum[1][x], sum[2][x]);
+        }
+        k1_store_pairs(sF[2], k, lane, o);
+    }
+    __syncthreads();
+    /* phase 2: warps 0,1 luma rows (luma table), warp 2 chroma */
+    if (k < 3) {
+        f32x2 P[4][8], Q[8][4];
+#pragma unroll
+        for (int kk = 0; kk < 4; kk++)
+#pragma unroll
+            for (int x = 0; x < 8; x++) P[kk][x] = sF[k][kk][x][lane];
+        fdct8x8_p(P, Q);
+        const float4 *m4 = reinterpret_cast<const float4 *>(sMul[k < 2 ? 0 : 1]);
+        float f[64];
+#pragma unroll
+        for (int v = 0; v < 8; v++)
+#pragma unroll
+            for (int hh = 0; hh < 2; hh++) {
+                const float4 m = m4[v * 2 + hh];
+                const f32x2 q0 = p_fma(Q[v][2 * hh], make_float2(m.x, m.y), p_bc(JPGB_ROUND_MAGIC));
+                const f32x2 q1 = p_fma(Q[v][2 * hh + 1], make_float2(m.z, m.w), p_bc(JPGB_ROUND_MAGIC));
+                f[v * 8 + 4 * hh + 0] = q0.x;
+                f[v * 8 + 4 * hh + 1] = q0.y;
+                f[v * 8 + 4 * hh + 2] = q1.x;
+                f[v * 8 + 4 * hh + 3] = q1.y;
+            }
+        uint32_t o[32];
+        zigzag_pack(f, o);
+#pragma unroll
+        for (int j = 0; j < 8; j++) sOut[k][lane][j ^ (lane & 7)] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+    }
+    __syncthreads();
+    /* phase 3: luma block (r, j) -> MCU (my, (tb0+j)/2), sub-block 2r + (j&1); chroma slot s -> MCU tb0/2 + (s&15) */
+    {
+        int16_t *zy = p.zz_y + (long long)frame * p.zz_stride;
+        int16_t *zcb = p.zz_cb + (long long)frame * p.zz_stride;
+        int16_t *zcr = p.zz_cr + (long long)frame * p.zz_stride;
+        const int mw = p.BW >> 1;
+        for (int i = tid; i < 3 * 256; i += K1_THREADS) {
+            const int crow = i >> 8, rem = i & 255, j = rem >> 3, ch = rem & 7;
+            uint4 *dst;
+            bool ok;
+            if (crow < 2) {
+                const int bx = tb0 + j;
+                ok = bx < p.BW;
+                const long long m = (long long)my * mw + (bx >> 1);
+                dst = reinterpret_cast<uint4 *>(zy + (m * 4 + 2 * crow + (bx & 1)) * 64) + ch;
+            } else {
+                const int mx = (tb0 >> 1) + (j & 15);
+                ok = mx < mw;
+                dst = reinterpret_cast<uint4 *>((j < 16 ? zcb : zcr) + ((long long)my * mw + mx) * 64) + ch;
+            }
+            if (ok) *dst = sOut[crow][j][ch ^ (j & 7)];
+        }
+    }
+}
+
+/* ---------------------------------------------------------------------------------------------
  * k1_transform_tma: persistent CTAs, raw pixel rows prefetched by TMA bulk copies
  * --------------------------------------------------------------------------------------------- */
 #define K1_STAGES 2

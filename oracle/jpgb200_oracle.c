@@ -107,6 +107,11 @@ int orc_block_counts(int w, int h, int sample_ratio, long n[3])
         if (w % 16) return -1;
         n[0] = (long)(w / 8) * (h / 8);
         n[1] = n[2] = n[0] / 2; /* ours: SURVEY.md B.9 */
+    } else if (sample_ratio == 2) {
+        /* 4:2:0 (ours; subsample_420 is a printf stub, src/downsample.c:29): 16x16 MCUs */
+        if ((w % 16) || (h % 16)) return -1;
+        n[0] = (long)(w / 8) * (h / 8);
+        n[1] = n[2] = n[0] / 4;
     } else {
         return -1;
     }
@@ -236,6 +241,28 @@ static void *coef_worker(void *arg)
             finish_block(Y, J->lum, zy + bi * 64, dy ? dy + bi * 64 : NULL);
             finish_block(Cb, J->chr, zcb + bi * 64, dcb ? dcb + bi * 64 : NULL);
             finish_block(Cr, J->chr, zcr + bi * 64, dcr ? dcr + bi * 64 : NULL);
+        }
+    } else if (J->sample_ratio == 2) {
+        /* 4:2:0 (ours): units are MCUs of 2x2 luma blocks.  Luma blocks are stored in MCU order
+         * (Y00 Y01 Y10 Y11 per MCU: the scan order), chroma is the mean of each 2x2 group of the
+         * full-resolution level-shifted samples the reference's blocks would hold. */
+        int mw = bw / 2;
+        for (long mi = J->lo; mi < J->hi; mi++) {
+            int my = (int)(mi / mw), mx = (int)(mi % mw);
+            double Yb[4][64], Cbf[4][64], Crf[4][64], Cb[64], Cr[64];
+            for (int q = 0; q < 4; q++)
+                convert_block(J->r, J->g, J->b, w, bw, 2 * mx + (q & 1), 2 * my + (q >> 1), J->oob, Yb[q], Cbf[q], Crf[q]);
+            for (int y = 0; y < 8; y++)
+                for (int x = 0; x < 8; x++) {
+                    const int q = (y >> 2) * 2 + (x >> 2), sy = (2 * y) & 7, sx = (2 * x) & 7;
+                    Cb[y * 8 + x] = 0.25 * (Cbf[q][sy * 8 + sx] + Cbf[q][sy * 8 + sx + 1] + Cbf[q][(sy + 1) * 8 + sx] +
+                                            Cbf[q][(sy + 1) * 8 + sx + 1]);
+                    Cr[y * 8 + x] = 0.25 * (Crf[q][sy * 8 + sx] + Crf[q][sy * 8 + sx + 1] + Crf[q][(sy + 1) * 8 + sx] +
+                                            Crf[q][(sy + 1) * 8 + sx + 1]);
+                }
+            for (int q = 0; q < 4; q++) finish_block(Yb[q], J->lum, zy + (mi * 4 + q) * 64, dy ? dy + (mi * 4 + q) * 64 : NULL);
+            finish_block(Cb, J->chr, zcb + mi * 64, dcb ? dcb + mi * 64 : NULL);
+            finish_block(Cr, J->chr, zcr + mi * 64, dcr ? dcr + mi * 64 : NULL);
         }
     } else {
         /* 4:2:2 (ours): form full-resolution level-shifted chroma
@@ -614,7 +641,7 @@ static uint64_t walk_scan_h(BitW *w, const HuffSet *hs, const int16_t *zz, int w
     long s = 0;
     long nmcu = n[1];
     for (long m = 0; m < nmcu; m++) {
-        int ny = (sample_ratio == 0) ? 1 : 2;
+        int ny = (sample_ratio == 0) ? 1 : (sample_ratio == 1 ? 2 : 4); /* 4:2:0: luma is stored in MCU order */
         for (int k = 0; k < ny; k++) {
             const int16_t *blk = zy + (m * ny + k) * 64;
             uint32_t bb = encode_block(w, &h, blk, pred[0], 0);
@@ -741,7 +768,7 @@ size_t orc_jfif_header_specs(int w, int h, int quality, int sample_ratio, const 
     p = put16(o, p, (unsigned)w);
     o[p++] = 3;
     o[p++] = 1;
-    o[p++] = (uint8_t)(sample_ratio == 1 ? 0x21 : 0x11);
+    o[p++] = (uint8_t)(sample_ratio == 1 ? 0x21 : (sample_ratio == 2 ? 0x22 : 0x11));
     o[p++] = 0;
     o[p++] = 2;
     o[p++] = 0x11;

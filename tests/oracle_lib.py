@@ -119,8 +119,8 @@ def set_standard(on):
 
 def pad_planes(r, g, b, w, h, ratio):
     """edge replication to whole MCUs, as jpgb200_encode_planar_any does on the device"""
-    mw = 16 if ratio else 8
-    pw, ph = (w + mw - 1) // mw * mw, (h + 7) // 8 * 8
+    mw, mh = (16 if ratio else 8), (16 if ratio == 2 else 8)
+    pw, ph = (w + mw - 1) // mw * mw, (h + mh - 1) // mh * mh
     out = [np.pad(np.asarray(p, np.uint8).reshape(h, w), ((0, ph - h), (0, pw - w)), mode="edge").reshape(-1) for p in (r, g, b)]
     return out[0], out[1], out[2], pw, ph
 

@@ -221,3 +221,33 @@ def test_optimal_huffman_tables_oracle(w, h, q, ratio, kind):
     ia = np.asarray(Image.open(io.BytesIO(a.tobytes())).convert("RGB"))
     io_ = np.asarray(Image.open(io.BytesIO(o.tobytes())).convert("RGB"))
     assert (ia == io_).all()
+
+
+@pytest.mark.parametrize("w,h,q", [(64, 48, 75), (160, 96, 90)])
+def test_oracle_420_decodes_to_the_source(w, h, q):
+    """4:2:0 in the oracle (the reference's subsample_420 is a printf stub, src/downsample.c:29-32):
+    16x16 MCUs, luma in MCU order, chroma = mean of 2x2 groups.  In standards-conforming mode PIL
+    and OpenCV decode the stream to (nearly) the source pixels and agree with each other."""
+    import io
+
+    import cv2
+    from PIL import Image
+
+    rng = np.random.default_rng(3)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = [(xx * 255 // (w - 1)), (yy * 255 // (h - 1)), ((xx + yy) * 255 // (w + h - 2))]
+    r, g, b = [np.clip(p + rng.integers(-6, 7, size=(h, w)), 0, 255).astype(np.uint8).reshape(-1) for p in base]
+    n = O.block_counts(w, h, 2)
+    assert n[0] == (w // 8) * (h // 8) and n[1] == n[2] == n[0] // 4
+    O.set_standard(True)
+    try:
+        jf = O.encode_jfif(r, g, b, w, h, q, 2)
+    finally:
+        O.set_standard(False)
+    im = Image.open(io.BytesIO(jf.tobytes()))
+    assert im.size == (w, h)
+    dec = np.asarray(im.convert("RGB")).astype(np.float64)
+    src = np.stack([r, g, b], -1).reshape(h, w, 3).astype(np.float64)
+    assert 10 * np.log10(255.0 ** 2 / ((dec - src) ** 2).mean()) > 32.0
+    bgr = cv2.imdecode(np.frombuffer(jf.tobytes(), np.uint8), cv2.IMREAD_COLOR)
+    assert np.abs(bgr[..., ::-1].astype(np.float64) - dec).max() <= 2

@@ -481,3 +481,62 @@ def test_standard_mode_any_size(enc, w, h, q, ratio, seed):
     mse = float(((dec - src) ** 2).mean())
     psnr = 99.0 if mse == 0 else 10 * np.log10(255.0 ** 2 / mse)
     assert psnr > 30.0, psnr
+
+
+@pytest.mark.parametrize("w,h,q,kind,seed", [(64, 48, 75, 0, 71), (272, 32, 90, 0, 72), (528, 80, 50, 1, 73), (1920, 1088, 75, 0, 74)])
+def test_420_vs_oracle(enc, w, h, q, kind, seed):
+    """4:2:0 (sample_ratio 2, HORIZONTAL_VERTICAL_SUBSAMPLING; a printf stub in the reference,
+    src/downsample.c:29-32): 16x16 MCUs, luma coefficients in MCU order,
+    chroma = mean of each 2x2 group.  Coefficients within tolerance of the oracle (including the
+    shifted last block column and its out-of-bounds bytes), bytes identical given equal
+    coefficients, and two independent decoders accept the stream."""
+    import cv2
+    from PIL import Image
+
+    r, g, b = O.synth_planes(w, h, seed, 0, kind)
+    oob = np.arange(24, dtype=np.uint8) * 5 + 9
+    enc.set_oob_bytes(oob)
+    try:
+        zz = enc.coefficients(r, g, b, w, h, q, 2)
+        jf = enc.encode_planar(r, g, b, w, h, q, 2)
+    finally:
+        enc.set_oob_bytes(np.zeros(24, np.uint8))
+    n = O.block_counts(w, h, 2)
+    assert zz.shape[0] == sum(n) and n[1] * 4 == n[0]
+    assert_coeff_close(zz, O.coefficients(r, g, b, w, h, q, 2, oob=oob), "4:2:0")
+    scan, _ = O.encode_scan(zz, w, h, 2)
+    want = np.concatenate([O.jfif_header(w, h, q, 2), scan, np.array([0xFF, 0xD9], np.uint8)])
+    assert jf.shape == want.shape and (jf == want).all()
+    im = Image.open(io.BytesIO(jf.tobytes()))
+    im.load()
+    assert im.size == (w, h)
+    bgr = cv2.imdecode(np.frombuffer(jf.tobytes(), np.uint8), cv2.IMREAD_COLOR)
+    assert bgr is not None and bgr.shape == (h, w, 3)
+    off = enc.block_bit_offsets()
+    bits = O.block_bits(zz, w, h, 2)
+    assert (np.diff(off.astype(np.int64)) == bits.astype(np.int64)).all()
+
+
+@pytest.mark.parametrize("w,h,q,seed", [(250, 130, 90, 81), (33, 17, 75, 82)])
+def test_420_standard_mode_any_size_and_optimal_tables(enc, w, h, q, seed):
+    """4:2:0 through the robust front door: any size, standards-conforming arithmetic, per-image
+    optimal Huffman tables -- PIL decodes the stream back to the source pixels."""
+    from PIL import Image
+
+    rng = np.random.default_rng(seed)
+    yy, xx = np.mgrid[0:h, 0:w]
+    base = [(xx * 255 // max(w - 1, 1)), (yy * 255 // max(h - 1, 1)), ((xx + yy) * 255 // max(w + h - 2, 1))]
+    r, g, b = [np.clip(p + rng.integers(-4, 5, size=(h, w)), 0, 255).astype(np.uint8).reshape(-1) for p in base]
+    enc.set_standard_mode(True)
+    enc.set_optimized_huffman(True)
+    try:
+        jf = enc.encode_planar_any(r, g, b, w, h, q, 2)
+    finally:
+        enc.set_standard_mode(False)
+        enc.set_optimized_huffman(False)
+    im = Image.open(io.BytesIO(jf.tobytes()))
+    assert im.size == (w, h)
+    dec = np.asarray(im.convert("RGB")).astype(np.float64)
+    src = np.stack([r, g, b], axis=-1).reshape(h, w, 3).astype(np.float64)
+    mse = float(((dec - src) ** 2).mean())
+    assert 10 * np.log10(255.0 ** 2 / max(mse, 1e-9)) > 30.0
