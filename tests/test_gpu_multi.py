@@ -147,7 +147,7 @@ def test_driver_robust_front_door(tmp_path):
     bmp = str(tmp_path / "in.bmp")
     Image.fromarray(rgb, "RGB").save(bmp)  # bottom-up, rows padded to 452 bytes
     exe = os.path.join(PKG, "jpg")
-    for ratio in (0, 1):
+    for ratio in (0, 1, 2):
         outp = str(tmp_path / ("out%d.jpg" % ratio))
         r = subprocess.run([exe, bmp, outp, "90", str(ratio), "--robust"], capture_output=True, text=True, timeout=120)
         assert r.returncode == 0, r.stderr + r.stdout
