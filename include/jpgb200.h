@@ -118,7 +118,11 @@ int jpgb200_encode_device(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d
                           int height, int quality, int sample_ratio, uint8_t *d_out, size_t cap,
                           unsigned long long *d_len);
 /* n frames back to back: frame f reads planes at d_planes + f*3*w*h (r,g,b contiguous),
- * writes its stream at d_out + f*out_stride and its length to d_lens[f]. */
+ * writes its stream at d_out + f*out_stride and its length to d_lens[f].  Inside the call the
+ * tail kernels (0xFF count, stuffed scatter) of frame f run on a second stream beside the chunk
+ * encode of frame f+1 (two sets of entropy workspaces alternate); the context's stream has
+ * waited for all of it when the call's work is done, so the caller sees plain stream order.
+ * JPGB200_OVERLAP=0 in the environment turns the overlap off. */
 int jpgb200_encode_batch_device(jpgb200_ctx *ctx, const uint8_t *d_planes, int n_frames, int width, int height,
                                 int quality, int sample_ratio, uint8_t *d_out, size_t out_stride,
                                 unsigned long long *d_lens);

@@ -111,6 +111,21 @@ struct jpgb200_ctx {
     long long band_n[3];
     bool std_mode;       /* standards-conforming K1: textbook Cb, no last-column shift */
     int sof_w, sof_h;    /* true image size for SOF0 when the planes were padded (0: same as the planes) */
+    /* batch overlap: the tail (KF, KS) of frame f runs on a second stream beside KE of frame f+1;
+     * the entropy workspaces exist twice and alternate with the frame parity */
+    struct EntWs {
+        uint32_t *tmp, *cta_bits, *cta_ff, *cta_tail, *super;
+        unsigned long long *cta_base;
+        size_t tmp_cap, cta_cap, n_super_bits, n_super_ff;
+    } alt;
+    cudaStream_t tail_stream;
+    cudaEvent_t ev_ke, ev_ks[2];
+    bool overlap_on;     /* jpgb200_encode_batch_device overlaps tails (JPGB200_OVERLAP=0 turns it off) */
+    bool overlap_now;    /* inside such a batch */
+    bool have_pending;   /* a frame's tail waits to be launched behind the next frame's K1 */
+    TailParams pending_q;
+    int pending_parity;
+    int ws_parity;
     bool opt_huff;       /* per-image optimal Huffman tables (T.81 K.2) instead of the tables.h ones */
     HuffSpecs specs;     /* tables in use: DHT segments and code tables derive from them */
     HuffDev std_huff;    /* the tables.h tables, kept for switching back */
@@ -417,6 +432,8 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         const char *e = getenv("JPGB200_ENTROPY"); /* "fused" | "staged": experiment switch for bench runs */
         if (e && !strcmp(e, "fused")) ctx->legacy_entropy = false;
         const char *k = getenv("JPGB200_K1"); /* "plain" | "tma" */
+        const char *ov = getenv("JPGB200_OVERLAP");
+        ctx->overlap_on = !(ov && !strcmp(ov, "0"));
         if (k && !strcmp(k, "plain")) ctx->k1_plain = true, ctx->k1_pc = false;
         if (k && !strcmp(k, "cta")) ctx->k1_cta = true, ctx->k1_pc = false;
         if (k && !strcmp(k, "pipe")) ctx->k1_pipe = true, ctx->k1_pc = false;
@@ -446,6 +463,10 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
+        CK(cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking));
+        CK(cudaEventCreateWithFlags(&ctx->ev_ke, cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_ks[0], cudaEventDisableTiming));
+        CK(cudaEventCreateWithFlags(&ctx->ev_ks[1], cudaEventDisableTiming));
         ctx->stream = ctx->own_stream;
         CK(cudaMalloc(&ctx->d_huff, sizeof(HuffDev)));
         CK(cudaMemcpy(ctx->d_huff, &hh, sizeof hh, cudaMemcpyHostToDevice));
@@ -492,6 +513,15 @@ extern "C" void jpgb200_destroy(jpgb200_ctx *ctx)
     cudaStreamDestroy(ctx->own_stream);
     cudaStreamDestroy(ctx->copy_in);
     cudaStreamDestroy(ctx->copy_out);
+    cudaStreamDestroy(ctx->tail_stream);
+    cudaEventDestroy(ctx->ev_ke);
+    cudaEventDestroy(ctx->ev_ks[0]);
+    cudaEventDestroy(ctx->ev_ks[1]);
+    {
+        void *alts[] = {ctx->alt.tmp, ctx->alt.cta_bits, ctx->alt.cta_ff, ctx->alt.cta_tail, ctx->alt.super, ctx->alt.cta_base};
+        for (void *q : alts)
+            if (q) cudaFree(q);
+    }
     delete ctx;
 }
 
@@ -1018,6 +1048,40 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     return JPGB200_OK;
 }
 
+static int run_tail(jpgb200_ctx *ctx, const TailParams &q)
+{
+    const unsigned grid = (unsigned)((q.n_chunks + TAIL_WARPS - 1) / TAIL_WARPS);
+    {
+        LaunchScope ls(ctx, KI_KF);
+        k_count_ff<<<grid, TAIL_THREADS, 0, ctx->stream>>>(q);
+    }
+    CK(cudaGetLastError());
+    {
+        LaunchScope ls(ctx, KI_KS);
+        k_scatter<<<grid, TAIL_THREADS, 0, ctx->stream>>>(q);
+    }
+    CK(cudaGetLastError());
+    return JPGB200_OK;
+}
+
+/* batch overlap: the previous frame's tail goes to the tail stream now, i.e. after everything the
+ * main stream holds so far (the previous frame's KE and, when called after K1, this frame's K1 --
+ * which fills the register files and is better left alone) */
+static int run_pending_tail(jpgb200_ctx *ctx)
+{
+    if (!ctx->have_pending) return JPGB200_OK;
+    ctx->have_pending = false;
+    cudaStream_t main_stream = ctx->stream;
+    CK(cudaEventRecord(ctx->ev_ke, main_stream));
+    CK(cudaStreamWaitEvent(ctx->tail_stream, ctx->ev_ke, 0));
+    ctx->stream = ctx->tail_stream;
+    const int rc = run_tail(ctx, ctx->pending_q);
+    ctx->stream = main_stream;
+    if (rc) return rc;
+    CK(cudaEventRecord(ctx->ev_ks[ctx->pending_parity], ctx->tail_stream));
+    return JPGB200_OK;
+}
+
 /* KF + KS: chunk streams -> stuffed bytes at d_out (+ header, EOI, length word) */
 static int launch_tail(jpgb200_ctx *ctx, const long long n[3], unsigned bit_phase, unsigned carry, int is_last_band,
                        int header_len, int write_eoi, uint8_t *d_out, size_t cap, unsigned long long *len_out)
@@ -1042,18 +1106,32 @@ static int launch_tail(jpgb200_ctx *ctx, const long long n[3], unsigned bit_phas
     q.len_out = len_out;
     q.write_eoi = write_eoi;
     q.st = ctx->d_state;
-    const unsigned grid = (unsigned)((q.n_chunks + TAIL_WARPS - 1) / TAIL_WARPS);
-    {
-        LaunchScope ls(ctx, KI_KF);
-        k_count_ff<<<grid, TAIL_THREADS, 0, ctx->stream>>>(q);
+    if (ctx->overlap_now) { /* deferred: it will run beside the next frame's KE (run_pending_tail) */
+        ctx->pending_q = q;
+        ctx->pending_parity = ctx->ws_parity;
+        ctx->have_pending = true;
+        return JPGB200_OK;
     }
-    CK(cudaGetLastError());
-    {
-        LaunchScope ls(ctx, KI_KS);
-        k_scatter<<<grid, TAIL_THREADS, 0, ctx->stream>>>(q);
-    }
-    CK(cudaGetLastError());
-    return JPGB200_OK;
+    return run_tail(ctx, q);
+}
+
+/* exchange the entropy workspaces in use with the alternate set */
+static void swap_entropy_ws(jpgb200_ctx *ctx)
+{
+    jpgb200_ctx::EntWs cur = {ctx->d_tmp,      ctx->d_cta_bits, ctx->d_cta_ff,     ctx->d_cta_tail,   ctx->d_super,
+                              ctx->d_cta_base, ctx->tmp_cap,    ctx->cta_cap,      ctx->n_super_bits, ctx->n_super_ff};
+    ctx->d_tmp = ctx->alt.tmp;
+    ctx->d_cta_bits = ctx->alt.cta_bits;
+    ctx->d_cta_ff = ctx->alt.cta_ff;
+    ctx->d_cta_tail = ctx->alt.cta_tail;
+    ctx->d_super = ctx->alt.super;
+    ctx->d_cta_base = ctx->alt.cta_base;
+    ctx->tmp_cap = ctx->alt.tmp_cap;
+    ctx->cta_cap = ctx->alt.cta_cap;
+    ctx->n_super_bits = ctx->alt.n_super_bits;
+    ctx->n_super_ff = ctx->alt.n_super_ff;
+    ctx->alt = cur;
+    ctx->ws_parity ^= 1;
 }
 
 static int launch_pack(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3], uint8_t *d_out, size_t cap,
@@ -1061,7 +1139,7 @@ static int launch_pack(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
 {
     (void)zz;
     (void)ratio;
-    return launch_tail(ctx, n, 0u, 0u, 1, ctx->hdr_len, 1, d_out, cap, len_out);
+    return launch_tail(ctx, n, 0u, 0u, 1, ctx->hdr_len, 1, d_out, cap, len_out); /* deferred inside a batch overlap */
 }
 
 /* K35: the whole entropy stage in one launch (entropy_fused.cuh) */
@@ -1152,6 +1230,7 @@ static int encode_core(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g,
     ctx->ratio = ratio;
     memcpy(ctx->n, n, sizeof n);
     if ((rc = launch_k1(ctx, d_r, d_g, d_b, w, h, ratio, n, 1, 0, ctx->d_zz, 0, 0))) return rc;
+    if (ctx->overlap_now && (rc = run_pending_tail(ctx))) return rc; /* the previous frame's tail, beside this frame's KE */
     if (d_out) {
         ctx->have_bits = false;
         if (ctx->opt_huff) {
@@ -1186,13 +1265,33 @@ extern "C" int jpgb200_encode_batch_device(jpgb200_ctx *ctx, const uint8_t *d_pl
     if (!ctx || !d_planes || !d_out || n_frames < 0) return JPGB200_ERR_BAD_ARG;
     CK(cudaSetDevice(ctx->device));
     const size_t npx = (size_t)w * h;
-    for (int f = 0; f < n_frames; f++) {
+    /* Overlap (default): frame f's tail (KF, KS: small, latency-bound) runs on a second stream
+     * beside frame f+1's KE (it is launched behind frame f+1's K1, which fills the register files
+     * and is better left alone: launched right behind KE it slowed K1 from 77 to 98 us).  The entropy
+     * workspaces alternate with the frame parity; the caller's stream order is kept (it waits for
+     * the last tails before this call's work counts as done). */
+    const bool overlap = ctx->overlap_on && ctx->legacy_entropy && !ctx->opt_huff && n_frames >= 2;
+    int rc = JPGB200_OK;
+    ctx->overlap_now = overlap;
+    for (int f = 0; f < n_frames && rc == JPGB200_OK; f++) {
         const uint8_t *pl = d_planes + (size_t)f * 3 * npx;
-        int rc = encode_core(ctx, pl, pl + npx, pl + 2 * npx, w, h, quality, ratio, d_out + (size_t)f * out_stride,
-                             out_stride, d_lens ? d_lens + f : ctx->d_len);
-        if (rc) return rc;
+        if (overlap) {
+            swap_entropy_ws(ctx);
+            /* this parity's workspaces were last read by the tail of frame f-2 */
+            if (f >= 2 && cudaStreamWaitEvent(ctx->stream, ctx->ev_ks[ctx->ws_parity], 0) != cudaSuccess) rc = JPGB200_ERR_CUDA;
+        }
+        if (rc == JPGB200_OK)
+            rc = encode_core(ctx, pl, pl + npx, pl + 2 * npx, w, h, quality, ratio, d_out + (size_t)f * out_stride, out_stride,
+                             d_lens ? d_lens + f : ctx->d_len);
     }
-    return JPGB200_OK;
+    if (overlap) {
+        if (rc == JPGB200_OK) rc = run_pending_tail(ctx); /* the last frame's tail */
+        ctx->have_pending = false;
+        ctx->overlap_now = false;
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_ks[0], 0);
+        cudaStreamWaitEvent(ctx->stream, ctx->ev_ks[1], 0);
+    }
+    return rc;
 }
 
 static int ensure_io(jpgb200_ctx *ctx, size_t npx, size_t cap, int slots)
