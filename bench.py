@@ -285,13 +285,16 @@ def run_b200(args):
     launches = enc.launch_count() - launches0
     ktimes = enc.kernel_times()
     enc.set_profiling(0)
-    # per-kernel breakdown of one more, untimed step (events around every launch)
+    # per-kernel breakdown of one more, untimed step (events around every launch; without the
+    # batch overlap, under which a tail kernel's event pair also spans its wait behind the next K1)
     enc.reset_profile()
     enc.set_profiling(1)
+    enc.set_batch_overlap(False)
     step()
     torch.cuda.synchronize()
     kbreak = enc.kernel_times()
     enc.set_profiling(0)
+    enc.set_batch_overlap(os.environ.get("JPGB200_OVERLAP", "1") != "0")
     t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

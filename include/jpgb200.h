@@ -122,7 +122,9 @@ int jpgb200_encode_device(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d
  * tail kernels (0xFF count, stuffed scatter) of frame f run on a second stream beside the chunk
  * encode of frame f+1 (two sets of entropy workspaces alternate); the context's stream has
  * waited for all of it when the call's work is done, so the caller sees plain stream order.
- * JPGB200_OVERLAP=0 in the environment turns the overlap off. */
+ * jpgb200_set_batch_overlap(ctx, 0), or JPGB200_OVERLAP=0 in the environment, turns the overlap
+ * off (per-kernel event timings are only meaningful without it). */
+int jpgb200_set_batch_overlap(jpgb200_ctx *ctx, int on);
 int jpgb200_encode_batch_device(jpgb200_ctx *ctx, const uint8_t *d_planes, int n_frames, int width, int height,
                                 int quality, int sample_ratio, uint8_t *d_out, size_t out_stride,
                                 unsigned long long *d_lens);

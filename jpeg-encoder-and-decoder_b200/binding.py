@@ -35,6 +35,7 @@ _SIGS = {
     "jpgb200_set_plain_transform": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_optimized_huffman": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_standard_mode": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_set_batch_overlap": (C.c_int, [_vp, C.c_int]),
     "jpgb200_huffman_specs": (C.c_int, [_vp, _vp, _vp, _vp]),
     "jpgb200_encode_planar": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "jpgb200_encode_planar_any": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -204,6 +205,9 @@ class Encoder:
         self._ck(lib().jpgb200_encode_planar_any(self._h, r.ctypes.data, g.ctypes.data, b.ctypes.data, w, h, quality, ratio,
                                                 out.ctypes.data, cap, C.byref(n)))
         return out[: n.value].copy()
+
+    def set_batch_overlap(self, on):
+        self._ck(lib().jpgb200_set_batch_overlap(self._h, 1 if on else 0))
 
     def set_standard_mode(self, on):
         self._ck(lib().jpgb200_set_standard_mode(self._h, 1 if on else 0))

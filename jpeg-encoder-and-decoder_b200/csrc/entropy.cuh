@@ -601,7 +601,8 @@ struct KeCfg {
     static const int OFF_PRIV = ROW_BYTES;
     static const int OFF_H = OFF_PRIV + NT * PSTRIDE * 4;
     static const int OFF_OFF = OFF_H + (int)sizeof(HuffPack);
-    static const int OFF_WARP = OFF_OFF + NT * 4;
+    static const int OFF_EX = OFF_OFF + NT * 4;
+    static const int OFF_WARP = OFF_EX + NT * 4;
     static const int OFF_FLAG = OFF_WARP + (NT / 32) * 4;
     static const int BYTES = OFF_FLAG + 16;
 };
@@ -685,6 +686,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     uint32_t *sP = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_PRIV);
     HuffPack &sH = *reinterpret_cast<HuffPack *>(ke_smem + L::OFF_H);
     uint32_t *sOff = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_OFF);
+    uint32_t *sEx = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_EX);
     uint32_t *sWarp = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_WARP);
     uint32_t *sFlag = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_FLAG);
     const int tid = threadIdx.x;
@@ -733,15 +735,16 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
         if (nbits > (uint32_t)L::PRIV * 32u) *sFlag = 1u;
     }
     sOff[mp.e_local] = nbits; /* stream order */
-    __syncthreads();
+    __syncthreads(); /* every entry is coded: the coefficient rows are dead from here on */
     uint32_t total;
     {
+        /* thread t scans stream position t; the result goes to a second array, so the lengths need
+         * no barrier of their own before they are overwritten */
         const uint32_t ex = cta_exclusive_scan<NT>(sOff[tid], sWarp, tid, total);
-        __syncthreads();
-        sOff[tid] = ex;
+        sEx[tid] = ex;
     }
     __syncthreads();
-    if (q.local_off && mp.valid && mp.blk_local >= 0) q.local_off[m0 * BPM + mp.blk_local] = sOff[mp.e_local];
+    if (q.local_off && mp.valid && mp.blk_local >= 0) q.local_off[m0 * BPM + mp.blk_local] = sEx[mp.e_local];
     if (tid == 0) {
         q.cta_bits[chunk] = total;
         atomicAdd(&q.super_bits[chunk >> EC_SUPER_SHIFT], total);
@@ -749,10 +752,9 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     const uint32_t nwords = (total + 31u) >> 5;
     const bool staged = (*sFlag == 0u) && nwords < (uint32_t)L::STAGE_WORDS; /* word [nwords] may receive an empty OR */
     uint32_t *slot = q.tmp + chunk * q.slot_words;
-    const uint32_t loff = sOff[mp.e_local];
+    const uint32_t loff = sEx[mp.e_local];
     if (staged) {
-        /* the coefficient rows are dead (every entry is coded): the chunk stream takes their place */
-        __syncthreads();
+        /* the chunk stream takes the place of the (dead) coefficient rows */
         for (uint32_t i = tid; i < nwords + 1u; i += NT) sS[i] = 0u;
         __syncthreads();
         if (mp.valid) {

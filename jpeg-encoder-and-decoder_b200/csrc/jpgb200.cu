@@ -560,6 +560,13 @@ extern "C" int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on)
     return JPGB200_OK;
 }
 
+extern "C" int jpgb200_set_batch_overlap(jpgb200_ctx *ctx, int on)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    ctx->overlap_on = on != 0;
+    return JPGB200_OK;
+}
+
 extern "C" int jpgb200_set_standard_mode(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;

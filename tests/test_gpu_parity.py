@@ -540,3 +540,40 @@ def test_420_standard_mode_any_size_and_optimal_tables(enc, w, h, q, seed):
     src = np.stack([r, g, b], axis=-1).reshape(h, w, 3).astype(np.float64)
     mse = float(((dec - src) ** 2).mean())
     assert 10 * np.log10(255.0 ** 2 / max(mse, 1e-9)) > 30.0
+
+
+@pytest.mark.parametrize("w,h,ratio,nf", [(512, 256, 0, 7), (1920, 1088, 2, 4), (640, 64, 1, 5)])
+def test_batch_overlap_is_invisible(enc, w, h, ratio, nf):
+    """jpgb200_encode_batch_device runs frame f's tail kernels on a second stream beside frame
+    f+1's chunk encode (two alternating sets of entropy workspaces).  Streams and lengths are the
+    same bytes with the overlap on, off, and frame by frame; a second batch right behind the
+    first (workspace parity carried over) as well."""
+    q, npx = 75, w * h
+    d_pl = enc.malloc(nf * 3 * npx)
+    cap = 3 * npx + 4096
+    d_out = enc.malloc(nf * cap)
+    d_len = enc.malloc(8 * nf)
+    try:
+        for f in range(nf):
+            enc.synth_device(d_pl + f * 3 * npx, w, h, 4321, f, f & 1)
+        enc.sync()
+        res = {}
+        for mode in ("on", "off", "on2"):
+            enc.set_batch_overlap(mode != "off")
+            enc.h2d(d_out, np.zeros(nf * cap, np.uint8))
+            enc.encode_batch_device(d_pl, nf, w, h, q, ratio, d_out, cap, d_len)
+            enc.sync()
+            res[mode] = (enc.d2h(d_len, 8 * nf).view(np.uint64).copy(), enc.d2h(d_out, nf * cap).reshape(nf, cap).copy())
+        enc.set_batch_overlap(True)
+        planes = enc.d2h(d_pl, nf * 3 * npx).reshape(nf, 3, -1)
+        for f in range(nf):
+            one = enc.encode_planar(planes[f, 0], planes[f, 1], planes[f, 2], w, h, q, ratio)
+            for mode in res:
+                lens, outs = res[mode]
+                assert int(lens[f]) == one.size, (mode, f)
+                assert (outs[f, :one.size] == one).all(), (mode, f)
+    finally:
+        enc.set_batch_overlap(True)
+        enc.free(d_pl)
+        enc.free(d_out)
+        enc.free(d_len)
