@@ -122,6 +122,7 @@ struct jpgb200_ctx {
     cudaEvent_t ev_ke, ev_ks[2];
     bool overlap_on;     /* jpgb200_encode_batch_device overlaps tails (JPGB200_OVERLAP=0 turns it off) */
     bool overlap_now;    /* inside such a batch */
+    bool in_batch;       /* inside a batch call: the per-block offset tap is not written */
     bool have_pending;   /* a frame's tail waits to be launched behind the next frame's K1 */
     TailParams pending_q;
     int pending_parity;
@@ -1033,7 +1034,7 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     e.cta_bits = ctx->d_cta_bits;
     e.cta_tail = ctx->d_cta_tail;
     e.super_bits = ctx->d_super;
-    e.local_off = ctx->d_local_off;
+    e.local_off = ctx->overlap_now || ctx->in_batch ? NULL : ctx->d_local_off; /* parity tap: not inside batches */
     const unsigned nc = (unsigned)n_chunks(n);
     if (!ctx->ke_attr_set) {
         CK(cudaFuncSetAttribute(k_encode_chunks<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<0>::BYTES));
@@ -1280,6 +1281,7 @@ extern "C" int jpgb200_encode_batch_device(jpgb200_ctx *ctx, const uint8_t *d_pl
     const bool overlap = ctx->overlap_on && ctx->legacy_entropy && !ctx->opt_huff && n_frames >= 2;
     int rc = JPGB200_OK;
     ctx->overlap_now = overlap;
+    ctx->in_batch = true;
     for (int f = 0; f < n_frames && rc == JPGB200_OK; f++) {
         const uint8_t *pl = d_planes + (size_t)f * 3 * npx;
         if (overlap) {
@@ -1291,6 +1293,8 @@ extern "C" int jpgb200_encode_batch_device(jpgb200_ctx *ctx, const uint8_t *d_pl
             rc = encode_core(ctx, pl, pl + npx, pl + 2 * npx, w, h, quality, ratio, d_out + (size_t)f * out_stride, out_stride,
                              d_lens ? d_lens + f : ctx->d_len);
     }
+    ctx->in_batch = false;
+    ctx->have_bits = false; /* no offset tap after a batch */
     if (overlap) {
         if (rc == JPGB200_OK) rc = run_pending_tail(ctx); /* the last frame's tail */
         ctx->have_pending = false;
@@ -1453,7 +1457,10 @@ extern "C" int jpgb200_encode_batch_host(jpgb200_ctx *ctx, const uint8_t *const 
         CK(cudaEventRecord(ev_in[s], ctx->copy_in));
         CK(cudaStreamWaitEvent(ctx->stream, ev_in[s], 0));
         uint8_t *dp = ctx->d_planes[s];
+        ctx->in_batch = true;
         rc = encode_core(ctx, dp, dp + npx, dp + 2 * npx, w, h, quality, ratio, ctx->d_out[s], cap, d_hlen + s);
+        ctx->in_batch = false;
+        ctx->have_bits = false;
         if (rc) break;
         CK(cudaEventRecord(ev_done[s], ctx->stream));
         if (f >= 1) rc = drain(f - 1);
