@@ -218,7 +218,9 @@ int jpgb200_synth_device(jpgb200_ctx *ctx, uint8_t *d_planes, int width, int hei
 /* ---- measurement --------------------------------------------------------------------- */
 /* With profiling on (1), every kernel launch of the encode path is bracketed by CUDA events on
  * the launching stream; with 2 only K1's launches are (two event records per frame instead of
- * eight: for a timed region that wants the roofline kernel's live duration and little else); sums are read back with jpgb200_kernel_times (ms and launch counts
+ * eight: for a timed region that wants the roofline kernel's live duration and little else), with
+ * 3 only every eighth K1 launch (jpgb200_kernel_times then reports the sampled launches: their
+ * count and their summed duration); sums are read back with jpgb200_kernel_times (ms and launch counts
  * per kernel, JPGB200_NUM_KERNELS entries) and cleared by jpgb200_reset_profile. */
 int jpgb200_set_profiling(jpgb200_ctx *ctx, int on);
 int jpgb200_kernel_times(jpgb200_ctx *ctx, double *ms, long long *launches);
