@@ -50,7 +50,7 @@ extern "C" {
 #define JPGB200_SYM_REF 0           /* AC histogram index run|size (src/huffman.c:218)          */
 #define JPGB200_SYM_SPEC 1          /* (run<<4)|size                                            */
 
-#define JPGB200_NUM_KERNELS 5 /* K1 transform, K35 fused entropy; staged: KE encode chunks, KF count 0xFF, KS scatter */
+#define JPGB200_NUM_KERNELS 6 /* K1 transform, K35 single-launch entropy, KE encode chunks, KF count 0xFF, KS scatter, K1E fused transform + chunk encode */
 
 typedef struct jpgb200_ctx jpgb200_ctx;
 
@@ -65,10 +65,21 @@ const char *jpgb200_last_error(const jpgb200_ctx *ctx);
 /* Run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = context's own. */
 int jpgb200_set_stream(jpgb200_ctx *ctx, void *cuda_stream);
 int jpgb200_sync(jpgb200_ctx *ctx);
-/* Entropy stage selection: 0 (default) = the fused single-launch kernel K35; 1 = the staged
- * K3 (bit lengths) / K4 (scan) / K5 (pack) / K6 (stuffing) pipeline, kept for the MCU-row
- * partition and as a cross-check -- both produce identical bytes. */
+/* Entropy stage selection: 1 (default) = the staged pipeline KE (chunk encode) / KF (0xFF count) /
+ * KS (stuffed scatter); 0 = the single-launch kernel K35 (count -> chained scan -> pack -> stuff),
+ * byte-identical and slower, kept as a cross-check; K35 takes 4:4:4 and 4:2:2 only and disables the
+ * batch overlap and the fused transform below. */
 int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on);
+/* Transform/entropy fusion: 1 (default) = K1E, one persistent kernel from pixels to chunk streams
+ * (csrc/k1_fused.cuh; the chain dct -> quantise -> zig_zag -> dpcm -> huffman_encode of
+ * src/jpg_encode.c:36-50 without the coefficients ever reaching HBM), followed by KF/KS;
+ * 0 = K1 and KE as separate kernels with the int16 coefficients in HBM between them.  Identical
+ * bytes.  K1E needs width % 16 == 0, 4:4:4 or 4:2:2 and the tables.h Huffman tables; other
+ * cases (4:2:0, per-image optimal tables, the parity taps, the MCU-row bands) take the separate kernels. */
+int jpgb200_set_fused_transform(jpgb200_ctx *ctx, int on);
+/* 1 = K1E also stores its coefficients (jpgb200_last_coefficients reads them): the parity tap of
+ * the fused kernel.  Default 0. */
+int jpgb200_set_fused_tap(jpgb200_ctx *ctx, int on);
 /* K1 selection (identical results; the alternatives are kept for A/B runs and as cross-checks):
  *   0 (default) producer/consumer form: convert, transform and store warps hand tiles over through
  *               mbarriers, TMA tensor stores (csrc/k1_pc.cuh); needs width % 16 == 0
@@ -166,6 +177,9 @@ int jpgb200_jfif_header(int width, int height, int quality, int sample_ratio, ui
  * (chroma halved for 4:2:2). */
 int jpgb200_coefficients(jpgb200_ctx *ctx, const uint8_t *r, const uint8_t *g, const uint8_t *b, int width,
                          int height, int quality, int sample_ratio, int16_t *zz_out);
+/* The coefficients the last encode left in HBM (same layout): every encode through the separate
+ * kernels, or through K1E with jpgb200_set_fused_tap(ctx, 1). */
+int jpgb200_last_coefficients(jpgb200_ctx *ctx, int16_t *zz_out);
 /* dpcm() on the coefficients of the last jpgb200_coefficients/encode call
  * (src/dpcm.c:6-21): d_out = int32 [Y | Cb | Cr] DC sequences in the requested mode. */
 int jpgb200_dc_sequence(jpgb200_ctx *ctx, int mode, int32_t *d_out);

@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(HERE, "libjpgb200.so")
 
 DC_REF, DC_SPEC = 0, 1
 SYM_REF, SYM_SPEC = 0, 1
-NUM_KERNELS = 5
+NUM_KERNELS = 6  # JPGB200_NUM_KERNELS
 
 ERR_NO_DEVICE, ERR_BAD_DIMS, ERR_BAD_QUALITY, ERR_CUDA, ERR_OUT_TOO_SMALL, ERR_BAD_ARG, ERR_NOMEM = -1, -2, -3, -4, -5, -6, -7
 
@@ -36,6 +36,9 @@ _SIGS = {
     "jpgb200_set_optimized_huffman": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_standard_mode": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_batch_overlap": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_set_fused_transform": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_set_fused_tap": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_last_coefficients": (C.c_int, [_vp, _vp]),
     "jpgb200_huffman_specs": (C.c_int, [_vp, _vp, _vp, _vp]),
     "jpgb200_encode_planar": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
     "jpgb200_encode_planar_any": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -209,6 +212,14 @@ class Encoder:
     def set_batch_overlap(self, on):
         self._ck(lib().jpgb200_set_batch_overlap(self._h, 1 if on else 0))
 
+    def set_fused_transform(self, on):
+        """K1E (transform + chunk encode in one kernel, the default) on/off"""
+        self._ck(lib().jpgb200_set_fused_transform(self._h, 1 if on else 0))
+
+    def set_fused_tap(self, on):
+        """K1E additionally writes its coefficients to HBM (read them back with last_coefficients)"""
+        self._ck(lib().jpgb200_set_fused_tap(self._h, 1 if on else 0))
+
     def set_standard_mode(self, on):
         self._ck(lib().jpgb200_set_standard_mode(self._h, 1 if on else 0))
 
@@ -264,6 +275,12 @@ class Encoder:
         zz = np.empty((sum(n), 64), np.int16)
         self._ck(lib().jpgb200_coefficients(self._h, r.ctypes.data, g.ctypes.data, b.ctypes.data, w, h, quality, ratio, zz.ctypes.data))
         self._n = n
+        return zz
+
+    def last_coefficients(self, w, h, ratio=0):
+        nb = num_blocks(w, h, ratio)
+        zz = np.empty((sum(nb), 64), dtype=np.int16)
+        self._ck(lib().jpgb200_last_coefficients(self._h, zz.ctypes.data))
         return zz
 
     def dc_sequence(self, mode):

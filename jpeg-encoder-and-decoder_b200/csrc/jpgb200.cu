@@ -31,6 +31,7 @@
 #include "k1_warp.cuh"
 #include "k1_pipe.cuh"
 #include "k1_pc.cuh"
+#include "k1_fused.cuh"
 #include "tail.cuh"
 #include "taps.cuh"
 
@@ -42,9 +43,9 @@ struct HuffSpecs {
     int nvals[4];
 };
 
-enum { KI_K1 = 0, KI_K35, KI_KE, KI_KF, KI_KS };
+enum { KI_K1 = 0, KI_K35, KI_KE, KI_KF, KI_KS, KI_K1E };
 static const char *kKernelNames[JPGB200_NUM_KERNELS] = {"k1_transform", "k35_entropy", "k_encode_chunks", "k_count_ff",
-                                                        "k_scatter"};
+                                                        "k_scatter", "k1e_fused"};
 
 struct EvPair {
     int k;
@@ -132,7 +133,14 @@ struct jpgb200_ctx {
     HuffDev std_huff;    /* the tables.h tables, kept for switching back */
     HuffBits std_hbits;
     HuffPack std_hpack;
-    bool legacy_entropy; /* staged K3/K4/K5/K6 pipeline instead of the fused K35 (tests) */
+    bool legacy_entropy; /* staged KE/KF/KS pipeline (default) instead of the single-launch K35 */
+    bool fused_k1e;      /* K1E: transform + chunk encode in one kernel, coefficients stay on chip (default) */
+    int k1e_per_sm[4];   /* resident CTAs per SM of k1e_fused<RATIO, STD>, 0 = not yet queried */
+    bool k1e_tap;        /* K1E also writes the coefficients to HBM (jpgb200_set_fused_tap) */
+    unsigned long long *d_dc_pub; /* K1E: last DC per tile and component, {epoch, DC} words */
+    size_t dc_pub_cap;
+    unsigned k1e_epoch;
+    long long geo_chunks, geo_slot_words; /* chunk geometry of the streams now in d_tmp (KE: 64 MCUs; K1E: tiles) */
     /* quantiser cache */
     int q_cached;
     float mul[2][64];
@@ -431,7 +439,10 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
     ctx->q_cached = -1;
     ctx->legacy_entropy = true; /* measured faster than the fused K35 so far */
     ctx->k1_pc = true;          /* K1 default: the producer/consumer form (fastest measured) */
+    ctx->fused_k1e = true;      /* transform + chunk encode in one kernel (k1_fused.cuh) */
     {
+        const char *fz = getenv("JPGB200_FUSED"); /* "0": K1 and KE as separate kernels (A/B runs) */
+        if (fz && !strcmp(fz, "0")) ctx->fused_k1e = false;
         const char *e = getenv("JPGB200_ENTROPY"); /* "fused" | "staged": experiment switch for bench runs */
         if (e && !strcmp(e, "fused")) ctx->legacy_entropy = false;
         const char *k = getenv("JPGB200_K1"); /* "plain" | "tma" */
@@ -504,7 +515,7 @@ extern "C" void jpgb200_destroy(jpgb200_ctx *ctx)
     void *ptrs[] = {ctx->d_huff,     ctx->d_hpack, ctx->d_hbits, ctx->d_scan_order, ctx->d_planes[0], ctx->d_planes[1], ctx->d_zz,   ctx->d_local_off,
                     ctx->d_cta_bits, ctx->d_super, ctx->d_cta_base,   ctx->d_cta_ff,    ctx->d_cta_tail,  ctx->d_tmp,
                     ctx->d_state,    ctx->d_bit_state, ctx->d_ff_state, ctx->d_header,     ctx->d_out[0],    ctx->d_out[1],    ctx->d_len,  ctx->d_dc,
-                    ctx->d_tile_sum, ctx->d_freq};
+                    ctx->d_tile_sum, ctx->d_freq,      ctx->d_dc_pub};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_len) cudaFreeHost(ctx->h_len);
@@ -560,6 +571,20 @@ extern "C" int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;
     ctx->legacy_entropy = on != 0;
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_set_fused_transform(jpgb200_ctx *ctx, int on)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    ctx->fused_k1e = on != 0;
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_set_fused_tap(jpgb200_ctx *ctx, int on)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    ctx->k1e_tap = on != 0;
     return JPGB200_OK;
 }
 
@@ -631,8 +656,8 @@ struct LaunchScope {
     bool on;
     LaunchScope(jpgb200_ctx *c, int kk) : ctx(c), k(kk)
     {
-        on = ctx->profiling == 1 || (ctx->profiling == 2 && kk == KI_K1) ||
-             (ctx->profiling == 3 && kk == KI_K1 && (ctx->k1_seen++ & 7) == 0);
+        const bool head = (kk == KI_K1 || kk == KI_K1E); /* the frame's first and largest kernel */
+        on = ctx->profiling == 1 || (ctx->profiling == 2 && head) || (ctx->profiling == 3 && head && (ctx->k1_seen++ & 7) == 0);
         if (on) {
             a = get_event(ctx);
             b = get_event(ctx);
@@ -733,13 +758,31 @@ static long long slot_words(const long long n[3])
     return (((long long)EC_MCUS * bpm * 1658 + 31) / 32 + 4) & ~3ll;
 }
 
-static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_zz)
+/* K1E's chunks are K1's tiles: 32 blocks of one block row per full-resolution component */
+static long long tile_chunks(int w, int h) { return (long long)((w / 8 + K1_TILE_BLOCKS - 1) / K1_TILE_BLOCKS) * (h / 8); }
+static long long tile_slot_words(int ratio)
+{
+    const long long blocks = ratio == 0 ? 96 : 64;
+    return ((blocks * 1658 + 31) / 32 + 4) & ~3ll;
+}
+
+/* w, h > 0: also size the chunk workspaces for K1E's tile geometry */
+static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_zz, int w = 0, int h = 0, int ratio = 0)
 {
     const long long nb = n[0] + n[1] + n[2];
     int rc;
     if ((rc = grow(ctx, &ctx->d_zz, &ctx->zz_cap, (size_t)nb * 128 * (size_t)nframes_zz))) return rc;
     if ((rc = grow(ctx, &ctx->d_local_off, &ctx->local_cap, (size_t)nb * 4))) return rc;
-    const size_t nc = (size_t)n_chunks(n);
+    size_t nc = (size_t)n_chunks(n);
+    size_t tmp_words = nc * (size_t)slot_words(n);
+    if (w > 0 && ratio != 2) {
+        const size_t nct = (size_t)tile_chunks(w, h);
+        if (nct * (size_t)tile_slot_words(ratio) > tmp_words) tmp_words = nct * (size_t)tile_slot_words(ratio);
+        if (nct > nc) nc = nct;
+        unsigned long long *before = ctx->d_dc_pub;
+        if ((rc = grow(ctx, &ctx->d_dc_pub, &ctx->dc_pub_cap, nct * 3 * 8))) return rc;
+        if (ctx->d_dc_pub != before) CK(cudaMemsetAsync(ctx->d_dc_pub, 0, ctx->dc_pub_cap, ctx->stream)); /* epoch 0 is never used */
+    }
     if (ctx->cta_cap < nc * 8 || !ctx->d_cta_bits) {
         size_t c1 = 0, c2 = 0;
         if (ctx->d_cta_bits) {
@@ -775,7 +818,7 @@ static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_
         CK(cudaMemsetAsync(ctx->d_ff_state, 0, c2, ctx->stream));
         ctx->chain_cap = c1 / 8;
     }
-    if ((rc = grow(ctx, &ctx->d_tmp, &ctx->tmp_cap, nc * (size_t)slot_words(n) * 4))) return rc;
+    if ((rc = grow(ctx, &ctx->d_tmp, &ctx->tmp_cap, tmp_words * 4))) return rc;
     {
         const size_t nsb = nc / 64 + 2, nsf = nc / 64 + 2;
         if (!ctx->d_super || ctx->n_super_bits < nsb || ctx->n_super_ff < nsf) {
@@ -1021,6 +1064,95 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
     return JPGB200_OK;
 }
 
+/* K1E: transform + chunk encode in one persistent kernel (k1_fused.cuh).  The chunk streams, their
+ * lengths and the two-level sums land where KE would leave them (tile geometry), KF/KS follow. */
+template <int RATIO, bool STD>
+static int launch_k1e_t(jpgb200_ctx *ctx, const K1Params &p, long long n_tiles, const K1PStore &st, const K1EParams &e)
+{
+    const size_t smem = sizeof(K1ESmem) + 1024;
+    int &per_sm = ctx->k1e_per_sm[RATIO * 2 + (STD ? 1 : 0)];
+    if (per_sm == 0) {
+        CK(cudaFuncSetAttribute((k1e_fused<RATIO, STD>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k1e_fused<RATIO, STD>), K1E_THREADS, smem));
+        if (per_sm < 1) {
+            per_sm = 0;
+            snprintf(ctx->err, sizeof ctx->err, "k1e_fused does not fit an SM");
+            return JPGB200_ERR_CUDA;
+        }
+    }
+    /* every CTA must be resident: tile t waits for the DC that tile t-1's CTA publishes */
+    const long long resident = (long long)ctx->sm_count * per_sm;
+    const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+    LaunchScope ls(ctx, KI_K1E);
+    k1e_fused<RATIO, STD><<<grid, K1E_THREADS, smem, ctx->stream>>>(p, n_tiles, st, e);
+    return JPGB200_OK;
+}
+
+static bool k1e_usable(const jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w, int ratio,
+                       long long plane_stride)
+{
+    return ctx->fused_k1e && ctx->legacy_entropy && !ctx->opt_huff && ratio != 2 && (w % 16 == 0) &&
+           (((uintptr_t)d_r | (uintptr_t)d_g | (uintptr_t)d_b) % 16 == 0) && (plane_stride % 16 == 0);
+}
+
+static int launch_k1e(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w, int h, int ratio,
+                      const long long n[3], int16_t *zz_tap, int has_halo, const int *pred)
+{
+    K1Params p;
+    p.r = d_r;
+    p.g = d_g;
+    p.b = d_b;
+    p.zz_y = zz_tap;
+    p.zz_cb = zz_tap ? zz_tap + n[0] * 64 : NULL;
+    p.zz_cr = zz_tap ? zz_tap + (n[0] + n[1]) * 64 : NULL;
+    p.plane_stride = 0;
+    p.zz_stride = 0;
+    p.W = w;
+    p.H = h;
+    p.BW = w / 8;
+    p.has_halo = has_halo;
+    p.clear = NULL; /* the two-level sums are cleared by a memset in front of the kernel: it accumulates into them */
+    p.clear_n = 0;
+    memcpy(p.mul, ctx->mul, sizeof p.mul);
+    memcpy(p.oob, ctx->oob, 24);
+    p.tiles_per_row = (p.BW + K1_TILE_BLOCKS - 1) / K1_TILE_BLOCKS;
+    p.n_frames = 1;
+    {
+        const unsigned long long per_frame = (unsigned long long)p.tiles_per_row * (unsigned long long)(h / 8);
+        const bool ok = per_frame * per_frame < (1ull << 40) && per_frame < (1ull << 31);
+        p.magic_pf = ok ? ((1ull << 40) + per_frame - 1) / per_frame : 0ull;
+        p.magic_tpr = ok ? ((1ull << 40) + (unsigned long long)p.tiles_per_row - 1) / (unsigned long long)p.tiles_per_row : 0ull;
+    }
+    const long long n_tiles = tile_chunks(w, h);
+    ctx->geo_chunks = n_tiles;
+    ctx->geo_slot_words = tile_slot_words(ratio);
+    K1EParams e;
+    e.tmp = ctx->d_tmp;
+    e.slot_words = ctx->geo_slot_words;
+    e.cta_bits = ctx->d_cta_bits;
+    e.cta_tail = ctx->d_cta_tail;
+    e.super_bits = ctx->d_super;
+    e.dc_pub = ctx->d_dc_pub;
+    if (++ctx->k1e_epoch == 0u) ctx->k1e_epoch = 1u;
+    e.epoch = ctx->k1e_epoch;
+    e.huff = ctx->d_hpack;
+    e.store_coefs = zz_tap ? 1 : 0;
+    for (int c = 0; c < 3; c++) e.dc_pred[c] = pred ? pred[c] : 0;
+    K1PStore st;
+    memset(&st, 0, sizeof st);
+    if (zz_tap) make_store_maps(ctx, &st, zz_tap, n, 0, 1);
+    CK(cudaMemsetAsync(ctx->d_super, 0, (ctx->n_super_bits + ctx->n_super_ff) * 4, ctx->stream));
+    int rc;
+    if (ctx->std_mode)
+        rc = ratio == 0 ? launch_k1e_t<0, true>(ctx, p, n_tiles, st, e) : launch_k1e_t<1, true>(ctx, p, n_tiles, st, e);
+    else
+        rc = ratio == 0 ? launch_k1e_t<0, false>(ctx, p, n_tiles, st, e) : launch_k1e_t<1, false>(ctx, p, n_tiles, st, e);
+    if (rc) return rc;
+    CK(cudaGetLastError());
+    ctx->have_bits = false;
+    return JPGB200_OK;
+}
+
 /* KE: every chunk's bit lengths and its packed, chunk-local stream; two-level sums of the lengths */
 static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3], const int *pred = NULL,
                        bool clear_supers = false)
@@ -1039,6 +1171,8 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     e.super_bits = ctx->d_super;
     e.local_off = ctx->overlap_now || ctx->in_batch ? NULL : ctx->d_local_off; /* parity tap: not inside batches */
     const unsigned nc = (unsigned)n_chunks(n);
+    ctx->geo_chunks = n_chunks(n);
+    ctx->geo_slot_words = slot_words(n);
     if (!ctx->ke_attr_set) {
         CK(cudaFuncSetAttribute(k_encode_chunks<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<0>::BYTES));
         CK(cudaFuncSetAttribute(k_encode_chunks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<1>::BYTES));
@@ -1099,8 +1233,9 @@ static int launch_tail(jpgb200_ctx *ctx, const long long n[3], unsigned bit_phas
 {
     TailParams q;
     q.tmp = ctx->d_tmp;
-    q.slot_words = slot_words(n);
-    q.n_chunks = n_chunks(n);
+    (void)n;
+    q.slot_words = ctx->geo_slot_words;
+    q.n_chunks = ctx->geo_chunks;
     q.cta_bits = ctx->d_cta_bits;
     q.super_bits = ctx->d_super;
     q.cta_ff = ctx->d_cta_ff;
@@ -1233,13 +1368,19 @@ static int encode_core(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g,
     long long n[3];
     int rc = validate(w, h, quality, ratio, n);
     if (rc) return rc;
-    if ((rc = ensure_workspace(ctx, n, 1))) return rc;
+    if ((rc = ensure_workspace(ctx, n, 1, w, h, ratio))) return rc;
     if ((rc = ensure_tables(ctx, w, h, quality, ratio))) return rc;
     ctx->w = w;
     ctx->h = h;
     ctx->q = quality;
     ctx->ratio = ratio;
     memcpy(ctx->n, n, sizeof n);
+    if (d_out && k1e_usable(ctx, d_r, d_g, d_b, w, ratio, 0)) {
+        /* the default: pixels -> chunk streams in one kernel, coefficients stay on chip */
+        if ((rc = launch_k1e(ctx, d_r, d_g, d_b, w, h, ratio, n, ctx->k1e_tap ? ctx->d_zz : NULL, 0, NULL))) return rc;
+        if (ctx->overlap_now && (rc = run_pending_tail(ctx))) return rc;
+        return launch_pack(ctx, ctx->d_zz, ratio, n, d_out, cap, len_out);
+    }
     if ((rc = launch_k1(ctx, d_r, d_g, d_b, w, h, ratio, n, 1, 0, ctx->d_zz, 0, 0))) return rc;
     if (ctx->overlap_now && (rc = run_pending_tail(ctx))) return rc; /* the previous frame's tail, beside this frame's KE */
     if (d_out) {
@@ -1605,6 +1746,15 @@ extern "C" int jpgb200_coefficients(jpgb200_ctx *ctx, const uint8_t *r, const ui
     CK(cudaMemcpyAsync(dp + 2 * npx, b, npx, cudaMemcpyHostToDevice, ctx->stream));
     if ((rc = encode_core(ctx, dp, dp + npx, dp + 2 * npx, w, h, quality, ratio, NULL, 0, NULL))) return rc;
     CK(cudaMemcpyAsync(zz_out, ctx->d_zz, (size_t)(n[0] + n[1] + n[2]) * 128, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_last_coefficients(jpgb200_ctx *ctx, int16_t *zz_out)
+{
+    if (!ctx || !zz_out || !ctx->d_zz || ctx->n[0] == 0) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(zz_out, ctx->d_zz, (size_t)(ctx->n[0] + ctx->n[1] + ctx->n[2]) * 128, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return JPGB200_OK;
 }
