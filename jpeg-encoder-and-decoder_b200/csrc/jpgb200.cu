@@ -1073,7 +1073,7 @@ static int launch_k1e_t(jpgb200_ctx *ctx, const K1Params &p, long long n_tiles, 
     int &per_sm = ctx->k1e_per_sm[RATIO * 2 + (STD ? 1 : 0)];
     if (per_sm == 0) {
         CK(cudaFuncSetAttribute((k1e_fused<RATIO, STD>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k1e_fused<RATIO, STD>), K1E_THREADS, smem));
+        CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, (k1e_fused<RATIO, STD>), K1ECfg<RATIO>::THREADS, smem));
         if (per_sm < 1) {
             per_sm = 0;
             snprintf(ctx->err, sizeof ctx->err, "k1e_fused does not fit an SM");
@@ -1084,7 +1084,7 @@ static int launch_k1e_t(jpgb200_ctx *ctx, const K1Params &p, long long n_tiles, 
     const long long resident = (long long)ctx->sm_count * per_sm;
     const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
     LaunchScope ls(ctx, KI_K1E);
-    k1e_fused<RATIO, STD><<<grid, K1E_THREADS, smem, ctx->stream>>>(p, n_tiles, st, e);
+    k1e_fused<RATIO, STD><<<grid, K1ECfg<RATIO>::THREADS, smem, ctx->stream>>>(p, n_tiles, st, e);
     return JPGB200_OK;
 }
 

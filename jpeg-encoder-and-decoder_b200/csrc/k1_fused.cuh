@@ -36,10 +36,9 @@
 
 namespace jpgb200 {
 
-#define K1E_THREADS 384
-#define K1E_PRIV 12                /* words of private stream per entry */
+#define K1E_PRIV 10                /* words of private stream per entry */
 #define K1E_PSTRIDE (K1E_PRIV + 1) /* odd: lanes hit distinct banks */
-#define K1E_STAGE_WORDS 1536       /* chunk stream staging: 6 KB (a natural 8K tile needs ~0.5 KB) */
+#define K1E_STAGE_WORDS 768        /* chunk stream staging: 3 KB (a natural 8K tile needs ~0.5 KB) */
 
 template <int RATIO>
 struct K1ECfg {
@@ -47,9 +46,21 @@ struct K1ECfg {
     static const int NEW = (RATIO == 0) ? 4 : 3;       /* entropy warps with work */
     static const int NE = 32 * NEW;                    /* entropy threads = entries per full tile */
     static const int BPT = (RATIO == 0) ? 96 : 64;     /* blocks per tile */
+    /* entropy groups: each is a warpgroup that codes every NG-th tile of the CTA on its own (a tile's
+     * coding is a long dependent chain per lane: what hides its latency is a second tile in flight) */
+    static const int NG = (RATIO == 0) ? 2 : 1;
+    static const int THREADS = 256 + 128 * NG;
+    /* registers per thread after setmaxnreg; the launch bound is 65536 / (2 * THREADS) rounded down to 8 */
     static const int REG_CONVERT = (RATIO == 0) ? 48 : 72;
-    static const int REG_TRANSFORM = (RATIO == 0) ? 128 : 112;
+    static const int REG_TRANSFORM = (RATIO == 0) ? 96 : 112;
     static const int REG_ENTROPY = 56;
+};
+
+struct K1EGroup {
+    uint32_t stage[K1E_STAGE_WORDS]; /* the chunk stream, numeric (MSB-first) words; all zero between tiles */
+    uint32_t priv[128 * K1E_PSTRIDE];
+    uint32_t off[128];               /* entry lengths in stream order */
+    uint32_t flag[4];                /* [0..1] per tile parity: an entry overflowed its private region */
 };
 
 struct K1ESmem {
@@ -57,11 +68,8 @@ struct K1ESmem {
     K1F samples[2][3];                               /* 48 KB */
     uint8_t raw[4][K1C_STAGES][3][2][K1_ROW_BYTES];  /* 18 KB */
     float mul[2][64];
-    uint32_t stage[K1E_STAGE_WORDS];                 /* the chunk stream, numeric (MSB-first) words; all zero between tiles */
-    uint32_t priv[128 * K1E_PSTRIDE];
     HuffPack huff;
-    uint32_t off[128];                               /* entry lengths in stream order */
-    uint32_t flag[2];                                /* per tile parity: an entry overflowed its private region */
+    K1EGroup grp[2];
     unsigned long long samples_full[2], samples_free[2], coef_full[2], coef_free[2];
 };
 
@@ -78,7 +86,14 @@ struct K1EParams {
     int dc_pred[3];        /* predictor of the image's first blocks (0) */
 };
 
-__device__ __forceinline__ void k1e_bar(int count) { asm volatile("bar.sync 2, %0;" ::"r"(count) : "memory"); }
+/* named barrier of entropy group 0 / 1 (ids 2 / 3; immediate ids keep the kernel's barrier count at 4) */
+__device__ __forceinline__ void k1e_bar(int grp, int count)
+{
+    if (grp == 0)
+        asm volatile("bar.sync 2, %0;" ::"r"(count) : "memory");
+    else
+        asm volatile("bar.sync 3, %0;" ::"r"(count) : "memory");
+}
 
 __device__ __forceinline__ void k1e_publish_dc(unsigned long long *w, unsigned epoch, uint32_t word0)
 {
@@ -147,7 +162,7 @@ __device__ __forceinline__ void k1e_code(unsigned rowbase, unsigned sw4, bool do
 }
 
 template <int RATIO, bool STD = false>
-__global__ void __launch_bounds__(K1E_THREADS, 2) k1e_fused(const K1Params p, long long n_tiles, const __grid_constant__ K1PStore st,
+__global__ void __launch_bounds__(K1ECfg<RATIO>::THREADS, 2) k1e_fused(const K1Params p, long long n_tiles, const __grid_constant__ K1PStore st,
                                                             const K1EParams e)
 {
     typedef K1ECfg<RATIO> C;
@@ -158,11 +173,10 @@ __global__ void __launch_bounds__(K1E_THREADS, 2) k1e_fused(const K1Params p, lo
     constexpr int NT = C::NT;
 
     if (tid < 128) S.mul[tid >> 6][tid & 63] = p.mul[tid >> 6][tid & 63];
-    for (int i = tid; i < K1E_STAGE_WORDS; i += K1E_THREADS) S.stage[i] = 0u;
-    for (int i = tid; i < (int)(sizeof(HuffPack) / 4); i += K1E_THREADS)
+    for (int i = tid; i < (int)(sizeof(S.grp) / 4); i += C::THREADS) reinterpret_cast<uint32_t *>(S.grp)[i] = 0u;
+    for (int i = tid; i < (int)(sizeof(HuffPack) / 4); i += C::THREADS)
         reinterpret_cast<uint32_t *>(&S.huff)[i] = reinterpret_cast<const uint32_t *>(e.huff)[i];
     if (tid == 0) {
-        S.flag[0] = S.flag[1] = 0u;
 #pragma unroll
         for (int b = 0; b < 2; b++) {
             mbar_init(&S.samples_full[b], 4);
@@ -302,11 +316,12 @@ __global__ void __launch_bounds__(K1E_THREADS, 2) k1e_fused(const K1Params p, lo
         }
     } else {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(C::REG_ENTROPY));
-        const int we = w - 8;
+        const int grp = (w - 8) >> 2, we = (w - 8) & 3;
         if (we >= C::NEW) return;
-        /* ================= entropy warps ================= */
-        constexpr int NE = C::NE;
-        const int te = tid - 256;
+        /* ================= entropy group `grp`: tiles grp, grp + NG, ... of this CTA ================= */
+        constexpr int NE = C::NE, NG = C::NG;
+        const int te = tid - 256 - 128 * grp;
+        K1EGroup &G = S.grp[grp];
         /* entry of this thread (component-major, so that warps are component-pure) */
         int crow, row, part, e_local;
         bool first_of_comp;
@@ -333,10 +348,10 @@ __global__ void __launch_bounds__(K1E_THREADS, 2) k1e_fused(const K1Params p, lo
         const int comp = (RATIO == 0) ? crow : (luma ? 0 : 1 + (row >> 4));
         const unsigned sw4 = (unsigned)(row & 7) << 4;
         const uint32_t *sAc = S.huff.ac[luma ? 0 : 1], *sDc = S.huff.dc[luma ? 0 : 1];
-        uint32_t *priv = S.priv + te * K1E_PSTRIDE;
+        uint32_t *priv = G.priv + te * K1E_PSTRIDE;
 
-        int it = 0;
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+        int it = grp;
+        for (long long t = (long long)blockIdx.x + (long long)grp * gridDim.x; t < n_tiles; t += (long long)NG * gridDim.x, it += NG) {
             const int b = it & 1;
             const unsigned use = (unsigned)(it >> 1);
             const K1Tile tl = k1_tile(p, t);
@@ -396,15 +411,15 @@ __global__ void __launch_bounds__(K1E_THREADS, 2) k1e_fused(const K1Params p, lo
                 s.nwords = 0;
                 k1e_code(rowbase, sw4, part == 0, diff, mm0, mm1, prev, eob, sAc, sDc, s);
                 nbits = s.finish();
-                if (nbits > (uint32_t)K1E_PRIV * 32u) S.flag[b] = 1u;
+                if (nbits > (uint32_t)K1E_PRIV * 32u) G.flag[b] = 1u;
             }
-            S.off[e_local] = nbits;
-            k1e_bar(NE); /* B1: every entry is coded */
+            G.off[e_local] = nbits;
+            k1e_bar(grp, NE); /* B1: every entry is coded */
 
             /* exclusive scan in stream order, redundantly per warp: lane = MCU */
             uint32_t loff, total;
             if (RATIO == 0) {
-                const uint4 l4 = reinterpret_cast<const uint4 *>(S.off)[lane];
+                const uint4 l4 = reinterpret_cast<const uint4 *>(G.off)[lane];
                 const uint32_t mt = l4.x + l4.y + l4.z + l4.w;
                 uint32_t inc = mt;
 #pragma unroll
@@ -420,7 +435,7 @@ __global__ void __launch_bounds__(K1E_THREADS, 2) k1e_fused(const K1Params p, lo
             } else {
                 uint32_t v[6];
                 {
-                    const uint2 *o2 = reinterpret_cast<const uint2 *>(S.off) + 3 * (lane & 15);
+                    const uint2 *o2 = reinterpret_cast<const uint2 *>(G.off) + 3 * (lane & 15);
                     const uint2 x0 = o2[0], x1 = o2[1], x2 = o2[2];
                     const bool on = lane < 16;
                     v[0] = on ? x0.x : 0u;
@@ -454,31 +469,31 @@ __global__ void __launch_bounds__(K1E_THREADS, 2) k1e_fused(const K1Params p, lo
                 }
             }
             const uint32_t nwords = (total + 31u) >> 5;
-            const bool staged = (S.flag[b] == 0u) && nwords < (uint32_t)K1E_STAGE_WORDS; /* word [nwords] may receive an empty OR */
+            const bool staged = (G.flag[b] == 0u) && nwords < (uint32_t)K1E_STAGE_WORDS; /* word [nwords] may receive an empty OR */
             uint32_t *slot = e.tmp + chunk * e.slot_words;
             if (staged) {
                 if (te == 0) mbar_arrive(&S.coef_free[b]); /* the coefficient rows are dead */
                 if (active) {
                     const uint32_t sh = loff & 31u, nw = (nbits + 31u) >> 5;
-                    const unsigned a0 = (unsigned)__cvta_generic_to_shared(S.stage + (loff >> 5));
+                    const unsigned a0 = (unsigned)__cvta_generic_to_shared(G.stage + (loff >> 5));
                     for (uint32_t i = 0; i < nw; i++) {
                         const uint32_t v = priv[i];
                         asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a0 + 4u * i), "r"(v >> sh) : "memory");
                         if (sh) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a0 + 4u * i + 4u), "r"(v << (32u - sh)) : "memory");
                     }
                 }
-                k1e_bar(NE); /* B2: the chunk stream is complete */
+                k1e_bar(grp, NE); /* B2: the chunk stream is complete */
                 /* copy-out; the words holding the stream's last 32 bits belong to thread 0, which needs them whole */
                 const uint32_t wt = total > 32u ? (total - 32u) >> 5 : 0u;
                 for (uint32_t i = (uint32_t)te; i < wt; i += NE) {
-                    slot[i] = __byte_perm(S.stage[i], 0, 0x0123);
-                    S.stage[i] = 0u;
+                    slot[i] = __byte_perm(G.stage[i], 0, 0x0123);
+                    G.stage[i] = 0u;
                 }
                 if (te == 0) {
-                    e.cta_tail[chunk] = stream_tail32(S.stage, total, false);
+                    e.cta_tail[chunk] = stream_tail32(G.stage, total, false);
                     for (uint32_t i = wt; i < nwords; i++) {
-                        slot[i] = __byte_perm(S.stage[i], 0, 0x0123);
-                        S.stage[i] = 0u;
+                        slot[i] = __byte_perm(G.stage[i], 0, 0x0123);
+                        G.stage[i] = 0u;
                     }
                     e.cta_bits[chunk] = total;
                     atomicAdd(&e.super_bits[chunk >> EC_SUPER_SHIFT], total);
@@ -486,7 +501,7 @@ __global__ void __launch_bounds__(K1E_THREADS, 2) k1e_fused(const K1Params p, lo
             } else {
                 /* rare (a block longer than its private region, or a very long chunk): straight into the slot */
                 for (uint32_t i = (uint32_t)te; i < nwords; i += NE) slot[i] = 0u;
-                k1e_bar(NE);
+                k1e_bar(grp, NE);
                 if (active) {
                     PackSink<false> s;
                     s.acc = 0;
@@ -496,10 +511,10 @@ __global__ void __launch_bounds__(K1E_THREADS, 2) k1e_fused(const K1Params p, lo
                     k1e_code(rowbase, sw4, part == 0, diff, mm0, mm1, prev, eob, sAc, sDc, s);
                     s.finish();
                 }
-                k1e_bar(NE);
+                k1e_bar(grp, NE);
                 if (te == 0) {
                     mbar_arrive(&S.coef_free[b]);
-                    S.flag[b] = 0u;
+                    G.flag[b] = 0u;
                     e.cta_tail[chunk] = stream_tail32(slot, total, true);
                     e.cta_bits[chunk] = total;
                     atomicAdd(&e.super_bits[chunk >> EC_SUPER_SHIFT], total);
