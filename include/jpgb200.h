@@ -70,11 +70,11 @@ int jpgb200_sync(jpgb200_ctx *ctx);
  * byte-identical and slower, kept as a cross-check; K35 takes 4:4:4 and 4:2:2 only and disables the
  * batch overlap and the fused transform below. */
 int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on);
-/* Transform/entropy fusion: 1 (default) = K1E, one persistent kernel from pixels to chunk streams
+/* Transform/entropy fusion: 1 = K1E, one persistent kernel from pixels to chunk streams
  * (csrc/k1_fused.cuh; the chain dct -> quantise -> zig_zag -> dpcm -> huffman_encode of
- * src/jpg_encode.c:36-50 without the coefficients ever reaching HBM), followed by KF/KS;
- * 0 = K1 and KE as separate kernels with the int16 coefficients in HBM between them.  Identical
- * bytes.  K1E needs width % 16 == 0, 4:4:4 or 4:2:2 and the tables.h Huffman tables; other
+ * src/jpg_encode.c:36-50 without the coefficients ever reaching HBM: 3.3 B/pixel of DRAM traffic
+ * instead of 15), followed by KF/KS; 0 (default: measured faster) = K1 and KE as separate
+ * kernels with the int16 coefficients in HBM between them.  Identical bytes.  K1E needs width % 16 == 0, 4:4:4 or 4:2:2 and the tables.h Huffman tables; other
  * cases (4:2:0, per-image optimal tables, the parity taps, the MCU-row bands) take the separate kernels. */
 int jpgb200_set_fused_transform(jpgb200_ctx *ctx, int on);
 /* 1 = K1E also stores its coefficients (jpgb200_last_coefficients reads them): the parity tap of

@@ -439,10 +439,10 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
     ctx->q_cached = -1;
     ctx->legacy_entropy = true; /* measured faster than the fused K35 so far */
     ctx->k1_pc = true;          /* K1 default: the producer/consumer form (fastest measured) */
-    ctx->fused_k1e = true;      /* transform + chunk encode in one kernel (k1_fused.cuh) */
+    ctx->fused_k1e = false;     /* transform + chunk encode in one kernel (k1_fused.cuh): measured slower than K1 -> KE so far */
     {
-        const char *fz = getenv("JPGB200_FUSED"); /* "0": K1 and KE as separate kernels (A/B runs) */
-        if (fz && !strcmp(fz, "0")) ctx->fused_k1e = false;
+        const char *fz = getenv("JPGB200_FUSED"); /* "1": K1E instead of K1 and KE as separate kernels (A/B runs) */
+        if (fz && !strcmp(fz, "1")) ctx->fused_k1e = true;
         const char *e = getenv("JPGB200_ENTROPY"); /* "fused" | "staged": experiment switch for bench runs */
         if (e && !strcmp(e, "fused")) ctx->legacy_entropy = false;
         const char *k = getenv("JPGB200_K1"); /* "plain" | "tma" */

@@ -1,5 +1,5 @@
 """GPU parity tests of K1E (csrc/k1_fused.cuh): the transform and the chunk encode in one
-persistent kernel, the default encode path.  What the reference chains as
+persistent kernel (jpgb200_set_fused_transform).  What the reference chains as
 dct -> quantise -> zig_zag -> dpcm -> huffman_encode (src/jpg_encode.c:36-50) must come out
 
   * byte-identical to the separate kernels (K1 -> KE) and to the oracle's bit writer fed with the
@@ -58,7 +58,7 @@ def test_fused_equals_separate_kernels_and_oracle(enc, w, h, q, ratio, kind, see
         sep = enc.encode_planar(r, g, b, w, h, q, ratio)
         zz = enc.coefficients(r, g, b, w, h, q, ratio)
     finally:
-        enc.set_fused_transform(True)
+        enc.set_fused_transform(False)
         enc.set_fused_tap(False)
         enc.set_oob_bytes(np.zeros(24, np.uint8))
     assert (zz_f == zz).all(), "the fused kernel's coefficients differ from K1's"
@@ -83,7 +83,7 @@ def test_fused_standard_mode(enc, w, h, q, ratio, seed):
         enc.set_fused_transform(False)
         sep = enc.encode_planar(r, g, b, w, h, q, ratio)
     finally:
-        enc.set_fused_transform(True)
+        enc.set_fused_transform(False)
         enc.set_standard_mode(False)
     assert fused.shape == sep.shape and (fused == sep).all()
 
@@ -93,17 +93,18 @@ def test_fused_repeated_launches_and_geometry_changes(enc):
     one context never see a stale word."""
     shapes = [(512, 64, 0), (256, 256, 1), (1024, 128, 0), (512, 64, 0), (256, 256, 1)]
     want = {}
-    for i, (w, h, ratio) in enumerate(shapes * 3):
-        r, g, b = O.synth_planes(w, h, 300 + (i % len(shapes)), 0, (i % len(shapes)) & 1)
-        got = enc.encode_planar(r, g, b, w, h, 75, ratio)
-        key = (i % len(shapes))
-        if key not in want:
-            enc.set_fused_transform(False)
-            try:
+    try:
+        for i, (w, h, ratio) in enumerate(shapes * 3):
+            r, g, b = O.synth_planes(w, h, 300 + (i % len(shapes)), 0, (i % len(shapes)) & 1)
+            enc.set_fused_transform(True)
+            got = enc.encode_planar(r, g, b, w, h, 75, ratio)
+            key = (i % len(shapes))
+            if key not in want:
+                enc.set_fused_transform(False)
                 want[key] = enc.encode_planar(r, g, b, w, h, 75, ratio)
-            finally:
-                enc.set_fused_transform(True)
-        assert got.shape == want[key].shape and (got == want[key]).all(), i
+            assert got.shape == want[key].shape and (got == want[key]).all(), i
+    finally:
+        enc.set_fused_transform(False)
 
 
 @pytest.mark.parametrize("w,h,ratio,nf", [(512, 256, 0, 7), (768, 64, 1, 5), (1920, 1088, 0, 4)])
@@ -120,6 +121,7 @@ def test_fused_batch_device(enc, w, h, ratio, nf):
             enc.synth_device(d_pl + f * 3 * npx, w, h, 777, f, f & 1)
         enc.sync()
         res = {}
+        enc.set_fused_transform(True)
         for mode in ("on", "off", "on2"):
             enc.set_batch_overlap(mode != "off")
             enc.h2d(d_out, np.zeros(nf * cap, np.uint8))
@@ -136,7 +138,7 @@ def test_fused_batch_device(enc, w, h, ratio, nf):
                 assert int(lens[f]) == one.size, (mode, f)
                 assert (outs[f, :one.size] == one).all(), (mode, f)
     finally:
-        enc.set_fused_transform(True)
+        enc.set_fused_transform(False)
         enc.set_batch_overlap(True)
         enc.free(d_pl)
         enc.free(d_out)
