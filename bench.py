@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-worst-case", action="store_true", help="skip the extra noise-distribution measurement")
+    ap.add_argument("--no-extras", action="store_true", help="skip the strong-scaling, small-frame and partition legs")
     return ap.parse_args()
 
 
@@ -265,33 +266,43 @@ def run_b200(args):
         enc.synth_device(planes.data_ptr() + f * frame_bytes, W, H, SEED, rank * F + f, KIND)
     torch.cuda.synchronize()
 
-    def step():
-        enc.encode_batch_device(planes.data_ptr(), F, W, H, QUALITY, RATIO, out.data_ptr(), cap, lens.data_ptr())
+    def step(nf=F):
+        enc.encode_batch_device(planes.data_ptr(), nf, W, H, QUALITY, RATIO, out.data_ptr(), cap, lens.data_ptr())
 
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        if dist is not None:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def timed(fn, steps):
+        """device time of `steps` calls of fn on the bench stream, barrier + synchronize on both sides, max over ranks"""
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        barrier()
+        return max_over_ranks(e0.elapsed_time(e1))
+
     for _ in range(args.warmup):
         step()
     barrier()
     enc.reset_profile()
-    # CUDA events inside the timed region: around every 8th K1 launch only (the roofline kernel; an event
-    # record costs ~2.7 us of stream time: bracketing all four kernels of every frame cost 16 us per frame)
+    # CUDA events inside the timed region: around every 8th K1 launch and, in other frames, every 8th KE launch
+    # (an event record costs ~2.7 us of stream time: bracketing all four kernels of every frame cost 16 us per frame)
     enc.set_profiling(3)
     launches0 = enc.launch_count()
     sampler = ClockSampler(local_rank)
     sampler.start()
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    ev0.record(stream)
-    for _ in range(args.steps):
-        step()
-    ev1.record(stream)
-    barrier()
+    ms_total = timed(step, args.steps)
     clocks = sampler.stop()
-    ms_total = ev0.elapsed_time(ev1)
     launches = enc.launch_count() - launches0
     ktimes = enc.kernel_times()
     enc.set_profiling(0)
@@ -305,42 +316,71 @@ def run_b200(args):
     kbreak = enc.kernel_times()
     enc.set_profiling(0)
     enc.set_batch_overlap(os.environ.get("JPGB200_OVERLAP", "1") != "0")
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    if dist is not None:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
     value = world * F * NPX / (ms_per_step * 1e-3) / 1e6
     lens_host = lens.cpu().numpy()
     assert (lens_host > 623).all() and (lens_host <= cap).all(), "an encode failed (length word out of range)"
     bytes_per_px = float(lens_host.mean()) / NPX
 
-    # ---- roofline of the dominant kernel (K1) from the live event timings
+    # ---- rooflines from the live event timings: K1 (north_star's target kernel) and the chunk encode
     peak, peak_src = measured_peak()
-    fused = ktimes.get("k1e_fused", (0.0, 0))[1] > 0
-    k1_ms, k1_n = ktimes["k1e_fused"] if fused else ktimes["k1_transform"]
-    k1_avg_s = k1_ms * 1e-3 / max(k1_n, 1)
-    # algorithmic bytes of the head kernel: K1 reads 3 B/px and writes 6 B/px of int16 coefficients; the fused
-    # K1E reads 3 B/px and writes only the chunk streams (the compressed bytes)
-    alg_bytes = (3.0 + bytes_per_px) * NPX if fused else 9.0 * NPX
-    achieved = alg_bytes / k1_avg_s / 1e9
-    traffic = None
-    tp = os.path.join(ROOT, "profiles", "k1_traffic.json")
+    traffic_file = {}
+    tp = os.path.join(ROOT, "profiles", "kernel_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
+            traffic_file = json.load(open(tp))
         except Exception:
-            traffic = None
-    roofline = {"bound": "hbm", "kernel": "k1e_fused<0>" if fused else "k1_transform_pc<0>", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "frac_of_nominal_8000": achieved / 8000.0,
-                "traffic": None if fused else traffic, "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "avg_launch_us": k1_avg_s * 1e6,
-                "k1_launches_timed": k1_n, "k1_event_sampling": "every 8th K1 launch of the timed region",
-                "k1_share_of_step": k1_avg_s * 1e3 * F / ms_per_step,
-                "kernel_ms_per_step_untimed_pass": {k: v[0] for k, v in kbreak.items()}}
+            traffic_file = {}
+
+    def roof(kname, label, alg_bytes, what):
+        ms, n = ktimes.get(kname, (0.0, 0))
+        if n == 0:
+            return None
+        avg = ms * 1e-3 / n
+        tr = traffic_file.get(kname, {})
+        return {"bound": "hbm", "kernel": label, "achieved": alg_bytes / avg / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": alg_bytes / avg / 1e9 / peak, "frac_of_nominal_8000": alg_bytes / avg / 1e9 / 8000.0,
+                "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"), "peak_source": peak_src,
+                "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes": what, "avg_launch_us": avg * 1e6,
+                "launches_timed": n, "event_sampling": "every 8th launch of the timed region",
+                "share_of_step": avg * 1e3 * F / ms_per_step}
+
+    fused = ktimes.get("k1e_fused", (0.0, 0))[1] > 0
+    roofs = {}
+    if fused:
+        roofs["k1e_fused"] = roof("k1e_fused", "k1e_fused<0>", (3.0 + bytes_per_px) * NPX,
+                                  "3 B/px of planes in + the chunk streams out (the coefficients stay on chip)")
+    else:
+        roofs["k1_transform"] = roof("k1_transform", "k1_transform_pc<0>", 9.0 * NPX,
+                                     "9 B/px: 3 B/px of planes in + 6 B/px of int16 coefficients out (SURVEY.md 8(d))")
+        roofs["k_encode_chunks"] = roof("k_encode_chunks", "k_encode_chunks<0>", (6.0 + bytes_per_px) * NPX,
+                                        "6 B/px of int16 coefficients in + the chunk streams out")
+    roofs = {k: v for k, v in roofs.items() if v}
+    dominant = max(roofs, key=lambda k: roofs[k]["avg_launch_us"])
+    roofline = dict(roofs[dominant])
+    roofline["dominant_kernel"] = dominant
+    roofline["all_timed_kernels"] = roofs
+    roofline["kernel_ms_per_step_untimed_pass"] = {k: v[0] for k, v in kbreak.items()}
+    # the whole pipeline against the same peak: the least it has to move is the planes in and the stream out
+    t_frame = ms_per_step * 1e-3 / F
+    pipeline = {"algorithmic_bytes_per_frame": (3.0 + bytes_per_px) * NPX, "us_per_frame": t_frame * 1e6,
+                "achieved_gbs": (3.0 + bytes_per_px) * NPX / t_frame / 1e9, "frac_of_peak": (3.0 + bytes_per_px) * NPX / t_frame / 1e9 / peak,
+                "dram_bytes_per_frame": traffic_file.get("pipeline_dram_bytes_per_frame"),
+                "dram_bytes_per_pixel": (traffic_file.get("pipeline_dram_bytes_per_frame") or 0) / NPX or None,
+                "traffic_source": traffic_file.get("pipeline_source")}
+
+    # ---- BASELINE.json configs[3] as written: 256 frames in total, sharded over the ranks (strong scaling)
+    strong = None
+    if not args.no_extras:
+        total_frames = 256
+        sf = max(1, total_frames // world)
+        if sf <= F:
+            ms = timed(lambda: step(sf), 2) / 2
+            strong = {"scaling": "strong", "frames_total": sf * world, "frames_per_gpu": sf, "ms_per_step": ms,
+                      "value": sf * world * NPX / (ms * 1e-3) / 1e6, "unit": UNIT}
 
     # ---- the other distribution of SURVEY.md 8(d): iid uniform noise, the worst case for the entropy
-    # stage and the largest output; a short separate measurement, reported beside the headline
+    # stage and the largest output; a short separate measurement on every rank, reported beside the headline
     noise = None
     try:
         if args.no_worst_case:
@@ -356,16 +396,11 @@ def run_b200(args):
             enc.encode_batch_device(planes.data_ptr(), NF, W, H, QUALITY, RATIO, nout.data_ptr(), 3 * NPX, nlens.data_ptr())
 
         nstep()
-        torch.cuda.synchronize()
-        n0, n1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        n0.record(stream)
-        for _ in range(3):
-            nstep()
-        n1.record(stream)
-        torch.cuda.synchronize()
+        nms = timed(nstep, 3)
         nl = nlens.cpu().numpy()
-        noise = {"distribution": "noise (iid uniform u8)", "value": NF * 3 * NPX / (n0.elapsed_time(n1) * 1e-3) / 1e6, "unit": UNIT,
-                 "frames": NF, "steps": 3, "compressed_bytes_per_pixel": float(nl.mean()) / NPX, "n_gpus_measured": 1}
+        noise = {"distribution": "noise (iid uniform u8)", "value": world * NF * 3 * NPX / (nms * 1e-3) / 1e6, "unit": UNIT,
+                 "frames_per_gpu": NF, "steps": 3, "compressed_bytes_per_pixel": float(nl.mean()) / NPX, "n_gpus_measured": world,
+                 "us_per_frame": nms * 1e3 / (3 * NF), "ratio_to_natural_frame_time": nms * 1e3 / (3 * NF) / (t_frame * 1e6)}
         del nout
         for f in range(NF):  # restore the natural frames for the e2e leg
             enc.synth_device(planes.data_ptr() + f * frame_bytes, W, H, SEED, rank * F + f, KIND)
@@ -373,14 +408,23 @@ def run_b200(args):
     except Exception as exc:  # the headline must not depend on this extra
         noise = {"error": str(exc)}
 
+    # ---- BASELINE.json configs[1]: small frames (1920x1080 4:4:4 q75), where launches, not bytes, set the pace
+    small = None
+    if not args.no_extras:
+        try:
+            small = small_frame_leg(enc, torch, stream, timed, world)
+        except Exception as exc:
+            small = {"error": str(exc)}
+
     # ---- e2e: host buffers through the C ABI, copies inside the timed region
     e2e = None
     if not args.no_e2e:
         EF = args.e2e_frames
         ring = 4
+        wc = os.environ.get("JPGB200_WC", "0") == "1"
         pins, pouts = [], []
         for i in range(ring):
-            a, p = pkg.binding.pinned_empty(frame_bytes)
+            a, p = pkg.binding.pinned_empty(frame_bytes, write_combined=wc)
             torch.cuda.synchronize()
             src = planes[i].contiguous().view(-1)
             a[:] = src.cpu().numpy()
@@ -395,24 +439,40 @@ def run_b200(args):
         def estep():
             return enc.encode_batch_host(in_ptrs, W, H, QUALITY, RATIO, out_ptrs, cap)
 
+        def host_timed(fn, steps):
+            barrier()
+            t0 = time.perf_counter()
+            r = None
+            for _ in range(steps):
+                r = fn()
+            torch.cuda.synchronize()
+            return max_over_ranks(time.perf_counter() - t0), r
+
         for _ in range(max(1, min(args.warmup, 3))):
             el = estep()
-        barrier()
         l0 = enc.launch_count()
-        t0 = time.perf_counter()
-        for _ in range(args.steps):
-            el = estep()
-        torch.cuda.synchronize()
-        dt = time.perf_counter() - t0
-        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
-        if dist is not None:
-            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
-        dt = float(tt.item())
+        dt, el = host_timed(estep, args.steps)
         launches_e2e = enc.launch_count() - l0
-        e2e = {"value": world * EF * NPX * args.steps / dt / 1e6, "unit": UNIT,
+        out_bytes = int(sum(el) // len(el))
+        # the ceiling: the same copies (one cudaMemcpyAsync per frame and direction, same streams) with no kernel
+        enc.copy_probe(in_ptrs, frame_bytes, out_ptrs, out_bytes)
+        dtc, _ = host_timed(lambda: enc.copy_probe(in_ptrs, frame_bytes, out_ptrs, out_bytes), args.steps)
+        gpu_node, nodes = pkg.binding.device_numa(local_rank)
+        e2e_value = world * EF * NPX * args.steps / dt / 1e6
+        ceiling = world * EF * NPX * args.steps / dtc / 1e6
+        e2e = {"value": e2e_value, "unit": UNIT,
                "h2d_bytes_per_step": EF * frame_bytes, "d2h_bytes_per_step": int(sum(el)) + 8 * EF,
                "frames_per_step": EF, "ms_per_step": 1e3 * dt / args.steps, "gpu_launches": launches_e2e,
-               "timer": "host perf_counter around jpgb200_encode_batch_host, stream-synchronised, max over ranks"}
+               "timer": "host perf_counter around jpgb200_encode_batch_host, stream-synchronised, max over ranks",
+               "pcie_ceiling": ceiling, "frac_of_ceiling": e2e_value / ceiling,
+               "pcie_ceiling_what": "jpgb200_copy_probe: the same pinned buffers, sizes and streams, one cudaMemcpyAsync per frame "
+                                    "and direction, no kernels, timed the same way at this N",
+               "h2d_gbs_per_gpu": EF * frame_bytes * args.steps / dt / 1e9,
+               "h2d_gbs_per_gpu_ceiling": EF * frame_bytes * args.steps / dtc / 1e9,
+               "pinned": "write-combined" if wc else "cudaHostAlloc default",
+               "numa": {"visible_nodes": nodes, "gpu_node": gpu_node, "cpus": len(os.sched_getaffinity(0)),
+                        "placement": "single NUMA node visible: nothing to place" if nodes <= 1 else
+                                     "pinned buffers first-touched by this rank's thread"}}
         enc.set_stream(stream.cuda_stream)
         for _, p in pins + pouts:
             pkg.binding.pinned_free(p)
@@ -421,6 +481,14 @@ def run_b200(args):
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         tmp = tempfile.mkdtemp(prefix="jpgb200_cpu_")
         cpu = cpu_baseline_one_core(tmp)
+
+    # ---- BASELINE.json configs[4]: one 32768x32768 image partitioned by MCU rows over the ranks
+    config5 = None
+    if world > 1 and not args.no_extras:
+        try:
+            config5 = partition_leg(pkg, enc, torch, dist, rank, world, local_rank)
+        except Exception as exc:
+            config5 = {"error": str(exc)}
 
     if rank == 0:
         line = {
@@ -433,13 +501,46 @@ def run_b200(args):
                        "compressed_bytes_per_pixel": bytes_per_px,
                        "l2_policy": "inputs larger than L2: %d distinct frames = %.1f GB per step" % (F, F * frame_bytes / 1e9),
                        "sharding": "frames independent, one image stream per GPU, no collective",
-                       "worst_case_distribution": noise},
-            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+                       "entropy_path": "K1E fused transform + chunk encode" if fused else "K1 -> KE (separate kernels)",
+                       "strong_scaling": strong, "worst_case_distribution": noise, "small_frame": small, "config5": config5},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "pipeline": pipeline,
+            "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
+
+
+def small_frame_leg(enc, torch, stream, timed, world):
+    """configs[1]: a batch of 1920x1080 4:4:4 q75 frames, device resident"""
+    w, h, nf = 1920, 1080, 64
+    npx = w * h
+    cap = npx
+    pl = torch.empty((nf, 3, h, w), dtype=torch.uint8, device="cuda")
+    out = torch.empty((nf, cap), dtype=torch.uint8, device="cuda")
+    lens = torch.zeros((nf,), dtype=torch.int64, device="cuda")
+    for f in range(nf):
+        enc.synth_device(pl.data_ptr() + f * 3 * npx, w, h, 1001, f, KIND)
+    torch.cuda.synchronize()
+
+    def sstep():
+        enc.encode_batch_device(pl.data_ptr(), nf, w, h, QUALITY, 0, out.data_ptr(), cap, lens.data_ptr())
+
+    sstep()
+    sstep()
+    l0 = enc.launch_count()
+    ms = timed(sstep, 5) / 5
+    launches = (enc.launch_count() - l0) // 5
+    ll = lens.cpu().numpy()
+    assert (ll > 623).all() and (ll <= cap).all()
+    return {"workload": "batch of %d synthetic 1920x1080 RGB frames per GPU, 4:4:4, q75 (BASELINE.json configs[1])" % nf,
+            "value": world * nf * npx / (ms * 1e-3) / 1e6, "unit": UNIT, "us_per_frame": ms * 1e3 / nf,
+            "launches_per_batch": launches, "compressed_bytes_per_pixel": float(ll.mean()) / npx}
+
+
+def partition_leg(pkg, enc, torch, dist, rank, world, local_rank):
+    raise RuntimeError("not built yet")
 
 
 def main():

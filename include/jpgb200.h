@@ -77,6 +77,10 @@ int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on);
  * kernels with the int16 coefficients in HBM between them.  Identical bytes.  K1E needs width % 16 == 0, 4:4:4 or 4:2:2 and the tables.h Huffman tables; other
  * cases (4:2:0, per-image optimal tables, the parity taps, the MCU-row bands) take the separate kernels. */
 int jpgb200_set_fused_transform(jpgb200_ctx *ctx, int on);
+/* jpgb200_encode_batch_device on frames of up to 4096x2304: 1 (default) = groups of frames share
+ * each kernel launch (K1's tile index and the entropy kernels' blockIdx.y run over the frames of a
+ * group of about one 8K frame's worth of pixels); 0 = four launches per frame.  Identical bytes. */
+int jpgb200_set_frame_groups(jpgb200_ctx *ctx, int on);
 /* 1 = K1E also stores its coefficients (jpgb200_last_coefficients reads them): the parity tap of
  * the fused kernel.  Default 0. */
 int jpgb200_set_fused_tap(jpgb200_ctx *ctx, int on);
@@ -222,6 +226,14 @@ int jpgb200_device_count(void);
 int jpgb200_malloc(jpgb200_ctx *ctx, void **dptr, size_t bytes);
 int jpgb200_free(jpgb200_ctx *ctx, void *dptr);
 int jpgb200_host_alloc(void **hptr, size_t bytes); /* pinned */
+int jpgb200_host_alloc_ex(void **hptr, size_t bytes, int flags); /* flags: 1 = write-combined (host-write-only buffers) */
+/* NUMA node of the device's PCIe function (-1 when the platform does not report one, e.g. a VM) and the
+ * number of NUMA nodes visible to this process: placement hints for the caller's pinned buffers. */
+int jpgb200_device_numa(int device, int *gpu_node, int *visible_nodes);
+/* The host<->device copies of jpgb200_encode_batch_host without its kernels (one cudaMemcpyAsync per frame
+ * and direction, both directions at once): the PCIe ceiling of an end-to-end encode on this host. */
+int jpgb200_copy_probe(jpgb200_ctx *ctx, const uint8_t *const *frames, int n_frames, size_t in_bytes, uint8_t *const *outs,
+                       size_t out_bytes);
 int jpgb200_host_free(void *hptr);
 int jpgb200_memcpy_h2d(jpgb200_ctx *ctx, void *dptr, const void *hptr, size_t bytes);
 int jpgb200_memcpy_d2h(jpgb200_ctx *ctx, void *hptr, const void *dptr, size_t bytes);
@@ -233,8 +245,8 @@ int jpgb200_synth_device(jpgb200_ctx *ctx, uint8_t *d_planes, int width, int hei
 /* With profiling on (1), every kernel launch of the encode path is bracketed by CUDA events on
  * the launching stream; with 2 only K1's launches are (two event records per frame instead of
  * eight: for a timed region that wants the roofline kernel's live duration and little else), with
- * 3 only every eighth K1 launch (jpgb200_kernel_times then reports the sampled launches: their
- * count and their summed duration); sums are read back with jpgb200_kernel_times (ms and launch counts
+ * 3 only every eighth K1 launch and, in other frames, every eighth KE launch
+ * (jpgb200_kernel_times then reports the sampled launches: their count and their summed duration); sums are read back with jpgb200_kernel_times (ms and launch counts
  * per kernel, JPGB200_NUM_KERNELS entries) and cleared by jpgb200_reset_profile. */
 int jpgb200_set_profiling(jpgb200_ctx *ctx, int on);
 int jpgb200_kernel_times(jpgb200_ctx *ctx, double *ms, long long *launches);

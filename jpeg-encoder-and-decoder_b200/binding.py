@@ -38,6 +38,7 @@ _SIGS = {
     "jpgb200_set_batch_overlap": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_fused_transform": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_fused_tap": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_set_frame_groups": (C.c_int, [_vp, C.c_int]),
     "jpgb200_last_coefficients": (C.c_int, [_vp, _vp]),
     "jpgb200_huffman_specs": (C.c_int, [_vp, _vp, _vp, _vp]),
     "jpgb200_encode_planar": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -69,6 +70,9 @@ _SIGS = {
     "jpgb200_malloc": (C.c_int, [_vp, C.POINTER(_vp), C.c_size_t]),
     "jpgb200_free": (C.c_int, [_vp, _vp]),
     "jpgb200_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
+    "jpgb200_host_alloc_ex": (C.c_int, [C.POINTER(_vp), C.c_size_t, C.c_int]),
+    "jpgb200_device_numa": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
+    "jpgb200_copy_probe": (C.c_int, [_vp, _vp, C.c_int, C.c_size_t, _vp, C.c_size_t]),
     "jpgb200_host_free": (C.c_int, [_vp]),
     "jpgb200_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "jpgb200_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
@@ -216,6 +220,10 @@ class Encoder:
         """K1E (transform + chunk encode in one kernel, the default) on/off"""
         self._ck(lib().jpgb200_set_fused_transform(self._h, 1 if on else 0))
 
+    def set_frame_groups(self, on):
+        """multi-frame launches for batches of small frames (default on)"""
+        self._ck(lib().jpgb200_set_frame_groups(self._h, 1 if on else 0))
+
     def set_fused_tap(self, on):
         """K1E additionally writes its coefficients to HBM (read them back with last_coefficients)"""
         self._ck(lib().jpgb200_set_fused_tap(self._h, 1 if on else 0))
@@ -244,6 +252,13 @@ class Encoder:
         lens = (C.c_size_t * n)()
         self._ck(lib().jpgb200_encode_batch_host(self._h, fa, n, w, h, quality, ratio, oa, cap, lens))
         return [int(x) for x in lens]
+
+    def copy_probe(self, frame_ptrs, in_bytes, out_ptrs, out_bytes):
+        """the copies of encode_batch_host without its kernels (the PCIe ceiling of an end-to-end encode)"""
+        n = len(frame_ptrs)
+        fa = (_vp * n)(*frame_ptrs)
+        oa = (_vp * n)(*out_ptrs)
+        self._ck(lib().jpgb200_copy_probe(self._h, fa, n, in_bytes, oa, out_bytes))
 
     # ---- MCU-row bands (one band per rank; see mgpu.py)
     def band_transform(self, d_r, d_g, d_b, w, band_h, has_halo, quality, ratio):
@@ -389,10 +404,19 @@ class Encoder:
         return int(lib().jpgb200_launch_count(self._h))
 
 
-def pinned_empty(nbytes):
-    """numpy view of pinned host memory (jpgb200_host_alloc); keep the returned owner alive."""
+def device_numa(device=0):
+    """(NUMA node of the GPU's PCIe function or -1, NUMA nodes visible to this process)"""
+    a, b = C.c_int(-1), C.c_int(0)
+    rc = lib().jpgb200_device_numa(device, C.byref(a), C.byref(b))
+    if rc:
+        raise Jpgb200Error(rc)
+    return int(a.value), int(b.value)
+
+
+def pinned_empty(nbytes, write_combined=False):
+    """numpy view of pinned host memory (jpgb200_host_alloc_ex); keep the returned owner alive."""
     p = _vp()
-    rc = lib().jpgb200_host_alloc(C.byref(p), nbytes)
+    rc = lib().jpgb200_host_alloc_ex(C.byref(p), nbytes, 1 if write_combined else 0)
     if rc:
         raise Jpgb200Error(rc)
     buf = (C.c_uint8 * nbytes).from_address(p.value)

@@ -582,6 +582,9 @@ struct KeParams {
     uint32_t *cta_tail;    /* [n_chunks] the chunk stream's last 32 bits: the next chunk's leading bits (KF, KS) */
     uint32_t *super_bits;  /* [n_chunks / 64 + 1], cleared by K1 */
     uint32_t *local_off;   /* optional parity tap: [n_mcu*BPM] offset of every block in its chunk */
+    /* batches of small frames in one launch: blockIdx.y = frame, every array advances by these strides */
+    long long zz_fstride, tmp_fstride; /* int16 elements, words */
+    int cta_fstride, super_fstride;    /* elements */
 };
 
 /* KE's threads: "entries" in component-major order -- two per luma block (part 0, part 1), one per
@@ -676,8 +679,17 @@ __device__ __forceinline__ void ke_code(const uint4 (*sC)[EC_ROW_CHUNKS], const 
 }
 
 template <int RATIO>
-__global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KeParams q, const HuffPack *huff)
+__global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KeParams q0, const HuffPack *huff)
 {
+    KeParams q = q0;
+    {
+        const long long f = blockIdx.y;
+        q.zz += f * q.zz_fstride;
+        q.tmp += f * q.tmp_fstride;
+        q.cta_bits += f * q.cta_fstride;
+        q.cta_tail += f * q.cta_fstride;
+        q.super_bits += f * q.super_fstride;
+    }
     constexpr int BPM = EcCfg<RATIO>::BPM, NT = KeCfg<RATIO>::NT;
     typedef KeCfg<RATIO> L;
     extern __shared__ __align__(16) unsigned char ke_smem[];

@@ -20,6 +20,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <string>
 #include <vector>
 
 #include "../../include/jpgb200.h"
@@ -70,7 +71,7 @@ struct jpgb200_ctx {
     size_t local_cap;
     uint32_t *d_cta_bits;
     uint32_t *d_super;   /* [n_super_bits | n_super_ff] two-level sums, cleared by K1 */
-    size_t n_super_bits, n_super_ff;
+    size_t n_super_bits, n_super_ff, super_frames;
     unsigned long long *d_cta_base;
     size_t cta_cap;
     uint32_t *d_cta_ff;   /* [n_chunks] 0xFF bytes owned by every chunk (KF) */
@@ -117,10 +118,11 @@ struct jpgb200_ctx {
     struct EntWs {
         uint32_t *tmp, *cta_bits, *cta_ff, *cta_tail, *super;
         unsigned long long *cta_base;
-        size_t tmp_cap, cta_cap, n_super_bits, n_super_ff;
+        size_t tmp_cap, cta_cap, n_super_bits, n_super_ff, super_frames;
     } alt;
     cudaStream_t tail_stream;
     cudaEvent_t ev_ke, ev_ks[2];
+    cudaEvent_t ev_in[2], ev_done[2], ev_out[2]; /* jpgb200_encode_batch_host: per plane/output slot */
     bool overlap_on;     /* jpgb200_encode_batch_device overlaps tails (JPGB200_OVERLAP=0 turns it off) */
     bool overlap_now;    /* inside such a batch */
     bool in_batch;       /* inside a batch call: the per-block offset tap is not written */
@@ -136,6 +138,7 @@ struct jpgb200_ctx {
     bool legacy_entropy; /* staged KE/KF/KS pipeline (default) instead of the single-launch K35 */
     bool fused_k1e;      /* K1E: transform + chunk encode in one kernel, coefficients stay on chip (default) */
     int k1e_per_sm[4];   /* resident CTAs per SM of k1e_fused<RATIO, STD>, 0 = not yet queried */
+    bool group_small;    /* jpgb200_encode_batch_device: multi-frame launches for small frames (default on) */
     bool k1e_tap;        /* K1E also writes the coefficients to HBM (jpgb200_set_fused_tap) */
     unsigned long long *d_dc_pub; /* K1E: last DC per tile and component, {epoch, DC} words */
     size_t dc_pub_cap;
@@ -147,7 +150,7 @@ struct jpgb200_ctx {
     /* profiling */
     int profiling; /* 0 off, 1 every kernel, 2 only K1 (the roofline kernel: fewer event records in a timed region),
                       3 only every 8th K1 launch (an event record costs ~2.7 us of stream time) */
-    long long k1_seen;
+    long long k1_seen, ke_seen;
     std::vector<EvPair> pending;
     std::vector<cudaEvent_t> free_events;
     double ms[JPGB200_NUM_KERNELS];
@@ -439,6 +442,7 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
     ctx->q_cached = -1;
     ctx->legacy_entropy = true; /* measured faster than the fused K35 so far */
     ctx->k1_pc = true;          /* K1 default: the producer/consumer form (fastest measured) */
+    ctx->group_small = true;
     ctx->fused_k1e = false;     /* transform + chunk encode in one kernel (k1_fused.cuh): measured slower than K1 -> KE so far */
     {
         const char *fz = getenv("JPGB200_FUSED"); /* "1": K1E instead of K1 and KE as separate kernels (A/B runs) */
@@ -481,6 +485,11 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         CK(cudaEventCreateWithFlags(&ctx->ev_ke, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_ks[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_ks[1], cudaEventDisableTiming));
+        for (int sl = 0; sl < 2; sl++) {
+            CK(cudaEventCreateWithFlags(&ctx->ev_in[sl], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_done[sl], cudaEventDisableTiming));
+            CK(cudaEventCreateWithFlags(&ctx->ev_out[sl], cudaEventDisableTiming));
+        }
         ctx->stream = ctx->own_stream;
         CK(cudaMalloc(&ctx->d_huff, sizeof(HuffDev)));
         CK(cudaMemcpy(ctx->d_huff, &hh, sizeof hh, cudaMemcpyHostToDevice));
@@ -531,6 +540,11 @@ extern "C" void jpgb200_destroy(jpgb200_ctx *ctx)
     cudaEventDestroy(ctx->ev_ke);
     cudaEventDestroy(ctx->ev_ks[0]);
     cudaEventDestroy(ctx->ev_ks[1]);
+    for (int sl = 0; sl < 2; sl++) {
+        cudaEventDestroy(ctx->ev_in[sl]);
+        cudaEventDestroy(ctx->ev_done[sl]);
+        cudaEventDestroy(ctx->ev_out[sl]);
+    }
     {
         void *alts[] = {ctx->alt.tmp, ctx->alt.cta_bits, ctx->alt.cta_ff, ctx->alt.cta_tail, ctx->alt.super, ctx->alt.cta_base};
         for (void *q : alts)
@@ -578,6 +592,13 @@ extern "C" int jpgb200_set_fused_transform(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;
     ctx->fused_k1e = on != 0;
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_set_frame_groups(jpgb200_ctx *ctx, int on)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    ctx->group_small = on != 0;
     return JPGB200_OK;
 }
 
@@ -656,8 +677,9 @@ struct LaunchScope {
     bool on;
     LaunchScope(jpgb200_ctx *c, int kk) : ctx(c), k(kk)
     {
-        const bool head = (kk == KI_K1 || kk == KI_K1E); /* the frame's first and largest kernel */
-        on = ctx->profiling == 1 || (ctx->profiling == 2 && head) || (ctx->profiling == 3 && head && (ctx->k1_seen++ & 7) == 0);
+        const bool head = (kk == KI_K1 || kk == KI_K1E); /* the transform kernel */
+        on = ctx->profiling == 1 || (ctx->profiling == 2 && head) || (ctx->profiling == 3 && head && (ctx->k1_seen++ & 7) == 0) ||
+             (ctx->profiling == 3 && kk == KI_KE && (ctx->ke_seen++ & 7) == 4); /* the chunk encode: in other frames than K1 */
         if (on) {
             a = get_event(ctx);
             b = get_event(ctx);
@@ -766,12 +788,14 @@ static long long tile_slot_words(int ratio)
     return ((blocks * 1658 + 31) / 32 + 4) & ~3ll;
 }
 
-/* w, h > 0: also size the chunk workspaces for K1E's tile geometry */
-static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_zz, int w = 0, int h = 0, int ratio = 0)
+/* w, h > 0: also size the chunk workspaces for K1E's tile geometry; nframes > 1: room for that many frames in
+ * every per-frame array (multi-frame launches of small frames) */
+static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes, int w = 0, int h = 0, int ratio = 0)
 {
     const long long nb = n[0] + n[1] + n[2];
+    const size_t G = (size_t)(nframes < 1 ? 1 : nframes);
     int rc;
-    if ((rc = grow(ctx, &ctx->d_zz, &ctx->zz_cap, (size_t)nb * 128 * (size_t)nframes_zz))) return rc;
+    if ((rc = grow(ctx, &ctx->d_zz, &ctx->zz_cap, (size_t)nb * 128 * G))) return rc;
     if ((rc = grow(ctx, &ctx->d_local_off, &ctx->local_cap, (size_t)nb * 4))) return rc;
     size_t nc = (size_t)n_chunks(n);
     size_t tmp_words = nc * (size_t)slot_words(n);
@@ -783,7 +807,8 @@ static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_
         if ((rc = grow(ctx, &ctx->d_dc_pub, &ctx->dc_pub_cap, nct * 3 * 8))) return rc;
         if (ctx->d_dc_pub != before) CK(cudaMemsetAsync(ctx->d_dc_pub, 0, ctx->dc_pub_cap, ctx->stream)); /* epoch 0 is never used */
     }
-    if (ctx->cta_cap < nc * 8 || !ctx->d_cta_bits) {
+    const size_t nct_all = nc * G; /* chunk entries over all frames */
+    if (ctx->cta_cap < nct_all * 8 || !ctx->d_cta_bits) {
         size_t c1 = 0, c2 = 0;
         if (ctx->d_cta_bits) {
             CK(cudaStreamSynchronize(ctx->stream));
@@ -792,16 +817,16 @@ static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_
             ctx->d_cta_bits = NULL;
             ctx->d_cta_base = NULL;
         }
-        if ((rc = grow(ctx, &ctx->d_cta_bits, &c1, nc * 4))) return rc;
-        if ((rc = grow(ctx, &ctx->d_cta_base, &c2, nc * 8))) return rc;
+        if ((rc = grow(ctx, &ctx->d_cta_bits, &c1, nct_all * 4))) return rc;
+        if ((rc = grow(ctx, &ctx->d_cta_base, &c2, nct_all * 8))) return rc;
         if (ctx->d_cta_ff) CK(cudaFree(ctx->d_cta_ff));
         if (ctx->d_cta_tail) CK(cudaFree(ctx->d_cta_tail));
         ctx->d_cta_ff = NULL;
         ctx->d_cta_tail = NULL;
         size_t c3 = 0, c4 = 0;
-        if ((rc = grow(ctx, &ctx->d_cta_ff, &c3, nc * 4))) return rc;
-        if ((rc = grow(ctx, &ctx->d_cta_tail, &c4, nc * 4))) return rc;
-        ctx->cta_cap = nc * 8;
+        if ((rc = grow(ctx, &ctx->d_cta_ff, &c3, nct_all * 4))) return rc;
+        if ((rc = grow(ctx, &ctx->d_cta_tail, &c4, nct_all * 4))) return rc;
+        ctx->cta_cap = nct_all * 8;
     }
     if (ctx->chain_cap < nc || !ctx->d_bit_state) {
         size_t c1 = 0, c2 = 0;
@@ -818,20 +843,22 @@ static int ensure_workspace(jpgb200_ctx *ctx, const long long n[3], int nframes_
         CK(cudaMemsetAsync(ctx->d_ff_state, 0, c2, ctx->stream));
         ctx->chain_cap = c1 / 8;
     }
-    if ((rc = grow(ctx, &ctx->d_tmp, &ctx->tmp_cap, tmp_words * 4))) return rc;
+    if ((rc = grow(ctx, &ctx->d_tmp, &ctx->tmp_cap, tmp_words * G * 4))) return rc;
     {
+        /* two-level sums: [n_super_bits | n_super_ff] per frame, frames back to back */
         const size_t nsb = nc / 64 + 2, nsf = nc / 64 + 2;
-        if (!ctx->d_super || ctx->n_super_bits < nsb || ctx->n_super_ff < nsf) {
+        if (!ctx->d_super || ctx->n_super_bits < nsb || ctx->n_super_ff < nsf || ctx->super_frames < G) {
             if (ctx->d_super) {
                 CK(cudaStreamSynchronize(ctx->stream));
                 CK(cudaFree(ctx->d_super));
                 ctx->d_super = NULL;
             }
             size_t c3 = 0;
-            if ((rc = grow(ctx, &ctx->d_super, &c3, (nsb + nsf) * 4))) return rc;
+            if ((rc = grow(ctx, &ctx->d_super, &c3, (nsb + nsf) * G * 4))) return rc;
             CK(cudaMemsetAsync(ctx->d_super, 0, c3, ctx->stream));
             ctx->n_super_bits = nsb;
             ctx->n_super_ff = nsf;
+            ctx->super_frames = G;
         }
     }
     return JPGB200_OK;
@@ -1170,6 +1197,8 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     e.cta_tail = ctx->d_cta_tail;
     e.super_bits = ctx->d_super;
     e.local_off = ctx->overlap_now || ctx->in_batch ? NULL : ctx->d_local_off; /* parity tap: not inside batches */
+    e.zz_fstride = e.tmp_fstride = 0;
+    e.cta_fstride = e.super_fstride = 0;
     const unsigned nc = (unsigned)n_chunks(n);
     ctx->geo_chunks = n_chunks(n);
     ctx->geo_slot_words = slot_words(n);
@@ -1252,6 +1281,8 @@ static int launch_tail(jpgb200_ctx *ctx, const long long n[3], unsigned bit_phas
     q.len_out = len_out;
     q.write_eoi = write_eoi;
     q.st = ctx->d_state;
+    q.tmp_fstride = q.out_fstride = 0;
+    q.cta_fstride = q.super_fstride = 0;
     if (ctx->overlap_now) { /* deferred: it will run beside the next frame's KE (run_pending_tail) */
         ctx->pending_q = q;
         ctx->pending_parity = ctx->ws_parity;
@@ -1265,7 +1296,8 @@ static int launch_tail(jpgb200_ctx *ctx, const long long n[3], unsigned bit_phas
 static void swap_entropy_ws(jpgb200_ctx *ctx)
 {
     jpgb200_ctx::EntWs cur = {ctx->d_tmp,      ctx->d_cta_bits, ctx->d_cta_ff,     ctx->d_cta_tail,   ctx->d_super,
-                              ctx->d_cta_base, ctx->tmp_cap,    ctx->cta_cap,      ctx->n_super_bits, ctx->n_super_ff};
+                              ctx->d_cta_base, ctx->tmp_cap,    ctx->cta_cap,      ctx->n_super_bits, ctx->n_super_ff,
+                              ctx->super_frames};
     ctx->d_tmp = ctx->alt.tmp;
     ctx->d_cta_bits = ctx->alt.cta_bits;
     ctx->d_cta_ff = ctx->alt.cta_ff;
@@ -1276,6 +1308,7 @@ static void swap_entropy_ws(jpgb200_ctx *ctx)
     ctx->cta_cap = ctx->alt.cta_cap;
     ctx->n_super_bits = ctx->alt.n_super_bits;
     ctx->n_super_ff = ctx->alt.n_super_ff;
+    ctx->super_frames = ctx->alt.super_frames;
     ctx->alt = cur;
     ctx->ws_parity ^= 1;
 }
@@ -1399,6 +1432,117 @@ static int encode_core(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g,
     return launch_bits(ctx, ctx->d_zz, ratio, n);
 }
 
+/* A group of G small frames in four launches (K1, KE, KF, KS over all of them: blockIdx.y = frame for the
+ * entropy kernels, K1's tile index runs over the frames): what a 1080p frame needs is a sixteenth of an 8K
+ * frame's work, and four launches per frame leave the GPU waiting for the next launch most of the time. */
+static int encode_group(jpgb200_ctx *ctx, const uint8_t *d_planes, int G, int w, int h, int quality, int ratio, uint8_t *d_out,
+                        size_t out_stride, unsigned long long *d_lens)
+{
+    long long n[3];
+    int rc = validate(w, h, quality, ratio, n);
+    if (rc) return rc;
+    if ((rc = ensure_workspace(ctx, n, G))) return rc;
+    if ((rc = ensure_tables(ctx, w, h, quality, ratio))) return rc;
+    ctx->w = w;
+    ctx->h = h;
+    ctx->q = quality;
+    ctx->ratio = ratio;
+    memcpy(ctx->n, n, sizeof n);
+    const size_t npx = (size_t)w * h;
+    const long long nb = n[0] + n[1] + n[2], nc = n_chunks(n), sw = slot_words(n);
+    const int S = (int)(ctx->n_super_bits + ctx->n_super_ff);
+    /* K1 over all frames; it also clears every frame's two-level sums */
+    const size_t keep_b = ctx->n_super_bits, keep_f = ctx->n_super_ff;
+    ctx->n_super_ff = (size_t)S * (size_t)G - keep_b; /* launch_k1 clears n_super_bits + n_super_ff words */
+    rc = launch_k1(ctx, d_planes, d_planes + npx, d_planes + 2 * npx, w, h, ratio, n, G, (long long)(3 * npx), ctx->d_zz, nb * 64, 0);
+    ctx->n_super_ff = keep_f;
+    if (rc) return rc;
+    ctx->geo_chunks = nc;
+    ctx->geo_slot_words = sw;
+    KeParams e;
+    e.zz = ctx->d_zz;
+    e.coff1 = n[0];
+    e.coff2 = n[0] + n[1];
+    e.n_mcu = n[1];
+    e.dc_pred[0] = e.dc_pred[1] = e.dc_pred[2] = 0;
+    e.tmp = ctx->d_tmp;
+    e.slot_words = sw;
+    e.cta_bits = ctx->d_cta_bits;
+    e.cta_tail = ctx->d_cta_tail;
+    e.super_bits = ctx->d_super;
+    e.local_off = NULL;
+    e.zz_fstride = nb * 64;
+    e.tmp_fstride = nc * sw;
+    e.cta_fstride = (int)nc;
+    e.super_fstride = S;
+    if (!ctx->ke_attr_set) {
+        CK(cudaFuncSetAttribute(k_encode_chunks<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<0>::BYTES));
+        CK(cudaFuncSetAttribute(k_encode_chunks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<1>::BYTES));
+        CK(cudaFuncSetAttribute(k_encode_chunks<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<2>::BYTES));
+        ctx->ke_attr_set = true;
+    }
+    {
+        const dim3 grid((unsigned)nc, (unsigned)G);
+        LaunchScope ls(ctx, KI_KE);
+        if (ratio == 0)
+            k_encode_chunks<0><<<grid, KeCfg<0>::NT, KeSmem<0>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
+        else if (ratio == 1)
+            k_encode_chunks<1><<<grid, KeCfg<1>::NT, KeSmem<1>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
+        else
+            k_encode_chunks<2><<<grid, KeCfg<2>::NT, KeSmem<2>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
+    }
+    CK(cudaGetLastError());
+    TailParams q;
+    q.tmp = ctx->d_tmp;
+    q.slot_words = sw;
+    q.n_chunks = nc;
+    q.cta_bits = ctx->d_cta_bits;
+    q.super_bits = ctx->d_super;
+    q.cta_ff = ctx->d_cta_ff;
+    q.cta_tail = ctx->d_cta_tail;
+    q.cta_base = ctx->d_cta_base;
+    q.super_ff = ctx->d_super + ctx->n_super_bits;
+    q.bit_phase = 0u;
+    q.carry = 0u;
+    q.is_last_band = 1;
+    q.header = ctx->d_header;
+    q.header_len = ctx->hdr_len;
+    q.out = d_out;
+    q.cap = (unsigned long long)out_stride;
+    q.len_out = d_lens;
+    q.write_eoi = 1;
+    q.st = NULL;
+    q.tmp_fstride = nc * sw;
+    q.out_fstride = (long long)out_stride;
+    q.cta_fstride = (int)nc;
+    q.super_fstride = S;
+    const dim3 tgrid((unsigned)((nc + TAIL_WARPS - 1) / TAIL_WARPS), (unsigned)G);
+    {
+        LaunchScope ls(ctx, KI_KF);
+        k_count_ff<<<tgrid, TAIL_THREADS, 0, ctx->stream>>>(q);
+    }
+    CK(cudaGetLastError());
+    {
+        LaunchScope ls(ctx, KI_KS);
+        k_scatter<<<tgrid, TAIL_THREADS, 0, ctx->stream>>>(q);
+    }
+    CK(cudaGetLastError());
+    ctx->have_bits = false;
+    return JPGB200_OK;
+}
+
+/* frames per multi-frame launch group: about one 8K frame's worth of pixels, 1 = frame-by-frame */
+static int group_frames(const jpgb200_ctx *ctx, int n_frames, int w, int h)
+{
+    if (!ctx->group_small || !ctx->legacy_entropy || ctx->opt_huff || ctx->fused_k1e || n_frames < 2) return 1;
+    const long long npx = (long long)w * h;
+    if (npx > 4096ll * 2304ll) return 1; /* large frames fill the GPU on their own */
+    long long g = (7680ll * 4320ll) / npx;
+    if (g > 256) g = 256;
+    if (g > n_frames) g = n_frames;
+    return g < 2 ? 1 : (int)g;
+}
+
 /* ---- public encode entry points -------------------------------------------------------------- */
 
 extern "C" int jpgb200_encode_device(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w,
@@ -1417,6 +1561,19 @@ extern "C" int jpgb200_encode_batch_device(jpgb200_ctx *ctx, const uint8_t *d_pl
     if (!ctx || !d_planes || !d_out || n_frames < 0) return JPGB200_ERR_BAD_ARG;
     CK(cudaSetDevice(ctx->device));
     const size_t npx = (size_t)w * h;
+    {
+        /* small frames: groups of frames per launch (identical bytes, a fraction of the launches) */
+        const int G = group_frames(ctx, n_frames, w, h);
+        if (G > 1) {
+            int rc = JPGB200_OK;
+            for (int f0 = 0; f0 < n_frames && rc == JPGB200_OK; f0 += G) {
+                const int g = n_frames - f0 < G ? n_frames - f0 : G;
+                rc = encode_group(ctx, d_planes + (size_t)f0 * 3 * npx, g, w, h, quality, ratio, d_out + (size_t)f0 * out_stride, out_stride,
+                                  d_lens ? d_lens + f0 : NULL);
+            }
+            return rc;
+        }
+    }
     /* Overlap (default): frame f's tail (KF, KS: small, latency-bound) runs on a second stream
      * beside frame f+1's KE (it is launched behind frame f+1's K1, which fills the register files
      * and is better left alone: launched right behind KE it slowed K1 from 77 to 98 us).  The entropy
@@ -1573,12 +1730,7 @@ extern "C" int jpgb200_encode_batch_host(jpgb200_ctx *ctx, const uint8_t *const 
     if ((rc = ensure_tables(ctx, w, h, quality, ratio))) return rc;
     unsigned long long *d_hlen = NULL;
     CK(cudaHostGetDevicePointer((void **)&d_hlen, ctx->h_len, 0));
-    cudaEvent_t ev_in[2], ev_done[2], ev_out[2];
-    for (int s = 0; s < 2; s++) {
-        CK(cudaEventCreateWithFlags(&ev_in[s], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_done[s], cudaEventDisableTiming));
-        CK(cudaEventCreateWithFlags(&ev_out[s], cudaEventDisableTiming));
-    }
+    cudaEvent_t *ev_in = ctx->ev_in, *ev_done = ctx->ev_done, *ev_out = ctx->ev_out;
     auto drain = [&](int f) -> int {
         const int s = f & 1;
         CK(cudaEventSynchronize(ev_done[s]));
@@ -1612,12 +1764,28 @@ extern "C" int jpgb200_encode_batch_host(jpgb200_ctx *ctx, const uint8_t *const 
     if (rc == JPGB200_OK && n_frames >= 1) rc = drain(n_frames - 1);
     cudaStreamSynchronize(ctx->copy_out);
     cudaStreamSynchronize(ctx->stream);
-    for (int s = 0; s < 2; s++) {
-        cudaEventDestroy(ev_in[s]);
-        cudaEventDestroy(ev_done[s]);
-        cudaEventDestroy(ev_out[s]);
-    }
     return rc;
+}
+
+/* The copies of jpgb200_encode_batch_host without its kernels: one cudaMemcpyAsync per frame and direction,
+ * host->device on the copy-in stream, device->host on the copy-out stream, both directions at once.  What
+ * this takes is the PCIe ceiling of the end-to-end number on this host (bench.py: e2e.pcie_ceiling). */
+extern "C" int jpgb200_copy_probe(jpgb200_ctx *ctx, const uint8_t *const *frames, int n_frames, size_t in_bytes,
+                                  uint8_t *const *outs, size_t out_bytes)
+{
+    if (!ctx || !frames || !outs || n_frames < 0) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    int rc;
+    if (ctx->planes_cap < in_bytes || ctx->out_cap < out_bytes || !ctx->d_planes[1] || !ctx->d_out[1]) {
+        if ((rc = ensure_io(ctx, (in_bytes + 2) / 3, out_bytes > ctx->out_cap ? out_bytes : ctx->out_cap, 2))) return rc;
+    }
+    for (int f = 0; f < n_frames; f++) {
+        CK(cudaMemcpyAsync(ctx->d_planes[f & 1], frames[f], in_bytes, cudaMemcpyHostToDevice, ctx->copy_in));
+        CK(cudaMemcpyAsync(outs[f], ctx->d_out[f & 1], out_bytes, cudaMemcpyDeviceToHost, ctx->copy_out));
+    }
+    CK(cudaStreamSynchronize(ctx->copy_in));
+    CK(cudaStreamSynchronize(ctx->copy_out));
+    return JPGB200_OK;
 }
 
 /* ---- MCU-row partition of one large image across GPUs -----------------------------
@@ -2078,6 +2246,42 @@ extern "C" int jpgb200_host_alloc(void **hptr, size_t bytes)
 {
     if (!hptr) return JPGB200_ERR_BAD_ARG;
     return cudaHostAlloc(hptr, bytes, cudaHostAllocDefault) == cudaSuccess ? JPGB200_OK : JPGB200_ERR_NOMEM;
+}
+
+/* flags: 1 = write-combined (a buffer the host only writes: frames on their way to the device) */
+extern "C" int jpgb200_host_alloc_ex(void **hptr, size_t bytes, int flags)
+{
+    if (!hptr) return JPGB200_ERR_BAD_ARG;
+    return cudaHostAlloc(hptr, bytes, (flags & 1) ? cudaHostAllocWriteCombined : cudaHostAllocDefault) == cudaSuccess ? JPGB200_OK
+                                                                                                                    : JPGB200_ERR_NOMEM;
+}
+
+/* NUMA node of the device's PCIe function (-1: not reported, e.g. inside a VM) and the number of NUMA
+ * nodes this process can see: what a caller needs to place its pinned buffers */
+extern "C" int jpgb200_device_numa(int device, int *gpu_node, int *visible_nodes)
+{
+    char bus[32] = {0};
+    if (cudaDeviceGetPCIBusId(bus, sizeof bus, device) != cudaSuccess) return JPGB200_ERR_NO_DEVICE;
+    for (char *c = bus; *c; c++)
+        if (*c >= 'A' && *c <= 'Z') *c = (char)(*c - 'A' + 'a');
+    char path[128];
+    snprintf(path, sizeof path, "/sys/bus/pci/devices/%s/numa_node", bus);
+    int node = -1;
+    if (FILE *f = fopen(path, "r")) {
+        if (fscanf(f, "%d", &node) != 1) node = -1;
+        fclose(f);
+    }
+    int nodes = 0;
+    for (int i = 0; i < 64; i++) {
+        snprintf(path, sizeof path, "/sys/devices/system/node/node%d", i);
+        if (FILE *f = fopen((std::string(path) + "/cpulist").c_str(), "r")) {
+            nodes++;
+            fclose(f);
+        }
+    }
+    if (gpu_node) *gpu_node = node;
+    if (visible_nodes) *visible_nodes = nodes;
+    return JPGB200_OK;
 }
 
 extern "C" int jpgb200_host_free(void *hptr) { return cudaFreeHost(hptr) == cudaSuccess ? JPGB200_OK : JPGB200_ERR_CUDA; }

@@ -48,8 +48,27 @@ struct TailParams {
     unsigned long long cap;
     unsigned long long *len_out;
     int write_eoi;
-    EncState *st;
+    EncState *st; /* optional */
+    /* batches of small frames in one launch: blockIdx.y = frame */
+    long long tmp_fstride, out_fstride; /* words, bytes */
+    int cta_fstride, super_fstride;     /* elements */
 };
+
+__device__ __forceinline__ TailParams tail_frame(const TailParams &q0)
+{
+    TailParams q = q0;
+    const long long f = blockIdx.y;
+    q.tmp += f * q.tmp_fstride;
+    q.cta_bits += f * q.cta_fstride;
+    q.cta_tail += f * q.cta_fstride;
+    q.cta_ff += f * q.cta_fstride;
+    q.cta_base += f * q.cta_fstride;
+    q.super_bits += f * q.super_fstride;
+    q.super_ff += f * q.super_fstride;
+    if (q.out) q.out += f * q.out_fstride;
+    if (q.len_out) q.len_out += f;
+    return q;
+}
 
 __device__ __forceinline__ uint32_t be32(uint32_t w) { return __byte_perm(w, 0, 0x0123); }
 
@@ -142,8 +161,9 @@ __device__ __forceinline__ uint32_t ff_mask(uint32_t v, int nvalid)
 }
 
 /* ---- KF ---- */
-__global__ void __launch_bounds__(TAIL_THREADS) k_count_ff(const TailParams q)
+__global__ void __launch_bounds__(TAIL_THREADS) k_count_ff(const TailParams q0)
 {
+    const TailParams q = tail_frame(q0);
     const int lane = threadIdx.x & 31;
     const long long chunk = (long long)blockIdx.x * TAIL_WARPS + (threadIdx.x >> 5);
     if (chunk >= q.n_chunks) return;
@@ -181,8 +201,9 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_count_ff(const TailParams q)
 }
 
 /* ---- KS ---- */
-__global__ void __launch_bounds__(TAIL_THREADS) k_scatter(const TailParams q)
+__global__ void __launch_bounds__(TAIL_THREADS) k_scatter(const TailParams q0)
 {
+    const TailParams q = tail_frame(q0);
     const int lane = threadIdx.x & 31;
     const long long chunk = (long long)blockIdx.x * TAIL_WARPS + (threadIdx.x >> 5);
     if (chunk >= q.n_chunks) return;
@@ -271,11 +292,12 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_scatter(const TailParams q)
             q.out[out_len - 2] = 0xFF;
             q.out[out_len - 1] = 0xD9; /* EOI */
         }
-        EncState *st = q.st;
-        st->nbytes = nbytes;
-        st->total_ff = total_ff;
-        st->out_len = out_len;
-        st->error = ok ? 0 : 1;
+        if (EncState *st = q.st) {
+            st->nbytes = nbytes;
+            st->total_ff = total_ff;
+            st->out_len = out_len;
+            st->error = ok ? 0 : 1;
+        }
         if (q.len_out) *q.len_out = ok ? out_len : 0ull;
     }
 }

@@ -577,3 +577,44 @@ def test_batch_overlap_is_invisible(enc, w, h, ratio, nf):
         enc.free(d_pl)
         enc.free(d_out)
         enc.free(d_len)
+
+
+@pytest.mark.parametrize("w,h,ratio,nf", [(1920, 1080, 0, 21), (640, 64, 1, 9), (256, 16, 0, 300), (1280, 720, 2, 6), (264, 40, 0, 5)])
+def test_frame_groups_equal_per_frame(enc, w, h, ratio, nf):
+    """Batches of small frames share kernel launches (jpgb200_set_frame_groups: K1's tile index and the
+    entropy kernels' blockIdx.y run over the frames of a group): same streams and lengths as four
+    launches per frame, including a group count that does not divide the batch, more frames than one
+    group holds, a ragged last tile and a width the fast K1 declines (264 = 33 blocks)."""
+    if ratio == 2:
+        h = (h + 15) // 16 * 16
+    q, npx = 75, w * h
+    d_pl = enc.malloc(nf * 3 * npx)
+    cap = 3 * npx + 4096
+    d_out = enc.malloc(nf * cap)
+    d_len = enc.malloc(8 * nf)
+    try:
+        for f in range(nf):
+            enc.synth_device(d_pl + f * 3 * npx, w, h, 9090, f, (f % 3 == 2))
+        enc.sync()
+        res = {}
+        for mode in (True, False):
+            enc.set_frame_groups(mode)
+            enc.h2d(d_out, np.zeros(nf * cap, np.uint8))
+            enc.h2d(d_len, np.zeros(8 * nf, np.uint8))
+            enc.encode_batch_device(d_pl, nf, w, h, q, ratio, d_out, cap, d_len)
+            enc.sync()
+            res[mode] = (enc.d2h(d_len, 8 * nf).view(np.uint64).copy(), enc.d2h(d_out, nf * cap).reshape(nf, cap).copy())
+        lg, og = res[True]
+        lp, op = res[False]
+        assert (lg == lp).all() and (lg > 623).all()
+        for f in range(nf):
+            assert (og[f, :int(lg[f])] == op[f, :int(lg[f])]).all(), f
+        # and one frame against the oracle's bytes
+        planes = enc.d2h(d_pl + (nf - 1) * 3 * npx, 3 * npx).reshape(3, -1)
+        one = enc.encode_planar(planes[0], planes[1], planes[2], w, h, q, ratio)
+        assert int(lg[nf - 1]) == one.size and (og[nf - 1, :one.size] == one).all()
+    finally:
+        enc.set_frame_groups(True)
+        enc.free(d_pl)
+        enc.free(d_out)
+        enc.free(d_len)
