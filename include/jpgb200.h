@@ -44,6 +44,7 @@ extern "C" {
 #define JPGB200_ERR_OUT_TOO_SMALL (-5)
 #define JPGB200_ERR_BAD_ARG (-6)
 #define JPGB200_ERR_NOMEM (-7)
+#define JPGB200_ERR_NCCL (-8)
 
 #define JPGB200_DC_REF_RECURRENCE 0 /* d[i]=dc[i]-d[i-1], what dpcm() computes (src/dpcm.c:10-12) */
 #define JPGB200_DC_SPEC_DIFF 1      /* d[i]=dc[i]-dc[i-1], what a decodable stream needs        */
@@ -175,6 +176,30 @@ int jpgb200_band_finish(jpgb200_ctx *ctx, int carry_byte, uint8_t *d_segment, si
 /* JFIF header bytes for (w,h,q,ratio): SOI..SOS, 623 bytes. */
 int jpgb200_jfif_header(int width, int height, int quality, int sample_ratio, uint8_t *out, size_t cap, size_t *len);
 
+/* ---- one very large image across the GPUs of a box (BASELINE.json configs[4]) ---------------
+ * The reference cannot hold such an image at all (int fileSize, src/bitmap.c:27); what is replaced is
+ * encode_bmp_to_jpeg's single pass (src/jpg_encode.c:19-52) by one band of whole MCU rows per GPU.  One
+ * process (or host thread) per GPU, each with its own context; `nccl_comm` is an ncclComm_t over the
+ * participating ranks (the caller's, or one made with the three helpers below; NCCL is resolved at run
+ * time with dlopen, this library does not link against it).  Rank 0 owns the output buffer, the other
+ * ranks map it through CUDA IPC and their KS kernels store their segments straight into it over NVLink.
+ * Per encode: two ncclAllGathers of 32 / 24 bytes per rank on the context's stream (DC predictors + bit
+ * counts, then stuffed lengths + boundary bytes; csrc/mgpu.cuh), one 8-byte allgather as the completion
+ * barrier, no host synchronisation until jpgb200_mgpu_result. */
+typedef struct jpgb200_mgpu jpgb200_mgpu;
+int jpgb200_nccl_unique_id(uint8_t id[128]);                                                   /* ncclGetUniqueId */
+int jpgb200_nccl_init(void **comm, int world, int rank, const uint8_t id[128], int device);   /* ncclCommInitRank */
+int jpgb200_nccl_destroy(void *comm);
+int jpgb200_mgpu_create(jpgb200_mgpu **mg, jpgb200_ctx *ctx, void *nccl_comm, int rank, int world, size_t out_cap);
+int jpgb200_mgpu_destroy(jpgb200_mgpu *mg);
+/* d_r/d_g/d_b: the band's first row on this GPU; the row above it must be readable when rank > 0 (the
+ * reference reads the last block column one pixel row higher).  Enqueues everything. */
+int jpgb200_mgpu_encode(jpgb200_mgpu *mg, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int width, int band_height,
+                        int image_height, int quality, int sample_ratio);
+/* waits for this rank's stream; on rank 0 *total_len = bytes of the stitched JFIF stream */
+int jpgb200_mgpu_result(jpgb200_mgpu *mg, unsigned long long *total_len);
+uint8_t *jpgb200_mgpu_output(jpgb200_mgpu *mg); /* rank 0: device pointer of the stitched stream; NULL elsewhere */
+
 /* ---- parity taps (test and staged-mode surface) ------------------------------------- */
 /* Quantised zig-zag coefficients after zig_zag() and before dpcm() (src/jpg_encode.c:44),
  * int16 [Y blocks | Cb blocks | Cr blocks][64]; blocks per component = (w/8)*(h/8)
@@ -240,6 +265,9 @@ int jpgb200_memcpy_d2h(jpgb200_ctx *ctx, void *hptr, const void *dptr, size_t by
 /* deterministic synthetic planes [3][h][w] on the device (kind 0 natural, 1 noise) */
 int jpgb200_synth_device(jpgb200_ctx *ctx, uint8_t *d_planes, int width, int height, uint64_t seed, uint32_t frame,
                          int kind);
+/* rows row0 .. row0 + rows - 1 of the same image into planes [3][rows][w] (bands of the MCU-row partition) */
+int jpgb200_synth_device_rows(jpgb200_ctx *ctx, uint8_t *d_planes, int width, int rows, int row0, uint64_t seed,
+                              uint32_t frame, int kind);
 
 /* ---- measurement --------------------------------------------------------------------- */
 /* With profiling on (1), every kernel launch of the encode path is bracketed by CUDA events on

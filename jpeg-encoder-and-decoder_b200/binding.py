@@ -69,6 +69,14 @@ _SIGS = {
     "jpgb200_device_count": (C.c_int, []),
     "jpgb200_malloc": (C.c_int, [_vp, C.POINTER(_vp), C.c_size_t]),
     "jpgb200_free": (C.c_int, [_vp, _vp]),
+    "jpgb200_nccl_unique_id": (C.c_int, [_vp]),
+    "jpgb200_nccl_init": (C.c_int, [C.POINTER(_vp), C.c_int, C.c_int, _vp, C.c_int]),
+    "jpgb200_nccl_destroy": (C.c_int, [_vp]),
+    "jpgb200_mgpu_create": (C.c_int, [C.POINTER(_vp), _vp, _vp, C.c_int, C.c_int, C.c_size_t]),
+    "jpgb200_mgpu_destroy": (C.c_int, [_vp]),
+    "jpgb200_mgpu_encode": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "jpgb200_mgpu_result": (C.c_int, [_vp, C.POINTER(C.c_ulonglong)]),
+    "jpgb200_mgpu_output": (_vp, [_vp]),
     "jpgb200_host_alloc": (C.c_int, [C.POINTER(_vp), C.c_size_t]),
     "jpgb200_host_alloc_ex": (C.c_int, [C.POINTER(_vp), C.c_size_t, C.c_int]),
     "jpgb200_device_numa": (C.c_int, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int)]),
@@ -77,6 +85,7 @@ _SIGS = {
     "jpgb200_memcpy_h2d": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "jpgb200_memcpy_d2h": (C.c_int, [_vp, _vp, _vp, C.c_size_t]),
     "jpgb200_synth_device": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_int]),
+    "jpgb200_synth_device_rows": (C.c_int, [_vp, _vp, C.c_int, C.c_int, C.c_int, C.c_uint64, C.c_uint32, C.c_int]),
     "jpgb200_set_profiling": (C.c_int, [_vp, C.c_int]),
     "jpgb200_kernel_times": (C.c_int, [_vp, _vp, _vp]),
     "jpgb200_reset_profile": (C.c_int, [_vp]),
@@ -386,6 +395,9 @@ class Encoder:
     def synth_device(self, d_planes, w, h, seed, frame=0, kind=0):
         self._ck(lib().jpgb200_synth_device(self._h, d_planes, w, h, seed, frame, kind))
 
+    def synth_device_rows(self, d_planes, w, rows, row0, seed, frame=0, kind=0):
+        self._ck(lib().jpgb200_synth_device_rows(self._h, d_planes, w, rows, row0, seed, frame, kind))
+
     # ---- measurement
     def set_profiling(self, on):
         self._ck(lib().jpgb200_set_profiling(self._h, int(on)))
@@ -402,6 +414,54 @@ class Encoder:
 
     def launch_count(self):
         return int(lib().jpgb200_launch_count(self._h))
+
+
+def nccl_unique_id():
+    """128 bytes of ncclGetUniqueId (rank 0 makes it, the caller broadcasts it)"""
+    buf = np.zeros(128, np.uint8)
+    rc = lib().jpgb200_nccl_unique_id(buf.ctypes.data)
+    if rc:
+        raise Jpgb200Error(rc)
+    return buf
+
+
+class MgpuEncoder:
+    """jpgb200_mgpu_*: one band of a large image per rank, stitched in rank 0's buffer (include/jpgb200.h)."""
+
+    def __init__(self, enc, unique_id, rank, world, out_cap):
+        self.enc, self.rank, self.world = enc, rank, world
+        self._comm = _vp()
+        uid = np.ascontiguousarray(unique_id, dtype=np.uint8)
+        rc = lib().jpgb200_nccl_init(C.byref(self._comm), world, rank, uid.ctypes.data, enc.device)
+        if rc:
+            raise Jpgb200Error(rc)
+        self._mg = _vp()
+        rc = lib().jpgb200_mgpu_create(C.byref(self._mg), enc._h, self._comm, rank, world, out_cap)
+        if rc:
+            raise Jpgb200Error(rc, lib().jpgb200_last_error(enc._h).decode())
+
+    def encode(self, d_r, d_g, d_b, w, band_h, image_h, quality, ratio):
+        rc = lib().jpgb200_mgpu_encode(self._mg, d_r, d_g, d_b, w, band_h, image_h, quality, ratio)
+        if rc:
+            raise Jpgb200Error(rc, lib().jpgb200_last_error(self.enc._h).decode())
+
+    def result(self):
+        n = C.c_ulonglong(0)
+        rc = lib().jpgb200_mgpu_result(self._mg, C.byref(n))
+        if rc:
+            raise Jpgb200Error(rc, lib().jpgb200_last_error(self.enc._h).decode())
+        return int(n.value)
+
+    def output_ptr(self):
+        return lib().jpgb200_mgpu_output(self._mg)
+
+    def close(self):
+        if self._mg:
+            lib().jpgb200_mgpu_destroy(self._mg)
+            self._mg = None
+        if self._comm:
+            lib().jpgb200_nccl_destroy(self._comm)
+            self._comm = None
 
 
 def device_numa(device=0):

@@ -585,6 +585,7 @@ struct KeParams {
     /* batches of small frames in one launch: blockIdx.y = frame, every array advances by these strides */
     long long zz_fstride, tmp_fstride; /* int16 elements, words */
     int cta_fstride, super_fstride;    /* elements */
+    const int *dc_pred_dev;            /* optional: the predictors in device memory (multi-GPU bands) */
 };
 
 /* KE's threads: "entries" in component-major order -- two per luma block (part 0, part 1), one per
@@ -710,9 +711,9 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     p.coff1 = q.coff1;
     p.coff2 = q.coff2;
     p.n_mcu = q.n_mcu;
-    p.dc_pred[0] = q.dc_pred[0];
-    p.dc_pred[1] = q.dc_pred[1];
-    p.dc_pred[2] = q.dc_pred[2];
+    p.dc_pred[0] = q.dc_pred_dev ? q.dc_pred_dev[0] : q.dc_pred[0];
+    p.dc_pred[1] = q.dc_pred_dev ? q.dc_pred_dev[1] : q.dc_pred[1];
+    p.dc_pred[2] = q.dc_pred_dev ? q.dc_pred_dev[2] : q.dc_pred[2];
 
     ec_fill<RATIO, NT>(sC, p, m0, tid);
     ec_load_table(&sH, huff, tid);

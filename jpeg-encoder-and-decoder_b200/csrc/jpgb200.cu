@@ -16,6 +16,7 @@
  */
 #include <cuda_runtime.h>
 
+#include <dlfcn.h>
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
@@ -34,9 +35,14 @@
 #include "k1_pc.cuh"
 #include "k1_fused.cuh"
 #include "tail.cuh"
+#include "mgpu.cuh"
 #include "taps.cuh"
 
 using namespace jpgb200;
+
+struct ncclUniqueIdBytes {
+    char internal[128];
+};
 
 struct HuffSpecs {
     uint8_t nr[4][17];
@@ -183,6 +189,7 @@ extern "C" const char *jpgb200_strerror(int code)
     case JPGB200_ERR_OUT_TOO_SMALL: return "output buffer too small";
     case JPGB200_ERR_BAD_ARG: return "bad argument";
     case JPGB200_ERR_NOMEM: return "out of memory";
+    case JPGB200_ERR_NCCL: return "NCCL error or libnccl.so.2 not found (see jpgb200_last_error)";
     default: return "unknown error";
     }
 }
@@ -1199,6 +1206,7 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     e.local_off = ctx->overlap_now || ctx->in_batch ? NULL : ctx->d_local_off; /* parity tap: not inside batches */
     e.zz_fstride = e.tmp_fstride = 0;
     e.cta_fstride = e.super_fstride = 0;
+    e.dc_pred_dev = NULL;
     const unsigned nc = (unsigned)n_chunks(n);
     ctx->geo_chunks = n_chunks(n);
     ctx->geo_slot_words = slot_words(n);
@@ -1283,6 +1291,8 @@ static int launch_tail(jpgb200_ctx *ctx, const long long n[3], unsigned bit_phas
     q.st = ctx->d_state;
     q.tmp_fstride = q.out_fstride = 0;
     q.cta_fstride = q.super_fstride = 0;
+    q.mg = NULL;
+    q.out_off = 0ull;
     if (ctx->overlap_now) { /* deferred: it will run beside the next frame's KE (run_pending_tail) */
         ctx->pending_q = q;
         ctx->pending_parity = ctx->ws_parity;
@@ -1475,6 +1485,7 @@ static int encode_group(jpgb200_ctx *ctx, const uint8_t *d_planes, int G, int w,
     e.tmp_fstride = nc * sw;
     e.cta_fstride = (int)nc;
     e.super_fstride = S;
+    e.dc_pred_dev = NULL;
     if (!ctx->ke_attr_set) {
         CK(cudaFuncSetAttribute(k_encode_chunks<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<0>::BYTES));
         CK(cudaFuncSetAttribute(k_encode_chunks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<1>::BYTES));
@@ -1516,6 +1527,8 @@ static int encode_group(jpgb200_ctx *ctx, const uint8_t *d_planes, int G, int w,
     q.out_fstride = (long long)out_stride;
     q.cta_fstride = (int)nc;
     q.super_fstride = S;
+    q.mg = NULL;
+    q.out_off = 0ull;
     const dim3 tgrid((unsigned)((nc + TAIL_WARPS - 1) / TAIL_WARPS), (unsigned)G);
     {
         LaunchScope ls(ctx, KI_KF);
@@ -1892,6 +1905,294 @@ extern "C" int jpgb200_band_finish(jpgb200_ctx *ctx, int carry_byte, uint8_t *d_
     if (own && l == 0) return JPGB200_ERR_OUT_TOO_SMALL;
     *segment_len = l;
     return JPGB200_OK;
+}
+
+
+/* ---- one image across the GPUs of a box: C entry over NCCL + peer memory (mgpu.cuh) ----------------------
+ * NCCL is resolved at run time (dlopen of libnccl.so.2: inside a PyTorch process that is the library torch
+ * already loaded, in a plain C host the system's), so libjpgb200.so itself does not depend on it. */
+namespace {
+typedef int (*nccl_get_unique_id_t)(void *);
+typedef int (*nccl_comm_init_rank_t)(void **, int, ncclUniqueIdBytes, int);
+typedef int (*nccl_comm_destroy_t)(void *);
+typedef int (*nccl_all_gather_t)(const void *, void *, size_t, int, void *, cudaStream_t);
+typedef const char *(*nccl_get_error_string_t)(int);
+struct NcclApi {
+    void *lib;
+    nccl_get_unique_id_t get_unique_id;
+    nccl_comm_init_rank_t comm_init_rank;
+    nccl_comm_destroy_t comm_destroy;
+    nccl_all_gather_t all_gather;
+    nccl_get_error_string_t error_string;
+};
+NcclApi *nccl_api()
+{
+    static NcclApi api = {};
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (h) {
+            api.lib = h;
+            api.get_unique_id = (nccl_get_unique_id_t)dlsym(h, "ncclGetUniqueId");
+            api.comm_init_rank = (nccl_comm_init_rank_t)dlsym(h, "ncclCommInitRank");
+            api.comm_destroy = (nccl_comm_destroy_t)dlsym(h, "ncclCommDestroy");
+            api.all_gather = (nccl_all_gather_t)dlsym(h, "ncclAllGather");
+            api.error_string = (nccl_get_error_string_t)dlsym(h, "ncclGetErrorString");
+            if (!api.get_unique_id || !api.comm_init_rank || !api.comm_destroy || !api.all_gather) api.lib = NULL;
+        }
+    }
+    return api.lib ? &api : NULL;
+}
+}  // namespace
+
+extern "C" int jpgb200_nccl_unique_id(uint8_t id[128])
+{
+    NcclApi *a = nccl_api();
+    if (!a || !id) return JPGB200_ERR_NCCL;
+    return a->get_unique_id(id) == 0 ? JPGB200_OK : JPGB200_ERR_NCCL;
+}
+
+extern "C" int jpgb200_nccl_init(void **comm, int world, int rank, const uint8_t id[128], int device)
+{
+    NcclApi *a = nccl_api();
+    if (!a || !comm || !id) return JPGB200_ERR_NCCL;
+    if (cudaSetDevice(device) != cudaSuccess) return JPGB200_ERR_NO_DEVICE;
+    ncclUniqueIdBytes u;
+    memcpy(u.internal, id, 128);
+    return a->comm_init_rank(comm, world, u, rank) == 0 ? JPGB200_OK : JPGB200_ERR_NCCL;
+}
+
+extern "C" int jpgb200_nccl_destroy(void *comm)
+{
+    NcclApi *a = nccl_api();
+    if (!a) return JPGB200_ERR_NCCL;
+    return (!comm || a->comm_destroy(comm) == 0) ? JPGB200_OK : JPGB200_ERR_NCCL;
+}
+
+struct jpgb200_mgpu {
+    jpgb200_ctx *ctx;
+    void *comm;
+    int rank, world;
+    size_t out_cap;
+    uint8_t *out_local; /* rank 0: the output buffer */
+    uint8_t *out_peer;  /* every rank: rank 0's buffer as seen from this GPU */
+    bool opened;
+    /* device exchange buffers */
+    MgMsg1 *msg1, *all1;
+    MgMsg2 *msg2, *all2;
+    MgState *state;
+    unsigned long long *all_bits, *total_len, *done_send, *done_recv;
+    cudaIpcMemHandle_t *handles; /* [world] device */
+};
+
+#define NK(call)                                                                                                              \
+    do {                                                                                                                      \
+        int r_ = (call);                                                                                                      \
+        if (r_ != 0) {                                                                                                        \
+            snprintf(ctx->err, sizeof ctx->err, "%s failed: %s (%s:%d)", #call, api->error_string ? api->error_string(r_) : "nccl", \
+                     __FILE__, __LINE__);                                                                                     \
+            return JPGB200_ERR_NCCL;                                                                                          \
+        }                                                                                                                     \
+    } while (0)
+
+extern "C" int jpgb200_mgpu_create(jpgb200_mgpu **out, jpgb200_ctx *ctx, void *nccl_comm, int rank, int world, size_t out_cap)
+{
+    if (!out || !ctx || !nccl_comm || world < 1 || world > MG_MAX_RANKS || rank < 0 || rank >= world) return JPGB200_ERR_BAD_ARG;
+    NcclApi *api = nccl_api();
+    if (!api) {
+        snprintf(ctx->err, sizeof ctx->err, "libnccl.so.2 not found");
+        return JPGB200_ERR_NCCL;
+    }
+    CK(cudaSetDevice(ctx->device));
+    jpgb200_mgpu *mg = new jpgb200_mgpu();
+    memset(mg, 0, sizeof *mg);
+    mg->ctx = ctx;
+    mg->comm = nccl_comm;
+    mg->rank = rank;
+    mg->world = world;
+    mg->out_cap = out_cap;
+    *out = mg;
+    CK(cudaMalloc(&mg->msg1, sizeof(MgMsg1)));
+    CK(cudaMalloc(&mg->all1, sizeof(MgMsg1) * world));
+    CK(cudaMalloc(&mg->msg2, sizeof(MgMsg2)));
+    CK(cudaMalloc(&mg->all2, sizeof(MgMsg2) * world));
+    CK(cudaMalloc(&mg->state, sizeof(MgState)));
+    CK(cudaMemset(mg->state, 0, sizeof(MgState)));
+    CK(cudaMalloc(&mg->all_bits, 8 * world));
+    CK(cudaMalloc(&mg->total_len, 8));
+    CK(cudaMalloc(&mg->done_send, 8));
+    CK(cudaMemset(mg->done_send, 0, 8));
+    CK(cudaMalloc(&mg->done_recv, 8 * world));
+    CK(cudaMalloc(&mg->handles, sizeof(cudaIpcMemHandle_t) * world));
+    /* rank 0 owns the output; its IPC handle travels to everyone through the communicator itself */
+    cudaIpcMemHandle_t mine;
+    memset(&mine, 0, sizeof mine);
+    if (rank == 0) {
+        CK(cudaMalloc(&mg->out_local, out_cap));
+        CK(cudaIpcGetMemHandle(&mine, mg->out_local));
+    }
+    cudaIpcMemHandle_t *d_mine = NULL;
+    CK(cudaMalloc(&d_mine, sizeof mine));
+    CK(cudaMemcpyAsync(d_mine, &mine, sizeof mine, cudaMemcpyHostToDevice, ctx->stream));
+    NK(api->all_gather(d_mine, mg->handles, sizeof mine, 1 /* ncclUint8 */, mg->comm, ctx->stream));
+    cudaIpcMemHandle_t h0;
+    CK(cudaMemcpyAsync(&h0, mg->handles, sizeof h0, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    CK(cudaFree(d_mine));
+    if (rank == 0) {
+        mg->out_peer = mg->out_local;
+    } else {
+        void *p = NULL;
+        CK(cudaIpcOpenMemHandle(&p, h0, cudaIpcMemLazyEnablePeerAccess));
+        mg->out_peer = (uint8_t *)p;
+        mg->opened = true;
+    }
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_mgpu_destroy(jpgb200_mgpu *mg)
+{
+    if (!mg) return JPGB200_OK;
+    jpgb200_ctx *ctx = mg->ctx;
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+    if (mg->opened) cudaIpcCloseMemHandle(mg->out_peer);
+    void *ptrs[] = {mg->msg1, mg->all1, mg->msg2, mg->all2, mg->state, mg->all_bits, mg->total_len, mg->done_send, mg->done_recv,
+                    mg->handles, mg->out_local};
+    for (void *p : ptrs)
+        if (p) cudaFree(p);
+    delete mg;
+    return JPGB200_OK;
+}
+
+extern "C" uint8_t *jpgb200_mgpu_output(jpgb200_mgpu *mg) { return mg ? mg->out_local : NULL; }
+
+/* Encode this rank's band (d_r/d_g/d_b: its first row; the row above must be readable when rank > 0) and
+ * stitch the stream in rank 0's buffer.  Everything is enqueued on the context's stream: K1, KE, exchange 1,
+ * the first chunk again, KF, exchange 2, KS through the peer pointer, completion allgather.  Nothing is
+ * synchronised with the host; jpgb200_mgpu_result waits and reads the length. */
+extern "C" int jpgb200_mgpu_encode(jpgb200_mgpu *mg, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w, int band_h,
+                                   int image_h, int quality, int ratio)
+{
+    if (!mg || !d_r || !d_g || !d_b) return JPGB200_ERR_BAD_ARG;
+    if (ratio != 0 && ratio != 1) return JPGB200_ERR_BAD_ARG; /* the MCU-row partition is built for 8-row MCUs */
+    jpgb200_ctx *ctx = mg->ctx;
+    NcclApi *api = nccl_api();
+    if (!api) return JPGB200_ERR_NCCL;
+    long long n[3], n_img[3];
+    int rc = validate(w, band_h, quality, ratio, n);
+    if (rc) return rc;
+    if ((rc = validate(w, image_h, quality, ratio, n_img))) return rc;
+    CK(cudaSetDevice(ctx->device));
+    if ((rc = ensure_workspace(ctx, n, 1))) return rc;
+    if ((rc = ensure_tables(ctx, w, image_h, quality, ratio))) return rc; /* the header describes the WHOLE image */
+    ctx->w = w;
+    ctx->h = band_h;
+    ctx->q = quality;
+    ctx->ratio = ratio;
+    memcpy(ctx->n, n, sizeof n);
+    const int rank = mg->rank, world = mg->world, is_last = rank == world - 1;
+    cudaStream_t st = ctx->stream;
+    const bool was_batch = ctx->in_batch;
+    ctx->in_batch = true; /* no per-block offset tap */
+    /* K1 + KE with a zero predictor */
+    if ((rc = launch_k1(ctx, d_r, d_g, d_b, w, band_h, ratio, n, 1, 0, ctx->d_zz, 0, rank > 0 ? 1 : 0))) return rc;
+    rc = launch_bits(ctx, ctx->d_zz, ratio, n);
+    if (rc) {
+        ctx->in_batch = was_batch;
+        return rc;
+    }
+    const long long nc = n_chunks(n), sw = slot_words(n);
+    const int nsb = (int)(nc / 64 + 1);
+    k_mg_pack1<<<1, 32, 0, st>>>(ctx->d_zz, n[0], n[1], n[2], ctx->d_super, nsb, mg->msg1);
+    ctx->launch_total++;
+    NK(api->all_gather(mg->msg1, mg->all1, sizeof(MgMsg1), 1, mg->comm, st)); /* exchange 1 */
+    k_mg_fix0<<<1, 32, 0, st>>>(mg->all1, rank, world, ctx->d_hpack, mg->state, ctx->d_super, ctx->d_cta_bits, mg->all_bits);
+    ctx->launch_total++;
+    {
+        /* the band's first chunk again, now with the true predictor (device memory) */
+        KeParams e;
+        e.zz = ctx->d_zz;
+        e.coff1 = n[0];
+        e.coff2 = n[0] + n[1];
+        e.n_mcu = n[1];
+        e.dc_pred[0] = e.dc_pred[1] = e.dc_pred[2] = 0;
+        e.tmp = ctx->d_tmp;
+        e.slot_words = sw;
+        e.cta_bits = ctx->d_cta_bits;
+        e.cta_tail = ctx->d_cta_tail;
+        e.super_bits = ctx->d_super;
+        e.local_off = NULL;
+        e.zz_fstride = e.tmp_fstride = 0;
+        e.cta_fstride = e.super_fstride = 0;
+        e.dc_pred_dev = mg->state->pred;
+        LaunchScope ls(ctx, KI_KE);
+        if (ratio == 0)
+            k_encode_chunks<0><<<1, KeCfg<0>::NT, KeSmem<0>::BYTES, st>>>(e, ctx->d_hpack);
+        else
+            k_encode_chunks<1><<<1, KeCfg<1>::NT, KeSmem<1>::BYTES, st>>>(e, ctx->d_hpack);
+    }
+    ctx->in_batch = was_batch;
+    CK(cudaGetLastError());
+    TailParams q;
+    q.tmp = ctx->d_tmp;
+    q.slot_words = sw;
+    q.n_chunks = nc;
+    q.cta_bits = ctx->d_cta_bits;
+    q.super_bits = ctx->d_super;
+    q.cta_ff = ctx->d_cta_ff;
+    q.cta_tail = ctx->d_cta_tail;
+    q.cta_base = ctx->d_cta_base;
+    q.super_ff = ctx->d_super + ctx->n_super_bits;
+    q.bit_phase = 0u;
+    q.carry = 0u;
+    q.is_last_band = is_last;
+    q.header = ctx->d_header;
+    q.header_len = rank == 0 ? ctx->hdr_len : 0;
+    q.out = mg->out_peer;
+    q.cap = (unsigned long long)mg->out_cap;
+    q.len_out = NULL;
+    q.write_eoi = is_last;
+    q.st = NULL;
+    q.tmp_fstride = q.out_fstride = 0;
+    q.cta_fstride = q.super_fstride = 0;
+    q.mg = mg->state;
+    q.out_off = 0ull;
+    const unsigned tgrid = (unsigned)((nc + TAIL_WARPS - 1) / TAIL_WARPS);
+    {
+        LaunchScope ls(ctx, KI_KF);
+        k_count_ff<<<tgrid, TAIL_THREADS, 0, st>>>(q);
+    }
+    CK(cudaGetLastError());
+    k_mg_pack2<<<1, 32, 0, st>>>(mg->state, is_last, ctx->d_tmp, sw, nc, ctx->d_cta_bits, ctx->d_super + ctx->n_super_bits, nsb, mg->msg2);
+    ctx->launch_total++;
+    NK(api->all_gather(mg->msg2, mg->all2, sizeof(MgMsg2), 1, mg->comm, st)); /* exchange 2 */
+    k_mg_fix1<<<1, 32, 0, st>>>(mg->all2, mg->all_bits, rank, world, ctx->hdr_len, mg->state, ctx->d_cta_ff,
+                                ctx->d_super + ctx->n_super_bits, mg->total_len);
+    ctx->launch_total++;
+    {
+        LaunchScope ls(ctx, KI_KS);
+        k_scatter<<<tgrid, TAIL_THREADS, 0, st>>>(q); /* through the peer pointer: straight into rank 0's buffer */
+    }
+    CK(cudaGetLastError());
+    /* completion: when this allgather has run on rank 0's stream, every rank's KS has finished */
+    NK(api->all_gather(mg->done_send, mg->done_recv, 8, 1, mg->comm, st));
+    return JPGB200_OK;
+}
+
+/* waits for the stream; rank 0 gets the length of the stitched stream (0: the output buffer was too small) */
+extern "C" int jpgb200_mgpu_result(jpgb200_mgpu *mg, unsigned long long *total_len)
+{
+    if (!mg) return JPGB200_ERR_BAD_ARG;
+    jpgb200_ctx *ctx = mg->ctx;
+    CK(cudaSetDevice(ctx->device));
+    unsigned long long l = 0;
+    CK(cudaMemcpyAsync(&l, mg->total_len, 8, cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    if (total_len) *total_len = l <= mg->out_cap ? l : 0ull;
+    return l <= mg->out_cap ? JPGB200_OK : JPGB200_ERR_OUT_TOO_SMALL;
 }
 
 /* ---- parity taps -------------------------------------------------------------------------------- */
@@ -2310,7 +2611,21 @@ extern "C" int jpgb200_synth_device(jpgb200_ctx *ctx, uint8_t *d_planes, int w, 
     if (!ctx || !d_planes || w <= 0 || h <= 0 || (w % 8)) return JPGB200_ERR_BAD_ARG;
     CK(cudaSetDevice(ctx->device));
     dim3 grid((unsigned)ctx->sm_count * 8, 1, 3);
-    ks_synth<<<grid, 256, 0, ctx->stream>>>(d_planes, w, h, (unsigned long long)seed, frame, kind);
+    ks_synth<<<grid, 256, 0, ctx->stream>>>(d_planes, w, h, (unsigned long long)seed, frame, kind, 0);
+    ctx->launch_total++;
+    CK(cudaGetLastError());
+    return JPGB200_OK;
+}
+
+/* rows row0 .. row0 + rows - 1 of the same synthetic image into planes [3][rows][w]: a rank of the MCU-row
+ * partition generates its band (and the halo row above it) without ever holding the whole image */
+extern "C" int jpgb200_synth_device_rows(jpgb200_ctx *ctx, uint8_t *d_planes, int w, int rows, int row0, uint64_t seed,
+                                         uint32_t frame, int kind)
+{
+    if (!ctx || !d_planes || w <= 0 || rows <= 0 || row0 < 0 || (w % 8)) return JPGB200_ERR_BAD_ARG;
+    CK(cudaSetDevice(ctx->device));
+    dim3 grid((unsigned)ctx->sm_count * 8, 1, 3);
+    ks_synth<<<grid, 256, 0, ctx->stream>>>(d_planes, w, rows, (unsigned long long)seed, frame, kind, row0);
     ctx->launch_total++;
     CK(cudaGetLastError());
     return JPGB200_OK;

@@ -32,6 +32,18 @@ namespace jpgb200 {
 #define TAIL_THREADS 256
 #define TAIL_WARPS (TAIL_THREADS / 32)
 
+/* what the band's own kernels read instead of host-side launch parameters */
+struct MgState {
+    int pred[3];              /* DC predictor of the band's first blocks */
+    unsigned int phase;       /* bit phase of the band's first bit in the scan, 0..7 */
+    unsigned int carry;       /* the previous band's trailing bits (low `phase` bits) */
+    unsigned int pad;
+    unsigned long long bits;     /* band bits with the true predictor */
+    unsigned long long bit_base; /* bit offset of the band in the scan */
+    unsigned long long out_off;  /* byte offset of the band's segment in the final stream */
+    unsigned long long total_len; /* whole stream: header + scan + EOI */
+};
+
 struct TailParams {
     const uint32_t *tmp; /* [n_chunks][slot_words] chunk streams, big-endian words (KE) */
     long long slot_words, n_chunks;
@@ -52,6 +64,9 @@ struct TailParams {
     /* batches of small frames in one launch: blockIdx.y = frame */
     long long tmp_fstride, out_fstride; /* words, bytes */
     int cta_fstride, super_fstride;     /* elements */
+    /* multi-GPU bands: bit phase, carry and output offset come from device memory (mgpu.cuh) */
+    const MgState *mg;
+    unsigned long long out_off;
 };
 
 __device__ __forceinline__ TailParams tail_frame(const TailParams &q0)
@@ -67,6 +82,11 @@ __device__ __forceinline__ TailParams tail_frame(const TailParams &q0)
     q.super_ff += f * q.super_fstride;
     if (q.out) q.out += f * q.out_fstride;
     if (q.len_out) q.len_out += f;
+    if (q.mg) {
+        q.bit_phase = q.mg->phase;
+        q.carry = q.mg->carry;
+        q.out_off = q.mg->out_off;
+    }
     return q;
 }
 
@@ -217,7 +237,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_scatter(const TailParams q0)
     const unsigned long long ff_before = tail_prefix(q.cta_ff, q.super_ff, chunk, lane);
     const TailGeom g(q, chunk, g0, T);
     const unsigned long long trailer = q.write_eoi ? 2ull : 0ull;
-    unsigned long long P = (unsigned long long)q.header_len + g.bA + ff_before;
+    unsigned long long P = q.out_off + (unsigned long long)q.header_len + g.bA + ff_before;
     const bool fits = P + g.nB + my_ff + trailer <= q.cap;
     const bool last = (chunk == q.n_chunks - 1);
     if (chunk == 0 && (unsigned long long)q.header_len <= q.cap)
@@ -286,7 +306,7 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_scatter(const TailParams q0)
     if (last && lane == 0) {
         const unsigned long long nbytes = g.bA + g.nB;
         const unsigned long long total_ff = ff_before + my_ff;
-        const unsigned long long out_len = (unsigned long long)q.header_len + nbytes + total_ff + trailer;
+        const unsigned long long out_len = q.out_off + (unsigned long long)q.header_len + nbytes + total_ff + trailer;
         const bool ok = out_len <= q.cap;
         if (ok && q.write_eoi) {
             q.out[out_len - 2] = 0xFF;

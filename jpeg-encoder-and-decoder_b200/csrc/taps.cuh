@@ -350,8 +350,9 @@ __global__ void __launch_bounds__(256) khs_histograms(const int *zz, long long n
 }
 
 /* ---- KS: synthetic planes ------------------------------------------------------------- */
+/* rows y0 .. y0 + h - 1 of the synthetic image into planes [3][h][w] (y0 = 0: the whole image) */
 __global__ void __launch_bounds__(256) ks_synth(uint8_t *planes, int w, int h, unsigned long long seed,
-                                                unsigned frame, int kind)
+                                                unsigned frame, int kind, int y0)
 {
     const int c = blockIdx.z;
     const unsigned long long key = synth_key(seed, frame, c);
@@ -360,7 +361,7 @@ __global__ void __launch_bounds__(256) ks_synth(uint8_t *planes, int w, int h, u
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long q = (long long)blockIdx.x * blockDim.x + threadIdx.x; q < npx4; q += stride) {
         const long long i = q * 4;
-        const int y = (int)(i / w), x = (int)(i % w); /* w % 8 == 0: the 4 pixels share a row */
+        const int y = y0 + (int)(i / w), x = (int)(i % w); /* w % 8 == 0: the 4 pixels share a row */
         uint32_t v = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) v |= (uint32_t)synth_px(key, kind, x + k, y) << (8 * k);

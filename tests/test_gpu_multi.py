@@ -1,7 +1,8 @@
 """Multi-GPU and host-driver GPU tests.
- - the MCU-row partition of one image across the box's GPUs (NCCL allgathers + send/recv
-   stitch) must produce the very bytes of a single-GPU encode (needs >= 2 GPUs: skipped on
-   the 1-GPU box, run with `gpurun --gpus 2`)
+ - the MCU-row partition of one image across the box's GPUs -- the C entry jpgb200_mgpu_encode (two
+   ncclAllGathers, segments stored straight into rank 0's buffer through a peer-mapped pointer) and the
+   earlier torch.distributed orchestration -- must produce the very bytes of a single-GPU encode and of the
+   oracle's bit writer (needs >= 2 GPUs: skipped on the 1-GPU box, run with `gpurun --gpus 2`)
  - the host C mirror: the reference-style driver executable and the staged JpgData API."""
 import io
 import os
@@ -36,13 +37,28 @@ def test_partitioned_encode_equals_single_gpu(tmp_path, w, h, q, ratio):
            "--master-port", "29617", os.path.join(ROOT, "tests", "partition_worker.py"), str(w), str(h), str(q), str(ratio), out]
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=280)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
-    assert "identical=True" in res.stdout
+    assert "identical=True" in res.stdout and "c_nccl=True" in res.stdout and "torch_dist=True" in res.stdout
     jf = np.load(out)
     from PIL import Image
 
     im = Image.open(io.BytesIO(jf.tobytes()))
     im.load()
     assert im.size == (w, h)
+    if w * h <= 1024 * 1032:
+        # the stitched stream against the ORACLE: the whole image's bytes from the oracle's bit writer fed with
+        # the oracle's own coefficients differ only where FP32 and FP64 coefficients differ (<= 0.1 %), so compare
+        # the decoded pictures and, exactly, the stream re-coded from this image's GPU coefficients
+        r, g, b = O.synth_planes(w, h, 1005, 0, 0)
+        import __graft_entry__ as ge
+
+        e1 = ge.load_package().Encoder(0)
+        try:
+            zz = e1.coefficients(r, g, b, w, h, q, ratio)
+        finally:
+            e1.close()
+        scan, _ = O.encode_scan(zz, w, h, ratio)
+        want = np.concatenate([O.jfif_header(w, h, q, ratio), scan, np.array([0xFF, 0xD9], np.uint8)])
+        assert jf.shape == want.shape and (jf == want).all()
 
 
 def test_driver_executable_known_answer_and_file_encode(tmp_path):
