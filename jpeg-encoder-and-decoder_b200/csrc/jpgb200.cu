@@ -1293,6 +1293,7 @@ static int launch_tail(jpgb200_ctx *ctx, const long long n[3], unsigned bit_phas
     q.cta_fstride = q.super_fstride = 0;
     q.mg = NULL;
     q.out_off = 0ull;
+    q.mg_local = 0;
     if (ctx->overlap_now) { /* deferred: it will run beside the next frame's KE (run_pending_tail) */
         ctx->pending_q = q;
         ctx->pending_parity = ctx->ws_parity;
@@ -1529,6 +1530,7 @@ static int encode_group(jpgb200_ctx *ctx, const uint8_t *d_planes, int G, int w,
     q.super_fstride = S;
     q.mg = NULL;
     q.out_off = 0ull;
+    q.mg_local = 0;
     const dim3 tgrid((unsigned)((nc + TAIL_WARPS - 1) / TAIL_WARPS), (unsigned)G);
     {
         LaunchScope ls(ctx, KI_KF);
@@ -1978,6 +1980,8 @@ struct jpgb200_mgpu {
     size_t out_cap;
     uint8_t *out_local; /* rank 0: the output buffer */
     uint8_t *out_peer;  /* every rank: rank 0's buffer as seen from this GPU */
+    uint8_t *seg;       /* ranks > 0: the band's segment before it is pushed to rank 0 */
+    size_t seg_cap;
     bool opened;
     /* device exchange buffers */
     MgMsg1 *msg1, *all1;
@@ -2060,7 +2064,7 @@ extern "C" int jpgb200_mgpu_destroy(jpgb200_mgpu *mg)
     cudaStreamSynchronize(ctx->stream);
     if (mg->opened) cudaIpcCloseMemHandle(mg->out_peer);
     void *ptrs[] = {mg->msg1, mg->all1, mg->msg2, mg->all2, mg->state, mg->all_bits, mg->total_len, mg->done_send, mg->done_recv,
-                    mg->handles, mg->out_local};
+                    mg->handles, mg->out_local, mg->seg};
     for (void *p : ptrs)
         if (p) cudaFree(p);
     delete mg;
@@ -2151,8 +2155,20 @@ extern "C" int jpgb200_mgpu_encode(jpgb200_mgpu *mg, const uint8_t *d_r, const u
     q.is_last_band = is_last;
     q.header = ctx->d_header;
     q.header_len = rank == 0 ? ctx->hdr_len : 0;
-    q.out = mg->out_peer;
-    q.cap = (unsigned long long)mg->out_cap;
+    if (rank > 0) {
+        /* worst case of a band's segment: every block at its longest, every byte stuffed */
+        const size_t need = (size_t)(n[0] + n[1] + n[2]) * 1658 / 8 * 2 + 64;
+        const size_t want = need < mg->out_cap + 64 ? need : mg->out_cap + 64;
+        if (mg->seg_cap < want) {
+            CK(cudaStreamSynchronize(st));
+            if (mg->seg) CK(cudaFree(mg->seg));
+            mg->seg = NULL;
+            CK(cudaMalloc(&mg->seg, want));
+            mg->seg_cap = want;
+        }
+    }
+    q.out = rank == 0 ? mg->out_local : mg->seg;
+    q.cap = (unsigned long long)(rank == 0 ? mg->out_cap : mg->seg_cap);
     q.len_out = NULL;
     q.write_eoi = is_last;
     q.st = NULL;
@@ -2160,6 +2176,7 @@ extern "C" int jpgb200_mgpu_encode(jpgb200_mgpu *mg, const uint8_t *d_r, const u
     q.cta_fstride = q.super_fstride = 0;
     q.mg = mg->state;
     q.out_off = 0ull;
+    q.mg_local = rank > 0 ? 1 : 0;
     const unsigned tgrid = (unsigned)((nc + TAIL_WARPS - 1) / TAIL_WARPS);
     {
         LaunchScope ls(ctx, KI_KF);
@@ -2174,9 +2191,15 @@ extern "C" int jpgb200_mgpu_encode(jpgb200_mgpu *mg, const uint8_t *d_r, const u
     ctx->launch_total++;
     {
         LaunchScope ls(ctx, KI_KS);
-        k_scatter<<<tgrid, TAIL_THREADS, 0, st>>>(q); /* through the peer pointer: straight into rank 0's buffer */
+        k_scatter<<<tgrid, TAIL_THREADS, 0, st>>>(q); /* rank 0: in place; others: a local segment at the destination's 16-byte phase */
     }
     CK(cudaGetLastError());
+    if (rank > 0) {
+        /* the segment goes straight into rank 0's buffer through the peer pointer, 16 bytes per store */
+        k_mg_push<<<(unsigned)ctx->sm_count * 4, 256, 0, st>>>(mg->state, mg->seg, mg->out_peer, (unsigned long long)mg->out_cap);
+        ctx->launch_total++;
+        CK(cudaGetLastError());
+    }
     /* completion: when this allgather has run on rank 0's stream, every rank's KS has finished */
     NK(api->all_gather(mg->done_send, mg->done_recv, 8, 1, mg->comm, st));
     return JPGB200_OK;

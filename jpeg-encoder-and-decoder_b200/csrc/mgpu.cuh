@@ -140,6 +140,7 @@ __global__ void k_mg_fix1(const MgMsg2 *all, const unsigned long long *all_bits,
         if (j == rank) {
             st->carry = carry;
             st->out_off = j == 0 ? 0ull : off; /* rank 0's KS adds the header itself */
+            st->seg_len = all[j].owned + all[j].ff + fix + (j == world - 1 ? 2ull : 0ull);
             if (fix) {
                 cta_ff[0] += 1u;
                 super_ff[0] += 1u;
@@ -150,6 +151,24 @@ __global__ void k_mg_fix1(const MgMsg2 *all, const unsigned long long *all_bits,
     }
     st->total_len = off + 2ull;
     if (total_len_out) *total_len_out = off + 2ull;
+}
+
+/* the band's segment, written by KS into local memory at the 16-byte phase of its destination, goes to
+ * rank 0's buffer with 16-byte stores through the peer pointer (single-byte stores over NVLink are slow) */
+__global__ void __launch_bounds__(256) k_mg_push(const MgState *st, const uint8_t *seg, uint8_t *peer, unsigned long long cap)
+{
+    const unsigned long long off = st->out_off, len = st->seg_len;
+    if (off + len > cap) return;
+    const uint8_t *src = seg + (off & 15ull);
+    uint8_t *dst = peer + off;
+    const unsigned long long head = min(len, (16ull - (off & 15ull)) & 15ull);
+    const unsigned long long body = (len - head) >> 4, tail0 = head + (body << 4);
+    const unsigned long long tid = (unsigned long long)blockIdx.x * blockDim.x + threadIdx.x, nth = (unsigned long long)gridDim.x * blockDim.x;
+    if (tid < head) dst[tid] = src[tid];
+    const uint4 *s4 = reinterpret_cast<const uint4 *>(src + head);
+    uint4 *d4 = reinterpret_cast<uint4 *>(dst + head);
+    for (unsigned long long i = tid; i < body; i += nth) d4[i] = s4[i];
+    if (tid < len - tail0) dst[tail0 + tid] = src[tail0 + tid];
 }
 
 }  // namespace jpgb200

@@ -41,6 +41,7 @@ struct MgState {
     unsigned long long bits;     /* band bits with the true predictor */
     unsigned long long bit_base; /* bit offset of the band in the scan */
     unsigned long long out_off;  /* byte offset of the band's segment in the final stream */
+    unsigned long long seg_len;  /* bytes of the band's segment (stuffed scan bytes, + EOI on the last band) */
     unsigned long long total_len; /* whole stream: header + scan + EOI */
 };
 
@@ -67,6 +68,7 @@ struct TailParams {
     /* multi-GPU bands: bit phase, carry and output offset come from device memory (mgpu.cuh) */
     const MgState *mg;
     unsigned long long out_off;
+    int mg_local; /* 1: KS writes into a local segment buffer at offset (out_off & 15); k_mg_push moves it to rank 0 */
 };
 
 __device__ __forceinline__ TailParams tail_frame(const TailParams &q0)
@@ -85,7 +87,7 @@ __device__ __forceinline__ TailParams tail_frame(const TailParams &q0)
     if (q.mg) {
         q.bit_phase = q.mg->phase;
         q.carry = q.mg->carry;
-        q.out_off = q.mg->out_off;
+        q.out_off = q.mg_local ? (q.mg->out_off & 15ull) : q.mg->out_off;
     }
     return q;
 }

@@ -53,12 +53,14 @@ def main():
     n_c = mg.result()
     times = []
     for _ in range(reps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dist.barrier()
         torch.cuda.synchronize()
-        t0 = time.perf_counter()
+        e0.record(stream)
         mg.encode(ptrs[0], ptrs[1], ptrs[2], w, bh, h, q, ratio)
+        e1.record(stream)
         n_c = mg.result()
-        tt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=dev)
+        tt = torch.tensor([e0.elapsed_time(e1) * 1e-3], dtype=torch.float64, device=dev)
         dist.all_reduce(tt, op=dist.ReduceOp.MAX)
         times.append(float(tt.item()))
     c_stream = None
