@@ -35,6 +35,9 @@ struct HuffDev {
 struct HuffPack {
     uint32_t ac[2][256];
     uint32_t dc[2][16];
+    /* [lum|chr][run * 8 + value + 4], |value| <= 3 (99 % of the non-zero coefficients of the headline frames): the
+     * ac word of (run, category of value) with value's additional bits already merged */
+    uint32_t lut[2][128];
 };
 /* count tables: total bits of one symbol incl. its additional bits; the AC table is
  * extended to runs of up to 62 zeros, folding in the ZRL codes a long run needs */
@@ -348,40 +351,49 @@ __device__ __forceinline__ int ec_split(unsigned long long M)
     return 40;
 }
 
-/* WHOLE = true: one thread codes the entire block (chroma); otherwise part 0 or 1 of a split block,
- * coded by two ADJACENT lanes which each build one half of the non-zero mask and swap them.
- * Tables are HuffPack words. */
-template <bool WHOLE, class Sink>
-__device__ __forceinline__ void ec_pack_part(const uint4 *row, int diff, int part, const uint32_t *sAc, const uint32_t *sDc,
-                                             Sink &s)
+/* The masks of one entry.  WHOLE = true: one thread codes the entire block (chroma); otherwise part 0 or 1 of a
+ * split block, coded by two ADJACENT lanes which each build one half of the non-zero mask and swap them: that
+ * shuffle is executed by all 32 lanes of the (component-pure) warp with a full mask, valid block or not, so it
+ * must be called OUTSIDE any `valid` branch.  Returns false when this entry has nothing to code. */
+template <bool WHOLE>
+__device__ __forceinline__ bool ec_entry_masks(const uint4 *row, int part, uint32_t (&mm)[2], int &prev, bool &eob)
 {
-    uint32_t mm[2];
-    int prev = 0;
-    bool eob = true;
+    prev = 0;
+    eob = true;
     if (WHOLE) {
         ec_nz_masks(row, mm[0], mm[1]);
-    } else {
-        const uint32_t mine_half = part == 0 ? ((nz_mask16(row[0], row[1]) | (nz_mask16(row[2], row[3]) << 16)) & ~1u)
-                                             : (nz_mask16(row[4], row[5]) | (nz_mask16(row[6], row[7]) << 16));
-        const uint32_t other_half = __shfl_xor_sync(__activemask(), mine_half, 1);
-        const unsigned long long M = part == 0 ? ((unsigned long long)mine_half | ((unsigned long long)other_half << 32))
-                                               : ((unsigned long long)other_half | ((unsigned long long)mine_half << 32));
-        const int S = ec_split(M);
-        const unsigned long long lowmask = S >= 63 ? ~0ull : ((2ull << S) - 1ull);
-        unsigned long long mine;
-        if (part == 0) {
-            mine = M & lowmask;
-            eob = (S >= 63);
-        } else {
-            mine = M & ~lowmask;
-            const unsigned long long before = M & lowmask;
-            prev = before ? 63 - __clzll((long long)before) : 0;
-            if (S >= 63) return; /* part 0 coded the whole block */
-        }
-        mm[0] = (uint32_t)mine;
-        mm[1] = (uint32_t)(mine >> 32);
+        return true;
     }
-    if (WHOLE || part == 0) {
+    const uint32_t mine_half = part == 0 ? ((nz_mask16(row[0], row[1]) | (nz_mask16(row[2], row[3]) << 16)) & ~1u)
+                                         : (nz_mask16(row[4], row[5]) | (nz_mask16(row[6], row[7]) << 16));
+    const uint32_t other_half = __shfl_xor_sync(0xffffffffu, mine_half, 1);
+    const unsigned long long M = part == 0 ? ((unsigned long long)mine_half | ((unsigned long long)other_half << 32))
+                                           : ((unsigned long long)other_half | ((unsigned long long)mine_half << 32));
+    const int S = ec_split(M);
+    const unsigned long long lowmask = S >= 63 ? ~0ull : ((2ull << S) - 1ull);
+    unsigned long long mine;
+    bool active = true;
+    if (part == 0) {
+        mine = M & lowmask;
+        eob = (S >= 63);
+    } else {
+        mine = M & ~lowmask;
+        const unsigned long long before = M & lowmask;
+        prev = before ? 63 - __clzll((long long)before) : 0;
+        if (S >= 63) active = false; /* part 0 codes the whole block */
+    }
+    mm[0] = (uint32_t)mine;
+    mm[1] = (uint32_t)(mine >> 32);
+    return active;
+}
+
+/* codes of one entry from its masks: the DC difference (do_dc), the coefficients whose bits are set in mm, the
+ * end-of-block code (eob, unless position 63 is coded).  Tables are HuffPack words; lut = HuffPack::lut[table]. */
+template <class Sink>
+__device__ __forceinline__ void ec_pack_masked(const uint4 *row, bool do_dc, int diff, const uint32_t (&mm)[2], int prev, bool eob,
+                                               const uint32_t *sAc, const uint32_t *sDc, const uint32_t *lut, Sink &s)
+{
+    if (do_dc) {
         const int cat = diff == 0 ? 0 : msb_index((uint32_t)abs(diff)) + 1;
         const uint32_t e = sDc[cat];
         const uint32_t extra = (uint32_t)(diff - (diff < 0 ? 1 : 0)) & ((1u << cat) - 1u);
@@ -397,6 +409,12 @@ __device__ __forceinline__ void ec_pack_part(const uint4 *row, int diff, int par
             const int v = ec_coef(row, k);
             int run = k - prev - 1;
             prev = k;
+            const unsigned u = (unsigned)(v + 4);
+            if (run < 16 && u - 1u < 7u) { /* |v| <= 3: one table word holds code, additional bits and length */
+                const uint32_t e = lut[((unsigned)run << 3) + u];
+                s.put(e >> 5, (int)(e & 31u));
+                continue;
+            }
             if (run > 15) { /* rare: one ZRL code per 16 zeros */
                 const uint32_t zrl = sAc[0xF0];
                 do {
@@ -598,7 +616,7 @@ struct KeCfg {
     static const bool SPLIT = (RATIO != 2);              /* two lanes per luma block (4:2:0 has four luma blocks per MCU already) */
     static const int NT = (SPLIT ? 2 : 1) * NY + 128;    /* threads = entries: 256 / 384 / 384 */
     static const int EPM = (RATIO == 0) ? 4 : 6;         /* entries per MCU */
-    static const int PRIV = 12;                          /* words of private stream per entry */
+    static const int PRIV = 10;                          /* words of private stream per entry (with the tables: 5 CTAs per SM) */
     static const int PSTRIDE = PRIV + 1;                 /* odd: lanes hit distinct banks */
     static const int ROW_BYTES = ROWS * EC_ROW_CHUNKS * 16;
     static const int STAGE_WORDS = ROW_BYTES / 4;        /* the chunk stream reuses the coefficient rows */
@@ -669,16 +687,6 @@ struct KeMap {
     }
 };
 
-template <int RATIO, class Sink>
-__device__ __forceinline__ void ke_code(const uint4 (*sC)[EC_ROW_CHUNKS], const KeMap<RATIO> &mp, int diff, const HuffPack &sH,
-                                        Sink &s)
-{
-    if (mp.luma && KeCfg<RATIO>::SPLIT)
-        ec_pack_part<false>(sC[mp.row], diff, mp.part, sH.ac[0], sH.dc[0], s);
-    else
-        ec_pack_part<true>(sC[mp.row], diff, 0, sH.ac[mp.luma ? 0 : 1], sH.dc[mp.luma ? 0 : 1], s);
-}
-
 template <int RATIO>
 __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KeParams q0, const HuffPack *huff)
 {
@@ -726,6 +734,17 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     uint32_t nbits = 0;
     int diff = 0;
     uint32_t *priv = sP + tid * L::PSTRIDE;
+    /* masks first, by every lane: the two lanes of a split luma block swap their halves by shuffle */
+    uint32_t mm[2] = {0u, 0u};
+    int prev0 = 0;
+    bool eob = true, active;
+    const bool split = mp.luma && L::SPLIT; /* warp-uniform: warps are component-pure */
+    if (split)
+        active = ec_entry_masks<false>(sC[mp.row], mp.part, mm, prev0, eob);
+    else
+        active = ec_entry_masks<true>(sC[mp.row], 0, mm, prev0, eob);
+    active = active && mp.valid;
+    const uint32_t *tAc = sH.ac[mp.luma ? 0 : 1], *tDc = sH.dc[mp.luma ? 0 : 1], *tLut = sH.lut[mp.luma ? 0 : 1];
     if (mp.valid) {
         if (mp.part == 0) {
             int pred;
@@ -737,13 +756,15 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
                 pred = (int)p.zz[(mp.gabs - 1) * 64];
             diff = (int)(short)(sC[mp.row][0].x & 0xffffu) - pred;
         }
+    }
+    if (active) {
         PrivSink s;
         s.acc = 0;
         s.nacc = 0;
         s.wp = priv;
         s.end = priv + L::PRIV;
         s.nwords = 0;
-        ke_code<RATIO>(sC, mp, diff, sH, s);
+        ec_pack_masked(sC[mp.row], mp.part == 0, diff, mm, prev0, eob, tAc, tDc, tLut, s);
         nbits = s.finish();
         if (nbits > (uint32_t)L::PRIV * 32u) *sFlag = 1u;
     }
@@ -770,7 +791,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
         /* the chunk stream takes the place of the (dead) coefficient rows */
         for (uint32_t i = tid; i < nwords + 1u; i += NT) sS[i] = 0u;
         __syncthreads();
-        if (mp.valid) {
+        if (active) {
             const uint32_t sh = loff & 31u, nw = (nbits + 31u) >> 5;
             uint32_t *dst = sS + (loff >> 5);
             for (uint32_t i = 0; i < nw; i++) {
@@ -788,13 +809,13 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     /* rare: straight into the slot */
     for (uint32_t i = tid; i < nwords; i += NT) slot[i] = 0u;
     __syncthreads();
-    if (mp.valid) {
+    if (active) {
         PackSink<false> s;
         s.acc = 0;
         s.nacc = (int)(loff & 31u);
         s.wp = slot + (loff >> 5);
         s.first = true;
-        ke_code<RATIO>(sC, mp, diff, sH, s);
+        ec_pack_masked(sC[mp.row], mp.part == 0, diff, mm, prev0, eob, tAc, tDc, tLut, s);
         s.finish();
     }
     __syncthreads();

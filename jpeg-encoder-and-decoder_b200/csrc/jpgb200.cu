@@ -329,6 +329,15 @@ static void build_huff_pack(const HuffDev *h, HuffPack *k)
             const uint32_t c = (sym == 0xF0) ? 0u : (uint32_t)(sym & 15);
             if (len) k->ac[t][sym] = (((e >> 8) << c) << 5) | (len + c);
         }
+        /* small values: the word of (run, category) with the additional bits of the value merged */
+        for (int run = 0; run < 16; run++)
+            for (int v = -3; v <= 3; v++) {
+                if (v == 0) continue;
+                const int av = v < 0 ? -v : v, c = av == 1 ? 1 : 2;
+                const uint32_t extra = (uint32_t)(v - (v < 0 ? 1 : 0)) & ((1u << c) - 1u);
+                const uint32_t w = k->ac[t][(run << 4) | c];
+                k->lut[t][run * 8 + v + 4] = w ? (w | (extra << 5)) : 0u;
+            }
     }
 }
 
@@ -2534,6 +2543,21 @@ extern "C" int jpgb200_encode_coefficients(jpgb200_ctx *ctx, const int16_t *zz, 
     ctx->ratio = ratio;
     memcpy(ctx->n, n, sizeof n);
     CK(cudaMemcpyAsync(ctx->d_zz, zz, (size_t)(n[0] + n[1] + n[2]) * 128, cudaMemcpyHostToDevice, ctx->stream));
+    {
+        /* the entropy kernels index their tables with the categories: refuse what a quantiser cannot produce */
+        int bad = 0;
+        CK(cudaMemsetAsync(ctx->d_freq, 0, sizeof(int), ctx->stream));
+        const long long nb = n[0] + n[1] + n[2];
+        k_validate_coefs<<<(unsigned)((nb + 255) / 256), 256, 0, ctx->stream>>>(ctx->d_zz, n[0], n[1], n[2], ctx->d_freq);
+        ctx->launch_total++;
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(&bad, ctx->d_freq, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaStreamSynchronize(ctx->stream));
+        if (bad) {
+            snprintf(ctx->err, sizeof ctx->err, "coefficients out of range: AC must be in [-1023, 1023], DC differences in [-2047, 2047]");
+            return JPGB200_ERR_BAD_ARG;
+        }
+    }
     if (ctx->opt_huff && (rc = optimise_tables(ctx, w, h, quality, ratio))) return rc;
     if (ctx->legacy_entropy || ratio == 2) {
         if ((rc = launch_bits(ctx, ctx->d_zz, ratio, n, NULL, true))) return rc;

@@ -369,6 +369,37 @@ __global__ void __launch_bounds__(256) ks_synth(uint8_t *planes, int w, int h, u
     }
 }
 
+/* Range check of caller-supplied coefficients (jpgb200_encode_coefficients, the staged huffman_encode): the
+ * entropy kernels assume what K1 guarantees -- AC categories <= 10 and DC-difference categories <= 11 (T.81 tables
+ * F.1 / F.2) -- and index their code tables with them.  One thread per block; *bad becomes 1 on any violation. */
+__global__ void __launch_bounds__(256) k_validate_coefs(const int16_t *zz, long long n0, long long n1, long long n2, int *bad)
+{
+    const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x, nb = n0 + n1 + n2;
+    if (i >= nb) return;
+    const uint4 *row = reinterpret_cast<const uint4 *>(zz + i * 64);
+    bool ok = true;
+    int dc = 0;
+#pragma unroll
+    for (int j = 0; j < 8; j++) {
+        const uint4 v = row[j];
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            const int lo = (int)(short)(w[k] & 0xffffu), hi = (int)(short)(w[k] >> 16);
+            if (j == 0 && k == 0)
+                dc = lo;
+            else
+                ok = ok && lo >= -1023 && lo <= 1023;
+            ok = ok && hi >= -1023 && hi <= 1023;
+        }
+    }
+    const bool first = (i == 0 || i == n0 || i == n0 + n1);
+    const int prev = first ? 0 : (int)zz[(i - 1) * 64];
+    const int diff = dc - prev;
+    ok = ok && diff >= -2047 && diff <= 2047;
+    if (!ok) *bad = 1;
+}
+
 /* interleaved RGB24 -> planes (for encode_rgb_to_jpeg_ex) */
 __global__ void __launch_bounds__(256) ks_deinterleave(const uint8_t *rgb, uint8_t *r, uint8_t *g, uint8_t *b,
                                                        long long npx)

@@ -24,6 +24,16 @@ static int write_file(const char *path, const unsigned char *data, size_t len)
     return w == len ? JPGB200_OK : JPGB200_ERR_BAD_ARG;
 }
 
+/* Output capacity: a first guess of 3 B/pixel (a natural image needs ~0.3) and, when the library answers
+ * JPGB200_ERR_OUT_TOO_SMALL (noise at the highest qualities codes to 4 B/pixel and more), the true worst case:
+ * every block at its longest (1658 bits: a 20-bit DC code + 63 x 26-bit AC codes) and every byte stuffed. */
+static size_t out_cap(int w, int h, int attempt)
+{
+    const size_t pw = (size_t)(w + 15) / 16 * 16, ph = (size_t)(h + 15) / 16 * 16;
+    if (attempt == 0) return pw * ph * 3 + 65536;
+    return 1024 + (pw / 8) * (ph / 8) * 3 * ((1658 + 7) / 8) * 2 + 2;
+}
+
 int encode_bmp_to_jpeg_status(const char *input, const char *output, int quality, int sample_ratio)
 {
     jpgb200_ctx *ctx = host_ctx();
@@ -37,12 +47,17 @@ int encode_bmp_to_jpeg_status(const char *input, const char *output, int quality
         return e;
     }
     const int w = bmp_GetWidth(bmp), h = bmp_GetHeight(bmp);
-    const size_t cap = (size_t)w * h * 3 + 65536;
-    unsigned char *out = (unsigned char *)malloc(cap);
+    unsigned char *out = NULL;
     size_t len = 0;
-    int rc = out ? jpgb200_encode_planar(ctx, bmp_GetRed(bmp), bmp_GetGreen(bmp), bmp_GetBlue(bmp), w, h, quality,
-                                         sample_ratio, out, cap, &len)
+    int rc = JPGB200_ERR_OUT_TOO_SMALL;
+    for (int attempt = 0; attempt < 2 && rc == JPGB200_ERR_OUT_TOO_SMALL; attempt++) {
+        const size_t cap = out_cap(w, h, attempt);
+        free(out);
+        out = (unsigned char *)malloc(cap);
+        rc = out ? jpgb200_encode_planar(ctx, bmp_GetRed(bmp), bmp_GetGreen(bmp), bmp_GetBlue(bmp), w, h, quality, sample_ratio, out,
+                                         cap, &len)
                  : JPGB200_ERR_NOMEM;
+    }
     bmp_DestroyBitmap(bmp);
     if (rc == JPGB200_OK) rc = write_file(output, out, len);
     free(out);
@@ -65,11 +80,17 @@ int encode_bmp_to_jpeg_robust(const char *input, const char *output, int quality
         return e;
     }
     const int w = bmp_GetWidth(bmp), h = bmp_GetHeight(bmp);
-    const size_t cap = (size_t)(w + 16) * (h + 8) * 3 + 65536;
-    unsigned char *out = (unsigned char *)malloc(cap);
+    unsigned char *out = NULL;
     size_t len = 0;
-    int rc = out ? JPGB200_OK : JPGB200_ERR_NOMEM;
-    if (rc == JPGB200_OK) {
+    int rc = JPGB200_ERR_OUT_TOO_SMALL;
+    for (int attempt = 0; attempt < 2 && rc == JPGB200_ERR_OUT_TOO_SMALL; attempt++) {
+        const size_t cap = out_cap(w, h, attempt);
+        free(out);
+        out = (unsigned char *)malloc(cap);
+        if (!out) {
+            rc = JPGB200_ERR_NOMEM;
+            break;
+        }
         jpgb200_set_standard_mode(ctx, 1);
         rc = jpgb200_encode_planar_any(ctx, bmp_GetRed(bmp), bmp_GetGreen(bmp), bmp_GetBlue(bmp), w, h, quality, sample_ratio,
                                        out, cap, &len);
@@ -91,10 +112,15 @@ int encode_rgb_to_jpeg_ex(const Byte *rgb, int width, int height, const char *ou
 {
     jpgb200_ctx *ctx = host_ctx();
     if (!ctx) return JPGB200_ERR_NO_DEVICE;
-    const size_t cap = (size_t)width * height * 3 + 65536;
-    unsigned char *out = (unsigned char *)malloc(cap);
+    unsigned char *out = NULL;
     size_t len = 0;
-    int rc = out ? jpgb200_encode_rgb(ctx, rgb, width, height, quality, sample_ratio, out, cap, &len) : JPGB200_ERR_NOMEM;
+    int rc = JPGB200_ERR_OUT_TOO_SMALL;
+    for (int attempt = 0; attempt < 2 && rc == JPGB200_ERR_OUT_TOO_SMALL; attempt++) {
+        const size_t cap = out_cap(width, height, attempt);
+        free(out);
+        out = (unsigned char *)malloc(cap);
+        rc = out ? jpgb200_encode_rgb(ctx, rgb, width, height, quality, sample_ratio, out, cap, &len) : JPGB200_ERR_NOMEM;
+    }
     if (rc == JPGB200_OK) rc = write_file(output, out, len);
     free(out);
     return rc;

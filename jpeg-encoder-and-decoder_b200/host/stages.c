@@ -305,7 +305,8 @@ void huffman_encode(JpgData j)
     /* the byte stream the reference never gets to: standard tables, true DC differences */
     const size_t nb = (size_t)j->num_blocks_Y + j->num_blocks_Cb + j->num_blocks_Cr;
     int16_t *zz = (int16_t *)malloc(nb * 64 * sizeof(int16_t));
-    const size_t cap = (size_t)j->width * j->height * 3 + 65536;
+    /* worst case: every block at its longest (1658 bits) and every byte stuffed */
+    const size_t cap = 1024 + nb * ((1658 + 7) / 8) * 2 + 2;
     unsigned char *out = (unsigned char *)malloc(cap);
     if (zz && out) {
         pack_comp(zz, j->zig_zag_Y, j->num_blocks_Y);

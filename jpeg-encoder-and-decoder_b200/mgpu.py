@@ -69,34 +69,61 @@ def encode_partitioned(engine, band_ptrs, width, band_height, quality, ratio, he
     returns   : total stream length on rank 0, this rank's segment length elsewhere
     """
     rank, world = dist.get_rank(group), dist.get_world_size(group)
-    last_dc = engine.band_transform(band_ptrs[0], band_ptrs[1], band_ptrs[2], width, band_height, rank > 0, quality, ratio)
-    g0 = _allgather_i64(dist, list(last_dc), device, group)          # exchange 0: DC predictors
+
+    def grank(k):  # send/recv take GLOBAL ranks also when `group` is a sub-group
+        return dist.get_global_rank(group, k) if group is not None and hasattr(dist, "get_global_rank") else k
+
+    # Every exchange also carries a status word, so that a rank whose engine call failed cannot leave its peers
+    # blocked in a collective or a recv: everybody sees the failure in the same allgather and raises.
+    err = None
+
+    def step(fn, fallback):
+        nonlocal err
+        if err is not None:
+            return fallback
+        try:
+            return fn()
+        except Exception as exc:  # noqa: BLE001 -- reported to every rank below
+            err = exc
+            return fallback
+
+    def exchange(values):
+        got = _allgather_i64(dist, [0 if err is None else 1] + list(values), device, group)
+        bad = [k for k, g in enumerate(got) if g[0]]
+        if bad:
+            raise RuntimeError("encode_partitioned failed on rank(s) %s: %s" % (bad, err if err is not None else "see that rank"))
+        return [g[1:] for g in got]
+
+    last_dc = step(lambda: engine.band_transform(band_ptrs[0], band_ptrs[1], band_ptrs[2], width, band_height, rank > 0, quality,
+                                                 ratio), [0, 0, 0])
+    g0 = exchange(list(last_dc))                                      # exchange 0: DC predictors
     pred = g0[rank - 1] if rank > 0 else [0, 0, 0]
-    bits = engine.band_bits(pred)
-    g1 = _allgather_i64(dist, [bits], device, group)                 # exchange 1: bit offsets
+    bits = step(lambda: engine.band_bits(pred), 0)
+    g1 = exchange([bits])                                             # exchange 1: bit offsets
     bit_base = sum(g[0] for g in g1[:rank])
-    owned, tail = engine.band_pack(bit_base & 7, rank == world - 1)
-    g2 = _allgather_i64(dist, [tail], device, group)                 # exchange 2: boundary bytes
+    owned, tail = step(lambda: engine.band_pack(bit_base & 7, rank == world - 1), (0, 0))
+    g2 = exchange([tail])                                             # exchange 2: boundary bytes
     carry = g2[rank - 1][0] if rank > 0 else 0
-    seg_len = engine.band_finish(carry, segment.data_ptr(), segment.numel())
-    g3 = _allgather_i64(dist, [seg_len], device, group)              # exchange 3: byte offsets
+    seg_len = step(lambda: engine.band_finish(carry, segment.data_ptr(), segment.numel()), 0)
+    hl = header.numel()
+    cap0 = out.numel() if rank == 0 else 0
+    g3 = exchange([seg_len, cap0])                                    # exchange 3: byte offsets (+ rank 0's capacity)
     lens = [g[0] for g in g3]
+    total = hl + sum(lens) + 2
+    if total > g3[0][1]:  # checked on EVERY rank before any point-to-point call
+        raise ValueError("output buffer too small: need %d bytes" % total)
     if rank == 0:
-        hl = header.numel()
-        total = hl + sum(lens) + 2
-        if total > out.numel():
-            raise ValueError("output buffer too small: need %d bytes" % total)
         out[:hl].copy_(header)
         off = hl
         out[off:off + lens[0]].copy_(segment[:lens[0]])
         off += lens[0]
         for k in range(1, world):
             if lens[k]:
-                dist.recv(out[off:off + lens[k]], src=k, group=group)
+                dist.recv(out[off:off + lens[k]], src=grank(k), group=group)
             off += lens[k]
         out[off] = 0xFF
         out[off + 1] = 0xD9
         return total
     if seg_len:
-        dist.send(segment[:seg_len], dst=0, group=group)
+        dist.send(segment[:seg_len], dst=grank(0), group=group)
     return seg_len

@@ -124,3 +124,27 @@ def test_product_never_touches_the_oracle():
                 assert "oracle_lib" not in text and "libjpgb200_oracle" not in text and "orc_" not in text, f
     text = open(os.path.join(ROOT, "include", "jpgb200.h")).read()
     assert "orc_" not in text
+
+
+def test_reference_driver_source_links_against_the_product(built):
+    """The drop-in claim at the source level: the reference's OWN src/jpg_driver.c, unmodified and compiled
+    where it lies, builds against host/headers and links with libjpgenc.so + libjpgb200.so in place of the
+    reference's stage files (oracle/Makefile target `driver`).  Without a GPU the binary must stop with the
+    library's "no CPU fallback" message instead of computing anything; the GPU run is in tests/test_gpu_multi.py."""
+    ref_src = "/root/reference/src/jpg_driver.c"
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver_b200")
+    if os.path.exists(ref_src):
+        subprocess.check_call(["make", "-s", "-C", os.path.join(ROOT, "oracle"), "driver"])
+    if not os.path.exists(exe):
+        pytest.skip("reference sources not present and no prebuilt oracle/_ref/ref_driver_b200")
+    undefined = subprocess.check_output(["nm", "-D", "--undefined-only", exe], text=True)
+    for sym in ("dct_block", "quantise_lum", "zig_zag_block", "new_block", "set_value_block"):
+        assert sym in undefined, "the driver must take %s from the product library" % sym
+    ldd = subprocess.check_output(["ldd", exe], text=True)
+    assert "libjpgenc.so" in ldd and "libjpgb200.so" in ldd and "not found" not in ldd
+    import ctypes
+
+    L = ctypes.CDLL(os.path.join(PKG, "libjpgb200.so"))
+    if L.jpgb200_device_count() == 0:
+        r = subprocess.run([exe], capture_output=True, text=True, timeout=60)
+        assert "no CPU fallback" in (r.stdout + r.stderr)

@@ -75,3 +75,52 @@ def test_plan_bands_and_frame_sharding():
     for n, world in [(256, 8), (10, 4), (3, 8)]:
         seen = sorted(f for r in range(world) for f in mg.shard_frames(n, r, world))
         assert seen == list(range(n))
+
+
+def _failing_worker(rank, world, port, mode, result_dir):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import torch
+    import torch.distributed as dist
+
+    import __graft_entry__ as ge
+    import oracle_lib as O
+    from band_double import OracleBandEngine
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    pkg = ge.load_package()
+    mg = pkg.mgpu
+    w, h, q, ratio = 64, 48, 75, 0
+    planes = O.synth_planes(w, h, 77, 0, 0)
+    row0, bh = mg.plan_bands(h, world)[rank]
+    eng = OracleBandEngine(planes, w, h, q, ratio, row0, bh)
+    if mode == "engine" and rank == 1:
+        def boom(pred):
+            raise RuntimeError("engine failure on purpose")
+        eng.band_bits = boom
+    header = torch.from_numpy(pkg.binding.jfif_header(w, h, q, ratio))
+    segment = torch.zeros(w * bh * 3 + 4096, dtype=torch.uint8)
+    out = torch.zeros(700 if mode == "small" else w * h * 3 + 4096, dtype=torch.uint8) if rank == 0 else None
+    what = "no error"
+    try:
+        mg.encode_partitioned(eng, (0, 0, 0), w, bh, q, ratio, header, segment, out, dist, torch.device("cpu"))
+    except (RuntimeError, ValueError) as exc:
+        what = type(exc).__name__
+    open(os.path.join(result_dir, "r%d.txt" % rank), "w").write(what)
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("mode,expect", [("engine", "RuntimeError"), ("small", "ValueError")])
+def test_partition_failure_reaches_every_rank(tmp_path, mode, expect):
+    """A failing engine call on one rank, or an output buffer too small on rank 0, must raise on EVERY rank
+    instead of leaving the others blocked in an allgather or a send (the status word of each exchange)."""
+    import torch.multiprocessing as mp
+
+    world = 3
+    port = 29500 + (os.getpid() % 2000) + 17
+    mp.spawn(_failing_worker, args=(world, port, mode, str(tmp_path)), nprocs=world, join=True)
+    for r in range(world):
+        assert open(str(tmp_path / ("r%d.txt" % r))).read() == expect

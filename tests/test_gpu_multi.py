@@ -101,6 +101,31 @@ def test_driver_executable_known_answer_and_file_encode(tmp_path):
     assert abs(int(fused.size) - int(want.size)) < 64
 
 
+def test_reference_driver_source_runs_on_the_product():
+    """oracle/_ref/ref_driver_b200 = the reference's own, unmodified src/jpg_driver.c linked with libjpgenc.so +
+    libjpgb200.so (oracle/Makefile `driver`): its test_dct() walk runs every stage on the GPU and must print what
+    the all-reference build printed (tests/golden/test_dct_stdout.txt)."""
+    exe = os.path.join(ROOT, "oracle", "_ref", "ref_driver_b200")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/ref_driver_b200 not built (no reference sources in the build container)")
+    got = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert got.returncode == 0, got.stderr
+
+    def nums(text):
+        out = []
+        for t in text.split():
+            try:
+                out.append(float(t))
+            except ValueError:
+                pass
+        return np.array(out)
+
+    a, b = nums(got.stdout), nums(open(os.path.join(GOLDEN, "test_dct_stdout.txt")).read())
+    assert a.shape == b.shape == (256,)
+    assert np.abs(a - b).max() <= 0.011  # two printed decimals
+    assert (a[192:] == b[192:]).all()    # the zig-zag integers: exact
+
+
 def test_staged_stage_kernels_match_reference_stages(enc):
     """GPU-backed preprocess / subsample / dpcm / histogram stages vs the golden dumps."""
     d = np.load(os.path.join(GOLDEN, "tiger_q50.npz"))
