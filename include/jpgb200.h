@@ -78,6 +78,10 @@ int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on);
  * kernels with the int16 coefficients in HBM between them.  Identical bytes.  K1E needs width % 16 == 0, 4:4:4 or 4:2:2 and the tables.h Huffman tables; other
  * cases (4:2:0, per-image optimal tables, the parity taps, the MCU-row bands) take the separate kernels. */
 int jpgb200_set_fused_transform(jpgb200_ctx *ctx, int on);
+/* jpgb200_encode_batch_device on large frames: 1 (default) = three streams -- K1 of frame f+1 (high
+ * priority), KE of frame f and the tails of frame f-1 are in flight together, two coefficient buffers
+ * alternate; 0 = K1 and KE one after the other with only the tails overlapped.  Identical bytes. */
+int jpgb200_set_pipelined_batch(jpgb200_ctx *ctx, int on);
 /* jpgb200_encode_batch_device on frames of up to 4096x2304: 1 (default) = groups of frames share
  * each kernel launch (K1's tile index and the entropy kernels' blockIdx.y run over the frames of a
  * group of about one 8K frame's worth of pixels); 0 = four launches per frame.  Identical bytes. */

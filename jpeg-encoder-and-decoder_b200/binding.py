@@ -39,6 +39,7 @@ _SIGS = {
     "jpgb200_set_fused_transform": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_fused_tap": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_frame_groups": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_set_pipelined_batch": (C.c_int, [_vp, C.c_int]),
     "jpgb200_last_coefficients": (C.c_int, [_vp, _vp]),
     "jpgb200_huffman_specs": (C.c_int, [_vp, _vp, _vp, _vp]),
     "jpgb200_encode_planar": (C.c_int, [_vp, _vp, _vp, _vp, C.c_int, C.c_int, C.c_int, C.c_int, _vp, C.c_size_t, C.POINTER(C.c_size_t)]),
@@ -228,6 +229,10 @@ class Encoder:
     def set_fused_transform(self, on):
         """K1E (transform + chunk encode in one kernel, the default) on/off"""
         self._ck(lib().jpgb200_set_fused_transform(self._h, 1 if on else 0))
+
+    def set_pipelined_batch(self, on):
+        """K1 of frame f+1 beside KE of frame f (three streams, two coefficient buffers)"""
+        self._ck(lib().jpgb200_set_pipelined_batch(self._h, 1 if on else 0))
 
     def set_frame_groups(self, on):
         """multi-frame launches for batches of small frames (default on)"""

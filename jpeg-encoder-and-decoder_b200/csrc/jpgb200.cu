@@ -93,9 +93,12 @@ struct jpgb200_ctx {
     bool k1_ws;    /* the warp-autonomous K1 (k1_warp.cuh) */
     bool k1c_attr_set;
     bool no_tma_store; /* k1_pipe: copy the coefficients out with ordinary stores (A/B runs) */
-    CUtensorMap tm32, tm16; /* tensor maps of the coefficient buffer, cached */
+    CUtensorMap tm32, tm16; /* tensor maps of the coefficient buffer, cached (two entries: the pipelined batch alternates buffers) */
     int16_t *tm_ptr;
     long long tm_rows;
+    CUtensorMap tm32_b, tm16_b;
+    int16_t *tm_ptr_b;
+    long long tm_rows_b;
     bool k1_cta;   /* force the CTA-barrier TMA K1 instead of the warp-autonomous one (tests, A/B runs) */
     EncState *d_state;
     uint8_t *d_header;
@@ -144,6 +147,10 @@ struct jpgb200_ctx {
     bool legacy_entropy; /* staged KE/KF/KS pipeline (default) instead of the single-launch K35 */
     bool fused_k1e;      /* K1E: transform + chunk encode in one kernel, coefficients stay on chip (default) */
     int k1e_per_sm[4];   /* resident CTAs per SM of k1e_fused<RATIO, STD>, 0 = not yet queried */
+    int k1_ctas_per_sm;  /* persistent K1 CTAs per SM: 0 = as many as fit (2); the pipelined batch uses 1 and leaves room for KE */
+    bool pipelined;      /* jpgb200_encode_batch_device: K1 of frame f+1 runs beside KE of frame f (three streams) */
+    cudaStream_t k1_stream, ke_stream;
+    cudaEvent_t ev_k1[2], ev_ked[2], ev_start;
     bool group_small;    /* jpgb200_encode_batch_device: multi-frame launches for small frames (default on) */
     bool k1e_tap;        /* K1E also writes the coefficients to HBM (jpgb200_set_fused_tap) */
     unsigned long long *d_dc_pub; /* K1E: last DC per tile and component, {epoch, DC} words */
@@ -459,6 +466,12 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
     ctx->legacy_entropy = true; /* measured faster than the fused K35 so far */
     ctx->k1_pc = true;          /* K1 default: the producer/consumer form (fastest measured) */
     ctx->group_small = true;
+    {
+        const char *pz = getenv("JPGB200_PIPELINED"); /* "0": K1 and KE of a batch strictly one after the other */
+        ctx->pipelined = !(pz && !strcmp(pz, "0"));
+        const char *cz = getenv("JPGB200_K1_CTAS");
+        ctx->k1_ctas_per_sm = cz ? atoi(cz) : 0;
+    }
     ctx->fused_k1e = false;     /* transform + chunk encode in one kernel (k1_fused.cuh): measured slower than K1 -> KE so far */
     {
         const char *fz = getenv("JPGB200_FUSED"); /* "1": K1E instead of K1 and KE as separate kernels (A/B runs) */
@@ -498,6 +511,17 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking));
+        {
+            int lo = 0, hi = 0;
+            CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            CK(cudaStreamCreateWithPriority(&ctx->k1_stream, cudaStreamNonBlocking, hi)); /* K1's few persistent CTAs go first */
+            CK(cudaStreamCreateWithPriority(&ctx->ke_stream, cudaStreamNonBlocking, lo));
+            for (int sl = 0; sl < 2; sl++) {
+                CK(cudaEventCreateWithFlags(&ctx->ev_k1[sl], cudaEventDisableTiming));
+                CK(cudaEventCreateWithFlags(&ctx->ev_ked[sl], cudaEventDisableTiming));
+            }
+            CK(cudaEventCreateWithFlags(&ctx->ev_start, cudaEventDisableTiming));
+        }
         CK(cudaEventCreateWithFlags(&ctx->ev_ke, cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_ks[0], cudaEventDisableTiming));
         CK(cudaEventCreateWithFlags(&ctx->ev_ks[1], cudaEventDisableTiming));
@@ -553,6 +577,13 @@ extern "C" void jpgb200_destroy(jpgb200_ctx *ctx)
     cudaStreamDestroy(ctx->copy_in);
     cudaStreamDestroy(ctx->copy_out);
     cudaStreamDestroy(ctx->tail_stream);
+    cudaStreamDestroy(ctx->k1_stream);
+    cudaStreamDestroy(ctx->ke_stream);
+    cudaEventDestroy(ctx->ev_start);
+    for (int sl = 0; sl < 2; sl++) {
+        cudaEventDestroy(ctx->ev_k1[sl]);
+        cudaEventDestroy(ctx->ev_ked[sl]);
+    }
     cudaEventDestroy(ctx->ev_ke);
     cudaEventDestroy(ctx->ev_ks[0]);
     cudaEventDestroy(ctx->ev_ks[1]);
@@ -608,6 +639,13 @@ extern "C" int jpgb200_set_fused_transform(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;
     ctx->fused_k1e = on != 0;
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_set_pipelined_batch(jpgb200_ctx *ctx, int on)
+{
+    if (!ctx) return JPGB200_ERR_BAD_ARG;
+    ctx->pipelined = on != 0;
     return JPGB200_OK;
 }
 
@@ -931,6 +969,18 @@ static void make_store_maps(jpgb200_ctx *ctx, K1PStore *st, int16_t *zz, const l
         st->enabled = 1;
         return;
     }
+    if (ctx->tm_ptr_b == zz && ctx->tm_rows_b == rows) {
+        st->box32 = ctx->tm32_b;
+        st->box16 = ctx->tm16_b;
+        st->enabled = 1;
+        return;
+    }
+    /* the older entry moves to the second slot */
+    ctx->tm32_b = ctx->tm32;
+    ctx->tm16_b = ctx->tm16;
+    ctx->tm_ptr_b = ctx->tm_ptr;
+    ctx->tm_rows_b = ctx->tm_rows;
+    ctx->tm_ptr = NULL;
     static EncodeTiledFn fn = NULL;
     static bool tried = false;
     if (!tried) {
@@ -1010,7 +1060,7 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
             ctx->k1c_attr_set = true;
         }
         const long long n_tiles = (long long)p.tiles_per_row * (h / 8) * nframes;
-        const long long resident = (long long)ctx->sm_count * K1C_MIN_CTAS;
+        const long long resident = (long long)ctx->sm_count * (ctx->k1_ctas_per_sm > 0 ? ctx->k1_ctas_per_sm : K1C_MIN_CTAS);
         const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
         K1PStore st;
         make_store_maps(ctx, &st, zz, n, zz_stride, nframes);
@@ -1555,6 +1605,76 @@ static int encode_group(jpgb200_ctx *ctx, const uint8_t *d_planes, int G, int w,
     return JPGB200_OK;
 }
 
+/* Batch, pipelined over three streams: K1 of frame f+1 (persistent CTAs, high priority) is in flight together with
+ * KE of frame f and the tails of frame f-1.  Two coefficient buffers and two sets of entropy workspaces alternate
+ * with the frame parity.  K1's CTAs fill the register files, so the kernels mostly take turns -- what the pipeline
+ * removes are the bubbles: KE's CTAs start on every SM the moment K1's persistent CTAs retire from it and the next
+ * K1 moves in as KE drains (measured: 181 us per 8K frame against 192 us; with K1 held to ONE CTA per SM, so that
+ * KE's CTAs run beside it, both kernels slow down by more than the overlap gives: 213 us). */
+static int encode_batch_pipelined(jpgb200_ctx *ctx, const uint8_t *d_planes, int n_frames, int w, int h, int quality, int ratio,
+                                  uint8_t *d_out, size_t out_stride, unsigned long long *d_lens)
+{
+    long long n[3];
+    int rc = validate(w, h, quality, ratio, n);
+    if (rc) return rc;
+    const size_t npx = (size_t)w * h;
+    const long long nb = n[0] + n[1] + n[2];
+    cudaStream_t user = ctx->stream;
+    /* both parities' workspaces exist before anything is enqueued (growing one synchronises) */
+    for (int k = 0; k < 2; k++) {
+        swap_entropy_ws(ctx);
+        if ((rc = ensure_workspace(ctx, n, 2))) return rc; /* d_zz: two frames */
+    }
+    if ((rc = ensure_tables(ctx, w, h, quality, ratio))) return rc;
+    ctx->w = w;
+    ctx->h = h;
+    ctx->q = quality;
+    ctx->ratio = ratio;
+    memcpy(ctx->n, n, sizeof n);
+    CK(cudaEventRecord(ctx->ev_start, user));
+    CK(cudaStreamWaitEvent(ctx->k1_stream, ctx->ev_start, 0));
+    CK(cudaStreamWaitEvent(ctx->ke_stream, ctx->ev_start, 0));
+    CK(cudaStreamWaitEvent(ctx->tail_stream, ctx->ev_start, 0));
+    ctx->in_batch = true;
+    for (int f = 0; f < n_frames && rc == JPGB200_OK; f++) {
+        swap_entropy_ws(ctx);
+        const int par = ctx->ws_parity;
+        int16_t *zz = ctx->d_zz + (size_t)par * (size_t)nb * 64;
+        const uint8_t *pl = d_planes + (size_t)f * 3 * npx;
+        /* K1(f): its coefficient buffer was last read by KE(f-2), its two-level sums by the tails of frame f-2 */
+        if (f >= 2) {
+            CK(cudaStreamWaitEvent(ctx->k1_stream, ctx->ev_ked[par], 0));
+            CK(cudaStreamWaitEvent(ctx->k1_stream, ctx->ev_ks[par], 0));
+        }
+        ctx->stream = ctx->k1_stream;
+        rc = launch_k1(ctx, pl, pl + npx, pl + 2 * npx, w, h, ratio, n, 1, 0, zz, 0, 0);
+        if (rc) break;
+        CK(cudaEventRecord(ctx->ev_k1[par], ctx->k1_stream));
+        /* KE(f) */
+        CK(cudaStreamWaitEvent(ctx->ke_stream, ctx->ev_k1[par], 0));
+        ctx->stream = ctx->ke_stream;
+        rc = launch_bits(ctx, zz, ratio, n);
+        if (rc) break;
+        CK(cudaEventRecord(ctx->ev_ked[par], ctx->ke_stream));
+        /* KF, KS (f) */
+        CK(cudaStreamWaitEvent(ctx->tail_stream, ctx->ev_ked[par], 0));
+        ctx->stream = ctx->tail_stream;
+        ctx->overlap_now = false;
+        rc = launch_tail(ctx, n, 0u, 0u, 1, ctx->hdr_len, 1, d_out + (size_t)f * out_stride, out_stride, d_lens ? d_lens + f : ctx->d_len);
+        if (rc) break;
+        CK(cudaEventRecord(ctx->ev_ks[par], ctx->tail_stream));
+    }
+    ctx->stream = user;
+    ctx->in_batch = false;
+    ctx->have_bits = false;
+    /* the caller's stream order is kept: it continues when the last tails are done */
+    cudaStreamWaitEvent(user, ctx->ev_ks[0], 0);
+    cudaStreamWaitEvent(user, ctx->ev_ks[1], 0);
+    cudaStreamWaitEvent(user, ctx->ev_ked[0], 0);
+    cudaStreamWaitEvent(user, ctx->ev_ked[1], 0);
+    return rc;
+}
+
 /* frames per multi-frame launch group: about one 8K frame's worth of pixels, 1 = frame-by-frame */
 static int group_frames(const jpgb200_ctx *ctx, int n_frames, int w, int h)
 {
@@ -1598,6 +1718,8 @@ extern "C" int jpgb200_encode_batch_device(jpgb200_ctx *ctx, const uint8_t *d_pl
             return rc;
         }
     }
+    if (ctx->pipelined && ctx->legacy_entropy && !ctx->opt_huff && !ctx->fused_k1e && ratio != 2 && n_frames >= 3 && (w % 16 == 0))
+        return encode_batch_pipelined(ctx, d_planes, n_frames, w, h, quality, ratio, d_out, out_stride, d_lens);
     /* Overlap (default): frame f's tail (KF, KS: small, latency-bound) runs on a second stream
      * beside frame f+1's KE (it is launched behind frame f+1's K1, which fills the register files
      * and is better left alone: launched right behind KE it slowed K1 from 77 to 98 us).  The entropy

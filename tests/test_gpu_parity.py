@@ -655,3 +655,41 @@ def test_encode_coefficients_rejects_out_of_range_values(enc, pkg):
         with pytest.raises(pkg.binding.Jpgb200Error) as ei:
             enc.encode_coefficients(bad, w, h, 75, 0)
         assert ei.value.code == -6
+
+
+@pytest.mark.parametrize("w,h,ratio,nf", [(4096, 2320, 0, 5), (4112, 2304, 1, 4), (7680, 4320, 0, 3)])
+def test_pipelined_batch_is_invisible(enc, w, h, ratio, nf):
+    """jpgb200_set_pipelined_batch: K1 of frame f+1 beside KE of frame f on three streams, two coefficient buffers and
+    two sets of entropy workspaces alternating -- the same streams and lengths as the sequential batch, twice in a row
+    (the parities carry over), and as a single-frame encode."""
+    q, npx = 75, w * h
+    d_pl = enc.malloc(nf * 3 * npx)
+    cap = npx + 4096
+    d_out = enc.malloc(nf * cap)
+    d_len = enc.malloc(8 * nf)
+    try:
+        for f in range(nf):
+            enc.synth_device(d_pl + f * 3 * npx, w, h, 2468, f, 0)
+        enc.sync()
+        res = {}
+        for mode in ("pipe", "seq", "pipe2"):
+            enc.set_pipelined_batch(mode != "seq")
+            enc.h2d(d_len, np.zeros(8 * nf, np.uint8))
+            enc.encode_batch_device(d_pl, nf, w, h, q, ratio, d_out, cap, d_len)
+            enc.sync()
+            lens = enc.d2h(d_len, 8 * nf).view(np.uint64).copy()
+            outs = [enc.d2h(d_out + f * cap, int(lens[f])).copy() for f in range(nf)]
+            res[mode] = (lens, outs)
+        enc.set_pipelined_batch(True)
+        for mode in ("pipe", "pipe2"):
+            assert (res[mode][0] == res["seq"][0]).all(), mode
+            for f in range(nf):
+                assert (res[mode][1][f] == res["seq"][1][f]).all(), (mode, f)
+        planes = enc.d2h(d_pl + (nf - 1) * 3 * npx, 3 * npx).reshape(3, -1)
+        one = enc.encode_planar(planes[0], planes[1], planes[2], w, h, q, ratio)
+        assert one.size == int(res["pipe"][0][nf - 1]) and (one == res["pipe"][1][nf - 1]).all()
+    finally:
+        enc.set_pipelined_batch(True)
+        enc.free(d_pl)
+        enc.free(d_out)
+        enc.free(d_len)
