@@ -311,11 +311,13 @@ def run_b200(args):
     enc.reset_profile()
     enc.set_profiling(1)
     enc.set_batch_overlap(False)
+    enc.set_pipelined_batch(False)
     step()
     torch.cuda.synchronize()
     kbreak = enc.kernel_times()
     enc.set_profiling(0)
     enc.set_batch_overlap(os.environ.get("JPGB200_OVERLAP", "1") != "0")
+    enc.set_pipelined_batch(os.environ.get("JPGB200_PIPELINED", "1") != "0")
     ms_per_step = ms_total / args.steps
     value = world * F * NPX / (ms_per_step * 1e-3) / 1e6
     lens_host = lens.cpu().numpy()

@@ -66,6 +66,11 @@ const char *jpgb200_last_error(const jpgb200_ctx *ctx);
 /* Run on a caller-owned CUDA stream (cudaStream_t passed as void*); NULL = context's own. */
 int jpgb200_set_stream(jpgb200_ctx *ctx, void *cuda_stream);
 int jpgb200_sync(jpgb200_ctx *ctx);
+/* 1 when the library was built with the A/B forms (jpeg-encoder-and-decoder_b200/build.py with JPGB200_AB=1):
+ * the three older K1 kernels (forms 2..4 below) and the single-launch entropy kernel K35.  They produce the
+ * same coefficients and bytes as the product kernels and exist for cross-checks and A/B measurements; the
+ * default build leaves them out, and selecting them then returns JPGB200_ERR_BAD_ARG. */
+int jpgb200_has_ab_forms(void);
 /* Entropy stage selection: 1 (default) = the staged pipeline KE (chunk encode) / KF (0xFF count) /
  * KS (stuffed scatter); 0 = the single-launch kernel K35 (count -> chained scan -> pack -> stuff),
  * byte-identical and slower, kept as a cross-check; K35 takes 4:4:4 and 4:2:2 only and disables the

@@ -39,6 +39,7 @@ _SIGS = {
     "jpgb200_set_fused_transform": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_fused_tap": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_frame_groups": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_has_ab_forms": (C.c_int, []),
     "jpgb200_set_pipelined_batch": (C.c_int, [_vp, C.c_int]),
     "jpgb200_last_coefficients": (C.c_int, [_vp, _vp]),
     "jpgb200_huffman_specs": (C.c_int, [_vp, _vp, _vp, _vp]),
@@ -467,6 +468,10 @@ class MgpuEncoder:
         if self._comm:
             lib().jpgb200_nccl_destroy(self._comm)
             self._comm = None
+
+
+def has_ab_forms():
+    return bool(lib().jpgb200_has_ab_forms())
 
 
 def device_numa(device=0):

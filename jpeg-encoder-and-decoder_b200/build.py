@@ -53,6 +53,8 @@ def build_cuda(force=False, verbose=False):
     srcs = _sources(CSRC, (".cu", ".cuh", ".h")) + [os.path.join(ROOT, "include", "jpgb200.h")]
     if force or _newer(LIB, srcs):
         extra = os.environ.get("JPGB200_NVCC_EXTRA", "").split()  # e.g. -DK1C_NC=2 for A/B builds of a kernel variant
+        if os.environ.get("JPGB200_AB", "0") == "1":
+            extra.append("-DJPGB200_AB")  # the older K1 forms and K35: cross-checks, not product (include/jpgb200.h)
         cmd = [nvcc_path()] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB, os.path.join(CSRC, "jpgb200.cu")]
         subprocess.check_call(cmd)
     return LIB

@@ -79,6 +79,7 @@ struct EfSmem {
     static const int BYTES = OFF_OFF + (NT + 1) * 4 + 12;
 };
 
+#ifdef JPGB200_AB /* a cross-check: built only with -DJPGB200_AB (build.py: JPGB200_AB=1) */
 template <int RATIO>
 __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k35_entropy(const EfParams q, const HuffBits *hbits, const HuffDev *huff)
 {
@@ -324,6 +325,7 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k35_entropy(const EfParams q
         if (q.len_out) *q.len_out = ok ? out_len : 0ull;
     }
 }
+#endif /* JPGB200_AB */
 
 }  // namespace jpgb200
 #endif

@@ -477,16 +477,18 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         const char *fz = getenv("JPGB200_FUSED"); /* "1": K1E instead of K1 and KE as separate kernels (A/B runs) */
         if (fz && !strcmp(fz, "1")) ctx->fused_k1e = true;
         const char *e = getenv("JPGB200_ENTROPY"); /* "fused" | "staged": experiment switch for bench runs */
-        if (e && !strcmp(e, "fused")) ctx->legacy_entropy = false;
+        if (e && !strcmp(e, "fused") && jpgb200_has_ab_forms()) ctx->legacy_entropy = false;
         const char *k = getenv("JPGB200_K1"); /* "plain" | "tma" */
         const char *ov = getenv("JPGB200_OVERLAP");
         ctx->overlap_on = !(ov && !strcmp(ov, "0"));
         if (k && !strcmp(k, "plain")) ctx->k1_plain = true, ctx->k1_pc = false;
-        if (k && !strcmp(k, "cta")) ctx->k1_cta = true, ctx->k1_pc = false;
-        if (k && !strcmp(k, "pipe")) ctx->k1_pipe = true, ctx->k1_pc = false;
-        if (k && !strcmp(k, "pipe_notma")) ctx->k1_pipe = ctx->no_tma_store = true, ctx->k1_pc = false;
         if (k && !strcmp(k, "pc_notma")) ctx->no_tma_store = true;
-        if (k && !strcmp(k, "ws")) ctx->k1_ws = true, ctx->k1_pc = false;
+        if (jpgb200_has_ab_forms()) {
+            if (k && !strcmp(k, "cta")) ctx->k1_cta = true, ctx->k1_pc = false;
+            if (k && !strcmp(k, "pipe")) ctx->k1_pipe = true, ctx->k1_pc = false;
+            if (k && !strcmp(k, "pipe_notma")) ctx->k1_pipe = ctx->no_tma_store = true, ctx->k1_pc = false;
+            if (k && !strcmp(k, "ws")) ctx->k1_ws = true, ctx->k1_pc = false;
+        }
     }
     ctx->hdr_w = -1;
     ctx->err[0] = 0;
@@ -617,9 +619,19 @@ extern "C" int jpgb200_sync(jpgb200_ctx *ctx)
     return JPGB200_OK;
 }
 
+extern "C" int jpgb200_has_ab_forms(void)
+{
+#ifdef JPGB200_AB
+    return 1;
+#else
+    return 0;
+#endif
+}
+
 extern "C" int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;
+    if (on >= 2 && !jpgb200_has_ab_forms()) return JPGB200_ERR_BAD_ARG; /* forms 2..4 are A/B builds only */
     ctx->k1_pc = (on == 0);
     ctx->k1_plain = (on == 1);
     ctx->k1_cta = (on == 2);
@@ -631,6 +643,7 @@ extern "C" int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on)
 extern "C" int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;
+    if (!on && !jpgb200_has_ab_forms()) return JPGB200_ERR_BAD_ARG; /* K35 is an A/B build only */
     ctx->legacy_entropy = on != 0;
     return JPGB200_OK;
 }
@@ -1074,6 +1087,7 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
             k1_transform_pc<0, false><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
         else
             k1_transform_pc<1, false><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
+#ifdef JPGB200_AB
     } else if (aligned16 && ctx->k1_pipe && !ctx->k1_plain) {
         /* persistent CTAs, warps specialised and software-pipelined over tiles (k1_pipe.cuh) */
         if (!ctx->k1p_attr_set) {
@@ -1140,6 +1154,7 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
             k1_transform_tma<0><<<grid, K1_THREADS, sizeof(K1SmemTma), ctx->stream>>>(p, n_tiles);
         else
             k1_transform_tma<1><<<grid, K1_THREADS, sizeof(K1SmemTma), ctx->stream>>>(p, n_tiles);
+#endif /* JPGB200_AB */
     } else {
         dim3 grid((unsigned)p.tiles_per_row, (unsigned)(h / 8), (unsigned)nframes);
         LaunchScope ls(ctx, KI_K1);
@@ -1391,6 +1406,7 @@ static int launch_pack(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     return launch_tail(ctx, n, 0u, 0u, 1, ctx->hdr_len, 1, d_out, cap, len_out); /* deferred inside a batch overlap */
 }
 
+#ifdef JPGB200_AB
 /* K35: the whole entropy stage in one launch (entropy_fused.cuh) */
 static int launch_fused(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3], uint8_t *d_out, size_t cap,
                         unsigned long long *len_out)
@@ -1432,6 +1448,13 @@ static int launch_fused(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lo
     CK(cudaGetLastError());
     return JPGB200_OK;
 }
+#else
+static int launch_fused(jpgb200_ctx *ctx, const int16_t *, int, const long long *, uint8_t *, size_t, unsigned long long *)
+{
+    snprintf(ctx->err, sizeof ctx->err, "K35 is an A/B form: build with JPGB200_AB=1");
+    return JPGB200_ERR_BAD_ARG;
+}
+#endif /* JPGB200_AB */
 
 /* code tables and header of ctx->specs -> device (synchronises: the sources are stack buffers) */
 static int upload_tables(jpgb200_ctx *ctx)

@@ -157,6 +157,7 @@ __device__ __forceinline__ void k1p_store(const K1Out *sOut, const K1Params &p, 
     __syncwarp();
 }
 
+#ifdef JPGB200_AB /* an A/B form: built only with -DJPGB200_AB (build.py: JPGB200_AB=1) */
 template <int RATIO, bool STD = false>
 __global__ void __launch_bounds__(K1_THREADS, K1P_MIN_CTAS) k1_transform_pipe(const K1Params p, long long n_tiles,
                                                                               const __grid_constant__ K1PStore st)
@@ -276,6 +277,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1P_MIN_CTAS) k1_transform_pipe(co
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
+#endif /* JPGB200_AB */
 
 }  // namespace jpgb200
 #endif

@@ -479,6 +479,7 @@ __device__ __forceinline__ K1Tile k1_tile(const K1Params &p, long long t)
     return o;
 }
 
+#ifdef JPGB200_AB /* an A/B form: built only with -DJPGB200_AB (build.py: JPGB200_AB=1) */
 /* warp 0: arm the stage's mbarrier and issue the tile's bulk copies (one row per lane) */
 __device__ __forceinline__ void k1_issue_tile(const K1Params &p, K1Stage &st, unsigned long long *bar, long long t,
                                               int lane)
@@ -583,6 +584,7 @@ __global__ void __launch_bounds__(K1_THREADS, 4) k1_transform_tma(const K1Params
         k1_phase3<RATIO>(S.sOut, p, tl.frame, tl.by, tl.tb0, tid);
     }
 }
+#endif /* JPGB200_AB */
 
 }  // namespace jpgb200
 #endif

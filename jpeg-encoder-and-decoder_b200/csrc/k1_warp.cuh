@@ -92,6 +92,7 @@ __device__ __forceinline__ void k1w_fetch(const K1Params &p, K1WRaw &raw, long l
     asm volatile("cp.async.commit_group;\n" ::: "memory");
 }
 
+#ifdef JPGB200_AB /* an A/B form: built only with -DJPGB200_AB (build.py: JPGB200_AB=1) */
 template <int RATIO, bool STD = false>
 __global__ void __launch_bounds__(K1_THREADS, K1W_MIN_CTAS) k1_transform_ws(const K1Params p, long long n_tiles)
 {
@@ -251,6 +252,7 @@ __global__ void __launch_bounds__(K1_THREADS, K1W_MIN_CTAS) k1_transform_ws(cons
         __syncwarp(); /* the scratch is free for the next tile's phase 1 */
     }
 }
+#endif /* JPGB200_AB */
 
 }  // namespace jpgb200
 #endif

@@ -159,14 +159,14 @@ def test_staged_stage_kernels_match_reference_stages(enc):
     assert np.abs(got - want).max() < 1e-12
 
 
-def test_encode_coefficients_is_byte_exact_given_equal_coefficients(enc):
+def test_encode_coefficients_is_byte_exact_given_equal_coefficients(enc, pkg):
     """`Given identical coefficients, the entropy-coded scan data and full JFIF byte stream are
     byte-identical` (north_star): feed the ORACLE's coefficients to the GPU entropy stage."""
     for (w, h, q, ratio, kind) in [(640, 480, 75, 0, 0), (512, 512, 97, 1, 1), (264, 40, 24, 0, 0)]:
         r, g, b = O.synth_planes(w, h, 41, 0, kind)
         zz = O.coefficients(r, g, b, w, h, q, ratio)
         want = O.encode_jfif(r, g, b, w, h, q, ratio)
-        for staged in (True, False):
+        for staged in ((True, False) if pkg.binding.has_ab_forms() else (True,)):
             enc.set_staged_entropy(staged)
             got = enc.encode_coefficients(zz, w, h, q, ratio)
             assert got.shape == want.shape and (got == want).all()
