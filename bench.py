@@ -8,10 +8,15 @@ A step = one pass of the whole hot path (K1 transform, KE chunk encode, KF 0xFF 
 scatter -> complete JFIF streams) over one batch of synthetic frames.
   value : frames are resident in HBM when the timed region starts (device-resident encode)
   e2e   : the same batch through the C-ABI host-buffer call (jpgb200_encode_batch_host):
-          pinned host frames in, JFIF bytes out, H2D and D2H inside the timed region
-  roofline : K1 (fused colour->FDCT->quantise->zig-zag), algorithmic 9 B/pixel, timed with
-          CUDA events on its own stream inside the timed region, against the measured HBM
-          copy bandwidth in MEASURED_PEAKS.json
+          pinned host frames in, JFIF bytes out, H2D and D2H inside the timed region; beside it
+          the PCIe ceiling of this host at this N: the same copies with no kernel (jpgb200_copy_probe)
+  roofline : the dominant kernel (the longest when each runs alone) against the measured HBM copy
+          bandwidth in MEASURED_PEAKS.json, from CUDA events on the kernel's own stream inside the
+          timed region; all_timed_kernels holds K1 (north_star's target kernel: 9 B/pixel) and KE
+          (6 B/pixel + stream); pipeline = (3 B/pixel + stream) / frame time against the same peak
+  config.strong_scaling / small_frame / worst_case_distribution / config5 : BASELINE.json configs[3] as
+          written (256 frames in total), configs[1] (1080p batch), iid-noise frames, configs[4] (one
+          32768x32768 image partitioned over the ranks, N > 1 only)
   cpu_baseline : the reference's own C stage functions (oracle/_ref/ref_harness, built from
           the unmodified sources) on a bounded crop of frame 0, one core
 
@@ -339,13 +344,19 @@ def run_b200(args):
         if n == 0:
             return None
         avg = ms * 1e-3 / n
+        iso_ms = kbreak.get(kname, (0.0, 0))
+        iso = iso_ms[0] * 1e-3 / max(iso_ms[1], 1) if iso_ms[1] else None
         tr = traffic_file.get(kname, {})
         return {"bound": "hbm", "kernel": label, "achieved": alg_bytes / avg / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": alg_bytes / avg / 1e9 / peak, "frac_of_nominal_8000": alg_bytes / avg / 1e9 / 8000.0,
                 "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes": what, "avg_launch_us": avg * 1e6,
-                "launches_timed": n, "event_sampling": "every 8th launch of the timed region",
-                "share_of_step": avg * 1e3 * F / ms_per_step}
+                "launches_timed": n, "event_sampling": "every 8th launch of the timed region, CUDA events on the kernel's own stream; in the "
+                "pipelined batch the span of a launch includes the time its CTAs wait for room beside the other frames' kernels",
+                "share_of_step": avg * 1e3 * F / ms_per_step,
+                # the same kernel with nothing beside it: one extra, untimed step without pipelining, events around every launch
+                "avg_launch_us_isolated": iso * 1e6 if iso else None,
+                "frac_isolated": (alg_bytes / iso / 1e9 / peak) if iso else None}
 
     fused = ktimes.get("k1e_fused", (0.0, 0))[1] > 0
     roofs = {}
@@ -358,9 +369,11 @@ def run_b200(args):
         roofs["k_encode_chunks"] = roof("k_encode_chunks", "k_encode_chunks<0>", (6.0 + bytes_per_px) * NPX,
                                         "6 B/px of int16 coefficients in + the chunk streams out")
     roofs = {k: v for k, v in roofs.items() if v}
-    dominant = max(roofs, key=lambda k: roofs[k]["avg_launch_us"])
+    # the dominant kernel: the longest one when each runs alone
+    dominant = max(roofs, key=lambda k: roofs[k]["avg_launch_us_isolated"] or roofs[k]["avg_launch_us"])
     roofline = dict(roofs[dominant])
     roofline["dominant_kernel"] = dominant
+    roofline["north_star_target_kernel"] = "k1_transform" if "k1_transform" in roofs else "k1e_fused"
     roofline["all_timed_kernels"] = roofs
     roofline["kernel_ms_per_step_untimed_pass"] = {k: v[0] for k, v in kbreak.items()}
     # the whole pipeline against the same peak: the least it has to move is the planes in and the stream out
