@@ -100,7 +100,10 @@ int jpgb200_set_fused_tap(jpgb200_ctx *ctx, int on);
  *   1           one CTA per tile, direct loads (the only form for width % 16 == 8)
  *   2           persistent CTAs, TMA bulk loads, phases separated by CTA barriers
  *   3           software-pipelined CTA (csrc/k1_pipe.cuh)
- *   4           autonomous warps, per-warp cp.async ring (csrc/k1_warp.cuh) */
+ *   4           autonomous warps, per-warp cp.async ring (csrc/k1_warp.cuh)
+ *   6           form 0 fed by 2-D TMA tile loads (cp.async.bulk.tensor.2d, one per plane and tile, issued by the
+ *               store warp: k1_transform_pct in csrc/k1_pc.cuh); measured 9 % slower than form 0; needs width >= 256
+ * Forms 2..4 exist in A/B builds only (jpgb200_has_ab_forms). */
 int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on);
 /* Arithmetic of the transform: 0 (default) = bug-compatible with the reference (its Cb sign slip,
  * src/preprocess.c:161, and the last block column read one pixel row higher, :199-211); 1 =

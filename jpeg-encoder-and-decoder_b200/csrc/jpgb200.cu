@@ -92,6 +92,8 @@ struct jpgb200_ctx {
     bool k1_pc;    /* the producer/consumer K1 (k1_pc.cuh): the default */
     bool k1_ws;    /* the warp-autonomous K1 (k1_warp.cuh) */
     bool k1c_attr_set;
+    bool k1_tmaload, k1t_attr_set; /* K1 fed by 2-D TMA tile loads (k1_transform_pct, JPGB200_K1=pct) */
+    K1TLoad k1t_maps;
     bool no_tma_store; /* k1_pipe: copy the coefficients out with ordinary stores (A/B runs) */
     CUtensorMap tm32, tm16; /* tensor maps of the coefficient buffer, cached (two entries: the pipelined batch alternates buffers) */
     int16_t *tm_ptr;
@@ -483,6 +485,7 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         ctx->overlap_on = !(ov && !strcmp(ov, "0"));
         if (k && !strcmp(k, "plain")) ctx->k1_plain = true, ctx->k1_pc = false;
         if (k && !strcmp(k, "pc_notma")) ctx->no_tma_store = true;
+        if (k && !strcmp(k, "pct")) ctx->k1_tmaload = true;
         if (jpgb200_has_ab_forms()) {
             if (k && !strcmp(k, "cta")) ctx->k1_cta = true, ctx->k1_pc = false;
             if (k && !strcmp(k, "pipe")) ctx->k1_pipe = true, ctx->k1_pc = false;
@@ -631,8 +634,9 @@ extern "C" int jpgb200_has_ab_forms(void)
 extern "C" int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;
-    if (on >= 2 && !jpgb200_has_ab_forms()) return JPGB200_ERR_BAD_ARG; /* forms 2..4 are A/B builds only */
-    ctx->k1_pc = (on == 0);
+    if (on >= 2 && on <= 4 && !jpgb200_has_ab_forms()) return JPGB200_ERR_BAD_ARG; /* forms 2..4 are A/B builds only */
+    ctx->k1_pc = (on == 0 || on == 5 || on == 6);
+    ctx->k1_tmaload = (on == 6); /* 5: the cp.async-fed form explicitly, 6: the TMA-load-fed form */
     ctx->k1_plain = (on == 1);
     ctx->k1_cta = (on == 2);
     ctx->k1_pipe = (on == 3);
@@ -1022,6 +1026,45 @@ static void make_store_maps(jpgb200_ctx *ctx, K1PStore *st, int16_t *zz, const l
     st->enabled = 1;
 }
 
+/* tensor maps of the three planes for K1's 2-D TMA tile loads (k1_transform_pct) */
+static bool make_load_maps(jpgb200_ctx *ctx, K1TLoad *ld, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w, int h,
+                           int nframes, long long plane_stride, int has_halo)
+{
+    (void)ctx;
+    memset(ld, 0, sizeof *ld);
+    if (nframes > 1 && (plane_stride % w)) return false;
+    static EncodeTiledFn fn = NULL;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void *pfn = NULL;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &pfn, cudaEnableDefault, &qres) == cudaSuccess &&
+            qres == cudaDriverEntryPointSuccess)
+            fn = (EncodeTiledFn)pfn;
+    }
+    if (!fn) return false;
+    ld->rows_per_frame = nframes > 1 ? (int)(plane_stride / w) : 0;
+    ld->y_bias = has_halo ? 1 : 0;
+    const long long rows = (long long)(nframes > 1 ? (nframes - 1) : 0) * ld->rows_per_frame + h + (has_halo ? 1 : 0);
+    if (rows >= (1ll << 31)) return false;
+    const uint8_t *base[3] = {d_r, d_g, d_b};
+    const cuuint64_t gdim[2] = {(cuuint64_t)w, (cuuint64_t)rows};
+    const cuuint64_t gstride[1] = {(cuuint64_t)w};
+    const cuuint32_t estr[2] = {1, 1};
+    const cuuint32_t box[2] = {K1_ROW_BYTES, 8}, boxa[2] = {16, 8};
+    for (int c = 0; c < 3; c++) {
+        void *g = (void *)(base[c] - (has_halo ? w : 0));
+        if (fn(&ld->plane[c], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, g, gdim, gstride, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+        if (fn(&ld->alt[c], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, g, gdim, gstride, boxa, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+               CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) != CUDA_SUCCESS)
+            return false;
+    }
+    return true;
+}
+
 static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, const uint8_t *d_b, int w, int h,
                      int ratio, const long long n[3], int nframes, long long plane_stride, int16_t *zz,
                      long long zz_stride, int has_halo)
@@ -1062,6 +1105,32 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
             k1_transform420<true><<<grid, K1_THREADS, 0, ctx->stream>>>(p);
         else
             k1_transform420<false><<<grid, K1_THREADS, 0, ctx->stream>>>(p);
+    } else if (aligned16 && ctx->k1_pc && ctx->k1_tmaload && !ctx->k1_plain && w >= 256 &&
+               make_load_maps(ctx, &ctx->k1t_maps, d_r, d_g, d_b, w, h, nframes, plane_stride, has_halo)) {
+        /* the same roles fed by 2-D TMA tile loads issued by the store warp (k1_pc.cuh: k1_transform_pct) */
+        const size_t smem = sizeof(K1TSmem) + 1024;
+        if (!ctx->k1t_attr_set) {
+            CK(cudaFuncSetAttribute((k1_transform_pct<0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute((k1_transform_pct<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute((k1_transform_pct<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute((k1_transform_pct<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->k1t_attr_set = true;
+        }
+        const long long n_tiles = (long long)p.tiles_per_row * (h / 8) * nframes;
+        const long long resident = (long long)ctx->sm_count * (ctx->k1_ctas_per_sm > 0 ? ctx->k1_ctas_per_sm : K1C_MIN_CTAS);
+        const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+        K1PStore st;
+        make_store_maps(ctx, &st, zz, n, zz_stride, nframes);
+        LaunchScope ls(ctx, KI_K1);
+        if (ctx->std_mode) {
+            if (ratio == 0)
+                k1_transform_pct<0, true><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st, ctx->k1t_maps);
+            else
+                k1_transform_pct<1, true><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st, ctx->k1t_maps);
+        } else if (ratio == 0)
+            k1_transform_pct<0, false><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st, ctx->k1t_maps);
+        else
+            k1_transform_pct<1, false><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st, ctx->k1t_maps);
     } else if (aligned16 && ctx->k1_pc && !ctx->k1_plain) {
         /* eight specialised warps per CTA handing tiles over through mbarriers (k1_pc.cuh) */
         const size_t smem = sizeof(K1CSmem) + 1024;

@@ -238,5 +238,211 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pc(con
     }
 }
 
+/* ---- K1, producer/consumer form fed by 2-D TMA tile loads (k1_transform_pct) --------------------------------
+ * k1_transform_pc's convert warps fetch their own two rows of the tile with cp.async: 27 LDGSTS and their
+ * address arithmetic per lane and tile, issued on the schedulers the transform warps need.  Here the (otherwise
+ * idle) store warp issues ONE tensor load per plane and tile -- cp.async.bulk.tensor.2d, box 256 bytes x 8 rows,
+ * SASS UTMALDG -- into a CTA-shared ring; completion is counted in bytes on an mbarrier, the convert warps hand
+ * the slot back through a second one.  The block of column BW-1 is read one pixel row higher: the
+ * tile that holds it gets a second, 16-byte-wide box per plane starting one row up; rows outside the image (row -1
+ * of an image without halo) are zero-filled by the TMA unit and replaced by the caller's out-of-bounds bytes.
+ * MEASURED (profiles/README.md): 83.5 us per 8K frame against 76.7 us for the cp.async-fed form -- issued by
+ * convert warp 0 instead: 87.8 us, with a four-slot ring: 86.3 us.  The shared ring couples the four convert
+ * warps through two mbarriers per tile where the cp.async form gives every warp a private ring and no hand-over
+ * at all.  Selectable (jpgb200_set_plain_transform(ctx, 6)), bit-identical, not the default. */
+#ifndef K1T_STAGES
+#define K1T_STAGES 3
+#endif
+
+struct K1TLoad {
+    CUtensorMap plane[3]; /* [rows of all frames][W] u8, box 256 x 8 */
+    CUtensorMap alt[3];   /* same tensor, box 16 x 8 */
+    int rows_per_frame;   /* plane_stride / W */
+    int y_bias;           /* 1 when the tensors start one row above the band (halo) */
+};
+
+struct K1TSmem {
+    K1Out coef[2][3];                       /* 24 KB, 1 KB aligned (TMA swizzle) */
+    K1F samples[2][3];                      /* 48 KB */
+    uint8_t raw[K1T_STAGES][3][8][K1_ROW_BYTES]; /* 18 KB, [slot][plane][row][x]: 128-byte aligned TMA destinations */
+    uint8_t alt[K1T_STAGES][3][8][16];
+    float mul[2][64];
+    unsigned long long samples_full[2], samples_free[2], coef_full[2], coef_free[2];
+    unsigned long long raw_full[K1T_STAGES], raw_free[K1T_STAGES];
+};
+
+__device__ __forceinline__ void tma_load_2d(void *dst, const CUtensorMap *tm, int c0, int c1, unsigned long long *bar)
+{
+    const unsigned d = (unsigned)__cvta_generic_to_shared(dst), b = (unsigned)__cvta_generic_to_shared(bar);
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(d),
+                 "l"(tm), "r"(c0), "r"(c1), "r"(b)
+                 : "memory");
+}
+
+/* one lane: arm the slot's mbarrier and issue the tile's tensor loads */
+template <bool STD>
+__device__ __forceinline__ void k1t_issue(const K1Params &p, const K1TLoad &ld, K1TSmem &S, int s, const K1Tile &tl)
+{
+    const bool has_last = !STD && (tl.tb0 + K1_TILE_BLOCKS >= p.BW);
+    const int y = tl.frame * ld.rows_per_frame + tl.by * 8 + ld.y_bias;
+    mbar_expect_tx(&S.raw_full[s], 3u * 8u * K1_ROW_BYTES + (has_last ? 3u * 8u * 16u : 0u));
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        tma_load_2d(&S.raw[s][c][0][0], &ld.plane[c], tl.tb0 * 8, y, &S.raw_full[s]);
+        if (has_last) tma_load_2d(&S.alt[s][c][0][0], &ld.alt[c], p.W - 16, y - 1, &S.raw_full[s]);
+    }
+}
+
+template <int RATIO, bool STD = false>
+__global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pct(const K1Params p, long long n_tiles,
+                                                                               const __grid_constant__ K1PStore st,
+                                                                               const __grid_constant__ K1TLoad ld)
+{
+    extern __shared__ unsigned char k1_smem_raw[];
+    unsigned char *k1_smem = k1_smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(k1_smem_raw) & 1023u)) & 1023u);
+    K1TSmem &S = *reinterpret_cast<K1TSmem *>(k1_smem);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    constexpr int NT = (RATIO == 0) ? 3 : 2; /* transform warps with work */
+
+    if (tid < 128) S.mul[tid >> 6][tid & 63] = p.mul[tid >> 6][tid & 63];
+    if (blockIdx.x == 0)
+        for (int i = tid; i < p.clear_n; i += K1C_THREADS) p.clear[i] = 0u;
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&S.samples_full[b], 4);
+            mbar_init(&S.samples_free[b], NT);
+            mbar_init(&S.coef_full[b], NT);
+            mbar_init(&S.coef_free[b], 1);
+        }
+#pragma unroll
+        for (int s = 0; s < K1T_STAGES; s++) {
+            mbar_init(&S.raw_full[s], 1);
+            mbar_init(&S.raw_free[s], 4);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (w < 4) {
+        /* ================= convert warp k ================= */
+        const int k = w;
+        int it = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+            const int b = it & 1;
+            const unsigned use = (unsigned)(it >> 1);
+            const int s = it % K1T_STAGES;
+
+            const unsigned suse = (unsigned)(it / K1T_STAGES);
+            const K1Tile tl = k1_tile(p, t);
+            mbar_wait(&S.raw_full[s], suse & 1u);
+            const int jl = STD ? -1 : p.BW - 1 - tl.tb0;
+            const bool top_oob = (tl.by == 0 && !p.has_halo && k == 0);
+            auto ld8 = [&](int c, int sel, int j) -> uint2 {
+                const int rr = sel ? 7 - k : k;
+                if (j == jl) {
+                    if (top_oob && sel == 0) return ld_oob(p.oob + 8 * c);
+                    return *reinterpret_cast<const uint2 *>(&S.alt[s][c][rr][8]);
+                }
+                return *reinterpret_cast<const uint2 *>(&S.raw[s][c][rr][j * 8]);
+            };
+            uint2 pa[3], pb[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                pa[c] = ld8(c, 0, lane);
+                pb[c] = ld8(c, 1, lane);
+            }
+            uint4 ca[3], cb[3];
+            if (RATIO == 1) {
+                const int jc = lane & 15;
+#pragma unroll
+                for (int c = 0; c < 3; c++) {
+                    const uint2 l0 = ld8(c, 0, 2 * jc), l1 = ld8(c, 0, 2 * jc + 1);
+                    const uint2 h0 = ld8(c, 1, 2 * jc), h1 = ld8(c, 1, 2 * jc + 1);
+                    ca[c] = make_uint4(l0.x, l0.y, l1.x, l1.y);
+                    cb[c] = make_uint4(h0.x, h0.y, h1.x, h1.y);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.raw_free[s]); /* this warp's rows are in registers */
+            mbar_wait_relaxed(&S.samples_free[b], (use & 1u) ^ 1u); /* the transform warps have taken tile it-2 */
+            k1_convert_full<RATIO, STD>(S.samples[b], k, lane, pa, pb);
+            if (RATIO == 1) k1_convert_chroma422<STD>(S.samples[b], k, lane, ca, cb);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.samples_full[b]);
+        }
+    } else if (w < 4 + NT) {
+        /* ================= transform warp c ================= */
+        const int c = w - 4;
+        const float4 *m4 = reinterpret_cast<const float4 *>(S.mul[c == 0 ? 0 : 1]);
+        int it = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+            const int b = it & 1;
+            const unsigned use = (unsigned)(it >> 1);
+            f32x2 P[4][8], Q[8][4];
+            mbar_wait(&S.samples_full[b], use & 1u);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int x = 0; x < 8; x++) P[k][x] = S.samples[b][c][k][x][lane];
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.samples_free[b]);
+            fdct8x8_p(P, Q);
+            float f[64];
+#pragma unroll
+            for (int v = 0; v < 8; v++)
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const float4 m = m4[v * 2 + hh];
+                    const f32x2 q0 = p_fma(Q[v][2 * hh], make_float2(m.x, m.y), p_bc(JPGB_ROUND_MAGIC));
+                    const f32x2 q1 = p_fma(Q[v][2 * hh + 1], make_float2(m.z, m.w), p_bc(JPGB_ROUND_MAGIC));
+                    f[v * 8 + 4 * hh + 0] = q0.x;
+                    f[v * 8 + 4 * hh + 1] = q0.y;
+                    f[v * 8 + 4 * hh + 2] = q1.x;
+                    f[v * 8 + 4 * hh + 3] = q1.y;
+                }
+            uint32_t o[32];
+            zigzag_pack(f, o);
+            mbar_wait(&S.coef_free[b], (use & 1u) ^ 1u); /* tile it-2 has left the buffer */
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                S.coef[b][c][lane][j ^ (lane & 7)] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic writes -> the TMA's proxy */
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.coef_full[b]);
+        }
+    } else if (w == 7) {
+        /* ================= load + store warp ================= */
+        if (lane == 0) {
+#pragma unroll
+            for (int d = 0; d < K1T_STAGES - 1; d++) {
+                const long long td = (long long)blockIdx.x + (long long)d * gridDim.x;
+                if (td < n_tiles) k1t_issue<STD>(p, ld, S, d, k1_tile(p, td));
+            }
+        }
+        int it = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+            const int b = it & 1;
+            const unsigned use = (unsigned)(it >> 1);
+            const K1Tile tl = k1_tile(p, t);
+            {
+                /* the load of tile it + STAGES - 1 goes into the slot tile it - 1 used */
+                const long long tn = t + (long long)(K1T_STAGES - 1) * gridDim.x;
+                const int itn = it + K1T_STAGES - 1, sn = itn % K1T_STAGES;
+                if (tn < n_tiles && lane == 0) {
+                    if (itn >= K1T_STAGES) mbar_wait(&S.raw_free[sn], (unsigned)(itn / K1T_STAGES - 1) & 1u);
+                    k1t_issue<STD>(p, ld, S, sn, k1_tile(p, tn));
+                }
+                __syncwarp();
+            }
+            mbar_wait_relaxed(&S.coef_full[b], use & 1u);
+            k1p_store<RATIO>(S.coef[b], p, st, tl, lane); /* returns when shared memory has been read */
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.coef_free[b]);
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+
 }  // namespace jpgb200
 #endif

@@ -412,6 +412,9 @@ def test_tma_and_plain_transform_agree(enc, pkg, w, h, q, ratio, seed):
         a = enc.coefficients(r, g, b, w, h, q, ratio)
         enc.set_plain_transform(1)
         p = enc.coefficients(r, g, b, w, h, q, ratio)
+        enc.set_plain_transform(6)  # the producer/consumer form fed by 2-D TMA tile loads (UTMALDG)
+        t6 = enc.coefficients(r, g, b, w, h, q, ratio)
+        assert (a == t6).all()
         c = d = e = a
         if pkg.binding.has_ab_forms():  # the three older forms exist in JPGB200_AB=1 builds only
             enc.set_plain_transform(2)
