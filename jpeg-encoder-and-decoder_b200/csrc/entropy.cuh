@@ -158,13 +158,16 @@ __device__ __forceinline__ void ec_fill(uint4 (*sC)[EC_ROW_CHUNKS], const EcPara
     }
 }
 
-/* tables -> shared memory, 16 bytes per thread */
-template <class T>
+/* tables -> shared memory, 16 bytes per copy, NTH threads */
+template <int NTH, class T>
 __device__ __forceinline__ void ec_load_table(T *sT, const T *g, int tid)
 {
     static_assert(sizeof(T) % 16 == 0, "table size");
-    if (tid < (int)(sizeof(T) / 16))
-        cp_async16(reinterpret_cast<uint4 *>(sT) + tid, reinterpret_cast<const uint4 *>(g) + tid);
+#pragma unroll
+    for (int i = 0; i < ((int)(sizeof(T) / 16) + NTH - 1) / NTH; i++) {
+        const int j = i * NTH + tid;
+        if (j < (int)(sizeof(T) / 16)) cp_async16(reinterpret_cast<uint4 *>(sT) + j, reinterpret_cast<const uint4 *>(g) + j);
+    }
 }
 
 /* DC predictor: the previous block of the same component (raster == scan order per
@@ -613,7 +616,12 @@ template <int RATIO>
 struct KeCfg {
     static const int NY = (RATIO == 0) ? 64 : (RATIO == 1 ? 128 : 256); /* luma blocks per chunk */
     static const int ROWS = NY + 128;                    /* coefficient rows (blocks) per chunk */
-    static const bool SPLIT = (RATIO != 2);              /* two lanes per luma block (4:2:0 has four luma blocks per MCU already) */
+#ifndef KE_SPLIT
+#define KE_SPLIT 0 /* 1: two lanes per luma block.  Measured on the headline frames: 96.5 us split, 91.0 us one lane per block
+                      (the second lane halves the luma loop but pays the per-entry work -- masks, scan, relocation -- again);
+                      iid noise: 85 k against 92 k Mpixel/s */
+#endif
+    static const bool SPLIT = (RATIO != 2) && KE_SPLIT;
     static const int NT = (SPLIT ? 2 : 1) * NY + 128;    /* threads = entries: 256 / 384 / 384 */
     static const int EPM = (RATIO == 0) ? 4 : 6;         /* entries per MCU */
     static const int PRIV = 10;                          /* words of private stream per entry (with the tables: 5 CTAs per SM) */
@@ -639,7 +647,29 @@ struct KeMap {
     __device__ __forceinline__ KeMap(const EcParams &p, long long m0, int tid)
     {
         constexpr int NY = KeCfg<RATIO>::NY;
-        if (RATIO == 2) {
+        if (RATIO != 2 && !KeCfg<RATIO>::SPLIT) {
+            /* one lane per block, component-major */
+            part = 0;
+            if (tid < NY) {
+                luma = true;
+                comp = 0;
+                row = tid;
+                const int m = (RATIO == 0) ? row : (row >> 1);
+                e_local = blk_local = (RATIO == 0) ? 3 * m : 4 * m + (row & 1);
+                gabs = ((RATIO == 0) ? m0 : 2 * m0) + row;
+                valid = (m0 + m) < p.n_mcu;
+                first_of_comp = (row == 0);
+            } else {
+                luma = false;
+                const int c = (tid - NY) >> 6, m = (tid - NY) & 63;
+                comp = 1 + c;
+                row = NY + 64 * c + m;
+                e_local = blk_local = (RATIO == 0) ? 3 * m + 1 + c : 4 * m + 2 + c;
+                gabs = m0 + m + (c == 0 ? p.coff1 : p.coff2);
+                valid = (m0 + m) < p.n_mcu;
+                first_of_comp = (m == 0);
+            }
+        } else if (RATIO == 2) {
             /* 4:2:0: one lane per block; luma rows are already in stream order (MCU-major) */
             part = 0;
             if (tid < NY) {
@@ -691,7 +721,7 @@ template <int RATIO>
 __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KeParams q0, const HuffPack *huff)
 {
     KeParams q = q0;
-    {
+    if (blockIdx.y) { /* frame of a multi-frame launch */
         const long long f = blockIdx.y;
         q.zz += f * q.zz_fstride;
         q.tmp += f * q.tmp_fstride;
@@ -724,7 +754,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     p.dc_pred[2] = q.dc_pred_dev ? q.dc_pred_dev[2] : q.dc_pred[2];
 
     ec_fill<RATIO, NT>(sC, p, m0, tid);
-    ec_load_table(&sH, huff, tid);
+    ec_load_table<NT>(&sH, huff, tid);
     const KeMap<RATIO> mp(p, m0, tid);
     if (tid == 0) *sFlag = 0u;
     cp_async_wait_all();

@@ -120,8 +120,8 @@ __global__ void __launch_bounds__(EcCfg<RATIO>::NT) k35_entropy(const EfParams q
         const long long blk = ((tid < 8) ? q.coff1 : q.coff2) + m0 - 1;
         cp_async16(&sC[NT + (tid >> 3)][tid & 7], reinterpret_cast<const uint4 *>(q.zz) + blk * 8 + (tid & 7));
     }
-    ec_load_table(&sB, hbits, tid);
-    ec_load_table(&sH, huff, tid);
+    ec_load_table<EcCfg<RATIO>::NT>(&sB, hbits, tid);
+    ec_load_table<EcCfg<RATIO>::NT>(&sH, huff, tid);
     const EcMap<RATIO> mp(p, m0, tid);
     /* DC predictors of the previous chunk's last Cb and Cr block (m0 is a multiple of EC_MCUS,
      * so block m0-2 exists whenever m0 > 0) */
