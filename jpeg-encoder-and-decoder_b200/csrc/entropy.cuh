@@ -158,6 +158,43 @@ __device__ __forceinline__ void ec_fill(uint4 (*sC)[EC_ROW_CHUNKS], const EcPara
     }
 }
 
+
+/* ---- KE's coefficient rows: 128 bytes each, NOT padded; the 16-byte chunk j of row r sits at chunk j ^ (r & 7)
+ * (the swizzle of K1's coefficient tile): per-lane 16-byte row reads stay bank-conflict free and a CTA needs 3 KB
+ * less shared memory than with 144-byte rows -- the sixth resident CTA per SM (KE lives on occupancy). */
+#define KE_ROW_CHUNKS 8
+
+template <int RATIO, int NTH>
+__device__ __forceinline__ void ke_fill(uint4 (*sC)[KE_ROW_CHUNKS], const EcParams &p, long long m0, int tid)
+{
+    constexpr int NT = NTH;
+    const long long left = p.n_mcu - m0;
+    const int nv = left < EC_MCUS ? (int)left : EC_MCUS; /* valid MCUs of this chunk */
+    const uint4 *z = reinterpret_cast<const uint4 *>(p.zz);
+    {
+        constexpr int YPM = (RATIO == 0) ? 1 : (RATIO == 1 ? 2 : 4); /* luma blocks per MCU */
+        const int n0 = YPM * nv * 8;
+        const uint4 *src = z + YPM * m0 * 8;
+#pragma unroll
+        for (int k = 0; k < (YPM * 64 * 8 + NT - 1) / NT; k++) {
+            const int i = k * NT + tid, r = i >> 3;
+            if (i < n0) cp_async16(&sC[r][(i & 7) ^ (r & 7)], src + i);
+        }
+    }
+    {
+        const int n1 = nv * 8, r1 = (RATIO == 0 ? 64 : (RATIO == 1 ? 128 : 256));
+        const uint4 *s1 = z + (p.coff1 + m0) * 8, *s2 = z + (p.coff2 + m0) * 8;
+#pragma unroll
+        for (int k = 0; k < (64 * 8 + NT - 1) / NT; k++) {
+            const int i = k * NT + tid, r = i >> 3; /* r1 and r1 + 64 are multiples of 8: the swizzle sees r & 7 */
+            if (i < n1) {
+                cp_async16(&sC[r1 + r][(i & 7) ^ (r & 7)], s1 + i);
+                cp_async16(&sC[r1 + 64 + r][(i & 7) ^ (r & 7)], s2 + i);
+            }
+        }
+    }
+}
+
 /* tables -> shared memory, 16 bytes per copy, NTH threads */
 template <int NTH, class T>
 __device__ __forceinline__ void ec_load_table(T *sT, const T *g, int tid)
@@ -213,6 +250,11 @@ __device__ __forceinline__ void ec_nz_masks(const uint4 *row, uint32_t &m0, uint
 }
 
 __device__ __forceinline__ int ec_coef(const uint4 *row, int k) { return (int)reinterpret_cast<const short *>(row)[k]; }
+/* coefficient k of a swizzled row (sw4 = (row & 7) << 4): byte offset (2 k) ^ sw4 */
+__device__ __forceinline__ int ke_coef(const uint4 *row, unsigned sw4, int k)
+{
+    return (int)*reinterpret_cast<const short *>(reinterpret_cast<const unsigned char *>(row) + (((unsigned)k << 1) ^ sw4));
+}
 
 /* index of the most significant set bit (v != 0): category - 1 */
 __device__ __forceinline__ int msb_index(uint32_t v)
@@ -359,16 +401,17 @@ __device__ __forceinline__ int ec_split(unsigned long long M)
  * shuffle is executed by all 32 lanes of the (component-pure) warp with a full mask, valid block or not, so it
  * must be called OUTSIDE any `valid` branch.  Returns false when this entry has nothing to code. */
 template <bool WHOLE>
-__device__ __forceinline__ bool ec_entry_masks(const uint4 *row, int part, uint32_t (&mm)[2], int &prev, bool &eob)
+__device__ __forceinline__ bool ec_entry_masks(const uint4 *row, int sw, int part, uint32_t (&mm)[2], int &prev, bool &eob)
 {
     prev = 0;
     eob = true;
     if (WHOLE) {
-        ec_nz_masks(row, mm[0], mm[1]);
+        mm[0] = (nz_mask16(row[0 ^ sw], row[1 ^ sw]) | (nz_mask16(row[2 ^ sw], row[3 ^ sw]) << 16)) & ~1u; /* bit 0 is the DC */
+        mm[1] = nz_mask16(row[4 ^ sw], row[5 ^ sw]) | (nz_mask16(row[6 ^ sw], row[7 ^ sw]) << 16);
         return true;
     }
-    const uint32_t mine_half = part == 0 ? ((nz_mask16(row[0], row[1]) | (nz_mask16(row[2], row[3]) << 16)) & ~1u)
-                                         : (nz_mask16(row[4], row[5]) | (nz_mask16(row[6], row[7]) << 16));
+    const uint32_t mine_half = part == 0 ? ((nz_mask16(row[0 ^ sw], row[1 ^ sw]) | (nz_mask16(row[2 ^ sw], row[3 ^ sw]) << 16)) & ~1u)
+                                         : (nz_mask16(row[4 ^ sw], row[5 ^ sw]) | (nz_mask16(row[6 ^ sw], row[7 ^ sw]) << 16));
     const uint32_t other_half = __shfl_xor_sync(0xffffffffu, mine_half, 1);
     const unsigned long long M = part == 0 ? ((unsigned long long)mine_half | ((unsigned long long)other_half << 32))
                                            : ((unsigned long long)other_half | ((unsigned long long)mine_half << 32));
@@ -393,8 +436,8 @@ __device__ __forceinline__ bool ec_entry_masks(const uint4 *row, int part, uint3
 /* codes of one entry from its masks: the DC difference (do_dc), the coefficients whose bits are set in mm, the
  * end-of-block code (eob, unless position 63 is coded).  Tables are HuffPack words; lut = HuffPack::lut[table]. */
 template <class Sink>
-__device__ __forceinline__ void ec_pack_masked(const uint4 *row, bool do_dc, int diff, const uint32_t (&mm)[2], int prev, bool eob,
-                                               const uint32_t *sAc, const uint32_t *sDc, const uint32_t *lut, Sink &s)
+__device__ __forceinline__ void ec_pack_masked(const uint4 *row, unsigned sw4, bool do_dc, int diff, const uint32_t (&mm)[2], int prev,
+                                               bool eob, const uint32_t *sAc, const uint32_t *sDc, const uint32_t *lut, Sink &s)
 {
     if (do_dc) {
         const int cat = diff == 0 ? 0 : msb_index((uint32_t)abs(diff)) + 1;
@@ -409,7 +452,7 @@ __device__ __forceinline__ void ec_pack_masked(const uint4 *row, bool do_dc, int
             const int pos = __clz((int)mr);
             mr ^= 0x80000000u >> pos;
             const int k = half * 32 + pos;
-            const int v = ec_coef(row, k);
+            const int v = ke_coef(row, sw4, k);
             int run = k - prev - 1;
             prev = k;
             const unsigned u = (unsigned)(v + 4);
@@ -624,17 +667,26 @@ struct KeCfg {
     static const bool SPLIT = (RATIO != 2) && KE_SPLIT;
     static const int NT = (SPLIT ? 2 : 1) * NY + 128;    /* threads = entries: 256 / 384 / 384 */
     static const int EPM = (RATIO == 0) ? 4 : 6;         /* entries per MCU */
-    static const int PRIV = 10;                          /* words of private stream per entry (with the tables: 5 CTAs per SM) */
+#ifndef KE_TABLES_GLOBAL
+#define KE_TABLES_GLOBAL 0 /* 1: the code tables are read from global memory (L1) instead of a per-CTA copy in shared memory */
+#endif
+#ifndef KE_PRIV
+#define KE_PRIV 10 /* 4:4:4, one lane per block: 37.8 KB per CTA, six CTAs per SM */
+#endif
+    static const int PRIV = KE_PRIV;                     /* words of private stream per entry */
     static const int PSTRIDE = PRIV + 1;                 /* odd: lanes hit distinct banks */
-    static const int ROW_BYTES = ROWS * EC_ROW_CHUNKS * 16;
+    static const int ROW_BYTES = ROWS * KE_ROW_CHUNKS * 16;
     static const int STAGE_WORDS = ROW_BYTES / 4;        /* the chunk stream reuses the coefficient rows */
     static const int OFF_PRIV = ROW_BYTES;
     static const int OFF_H = OFF_PRIV + NT * PSTRIDE * 4;
-    static const int OFF_OFF = OFF_H + (int)sizeof(HuffPack);
+    static const int OFF_OFF = OFF_H + (KE_TABLES_GLOBAL ? 0 : (int)sizeof(HuffPack));
     static const int OFF_EX = OFF_OFF + NT * 4;
     static const int OFF_WARP = OFF_EX + NT * 4;
     static const int OFF_FLAG = OFF_WARP + (NT / 32) * 4;
-    static const int BYTES = OFF_FLAG + 16;
+#ifndef KE_PAD_BYTES
+#define KE_PAD_BYTES 0 /* occupancy experiments */
+#endif
+    static const int BYTES = OFF_FLAG + 16 + KE_PAD_BYTES;
 };
 template <int RATIO>
 using KeSmem = KeCfg<RATIO>;
@@ -732,10 +784,10 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     constexpr int BPM = EcCfg<RATIO>::BPM, NT = KeCfg<RATIO>::NT;
     typedef KeCfg<RATIO> L;
     extern __shared__ __align__(16) unsigned char ke_smem[];
-    uint4(*sC)[EC_ROW_CHUNKS] = reinterpret_cast<uint4(*)[EC_ROW_CHUNKS]>(ke_smem);
+    uint4(*sC)[KE_ROW_CHUNKS] = reinterpret_cast<uint4(*)[KE_ROW_CHUNKS]>(ke_smem);
     uint32_t *sS = reinterpret_cast<uint32_t *>(ke_smem); /* chunk stream, over the rows */
     uint32_t *sP = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_PRIV);
-    HuffPack &sH = *reinterpret_cast<HuffPack *>(ke_smem + L::OFF_H);
+    const HuffPack &sH = KE_TABLES_GLOBAL ? *huff : *reinterpret_cast<const HuffPack *>(ke_smem + L::OFF_H);
     uint32_t *sOff = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_OFF);
     uint32_t *sEx = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_EX);
     uint32_t *sWarp = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_WARP);
@@ -753,8 +805,8 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     p.dc_pred[1] = q.dc_pred_dev ? q.dc_pred_dev[1] : q.dc_pred[1];
     p.dc_pred[2] = q.dc_pred_dev ? q.dc_pred_dev[2] : q.dc_pred[2];
 
-    ec_fill<RATIO, NT>(sC, p, m0, tid);
-    ec_load_table<NT>(&sH, huff, tid);
+    ke_fill<RATIO, NT>(sC, p, m0, tid);
+    if (!KE_TABLES_GLOBAL) ec_load_table<NT>(reinterpret_cast<HuffPack *>(ke_smem + L::OFF_H), huff, tid);
     const KeMap<RATIO> mp(p, m0, tid);
     if (tid == 0) *sFlag = 0u;
     cp_async_wait_all();
@@ -769,22 +821,24 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     int prev0 = 0;
     bool eob = true, active;
     const bool split = mp.luma && L::SPLIT; /* warp-uniform: warps are component-pure */
+    const int sw = mp.row & 7;
+    const unsigned sw4 = (unsigned)sw << 4;
     if (split)
-        active = ec_entry_masks<false>(sC[mp.row], mp.part, mm, prev0, eob);
+        active = ec_entry_masks<false>(sC[mp.row], sw, mp.part, mm, prev0, eob);
     else
-        active = ec_entry_masks<true>(sC[mp.row], 0, mm, prev0, eob);
+        active = ec_entry_masks<true>(sC[mp.row], sw, 0, mm, prev0, eob);
     active = active && mp.valid;
     const uint32_t *tAc = sH.ac[mp.luma ? 0 : 1], *tDc = sH.dc[mp.luma ? 0 : 1], *tLut = sH.lut[mp.luma ? 0 : 1];
     if (mp.valid) {
         if (mp.part == 0) {
             int pred;
             if (!mp.first_of_comp)
-                pred = (int)(short)(sC[mp.row - 1][0].x & 0xffffu);
+                pred = (int)(short)(sC[mp.row - 1][(mp.row - 1) & 7].x & 0xffffu);
             else if (m0 == 0)
                 pred = p.dc_pred[mp.comp];
             else
                 pred = (int)p.zz[(mp.gabs - 1) * 64];
-            diff = (int)(short)(sC[mp.row][0].x & 0xffffu) - pred;
+            diff = (int)(short)(sC[mp.row][sw].x & 0xffffu) - pred;
         }
     }
     if (active) {
@@ -794,7 +848,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
         s.wp = priv;
         s.end = priv + L::PRIV;
         s.nwords = 0;
-        ec_pack_masked(sC[mp.row], mp.part == 0, diff, mm, prev0, eob, tAc, tDc, tLut, s);
+        ec_pack_masked(sC[mp.row], sw4, mp.part == 0, diff, mm, prev0, eob, tAc, tDc, tLut, s);
         nbits = s.finish();
         if (nbits > (uint32_t)L::PRIV * 32u) *sFlag = 1u;
     }
@@ -845,7 +899,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
         s.nacc = (int)(loff & 31u);
         s.wp = slot + (loff >> 5);
         s.first = true;
-        ec_pack_masked(sC[mp.row], mp.part == 0, diff, mm, prev0, eob, tAc, tDc, tLut, s);
+        ec_pack_masked(sC[mp.row], sw4, mp.part == 0, diff, mm, prev0, eob, tAc, tDc, tLut, s);
         s.finish();
     }
     __syncthreads();

@@ -29,7 +29,12 @@
 namespace jpgb200 {
 
 #define K1C_THREADS 256
+#ifndef K1C_STAGES
 #define K1C_STAGES 3
+#endif
+#ifndef K1C_SLEEP_NS
+#define K1C_SLEEP_NS 200
+#endif
 #define K1C_MIN_CTAS 2
 
 struct K1CSmem {
@@ -58,7 +63,7 @@ __device__ __forceinline__ void mbar_wait_relaxed(unsigned long long *bar, unsig
             : "r"(a), "r"(parity)
             : "memory");
         if (done) break;
-        __nanosleep(200);
+        __nanosleep(K1C_SLEEP_NS);
     }
 }
 
