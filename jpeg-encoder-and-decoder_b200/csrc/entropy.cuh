@@ -334,6 +334,40 @@ struct PackSink {
     }
 };
 
+/* ---- bit writer into KE's staged chunk stream (shared memory, NUMERIC words): the first and last word a block
+ * touches are shared with its neighbours and OR-ed, interior words are owned and stored */
+struct StageSink {
+    unsigned long long acc;
+    int nacc;
+    uint32_t *wp;
+    bool first;
+    __device__ __forceinline__ void or_word(uint32_t v)
+    {
+        const unsigned sa = (unsigned)__cvta_generic_to_shared(wp);
+        asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(sa), "r"(v) : "memory");
+    }
+    __device__ __forceinline__ void put(uint32_t v, int n)
+    {
+        acc = (acc << n) | (unsigned long long)v;
+        nacc += n;
+        if (nacc >= 32) {
+            nacc -= 32;
+            const uint32_t word = (uint32_t)(acc >> nacc);
+            if (first) {
+                or_word(word);
+                first = false;
+            } else {
+                *wp = word;
+            }
+            wp++;
+        }
+    }
+    __device__ __forceinline__ void finish()
+    {
+        if (nacc > 0) or_word((uint32_t)(acc << (32 - nacc)));
+    }
+};
+
 /* ---- block coder, packing form (K5) ------------------------------------------------------- */
 template <class Sink>
 __device__ __forceinline__ void ec_pack_block(const uint4 *row, int diff, const uint32_t *sAc, const uint32_t *sDc,
@@ -633,9 +667,10 @@ struct PrivSink {
  *              owns its slot, so nothing in HBM is shared between CTAs
  *   totals   : T per chunk and, atomically, per 64 chunks: the two-level sums from which KC
  *              derives every chunk's global bit offset (the device-wide exclusive prefix sum)
- * A chunk with a block longer than its private region, or a stream longer than the staging
- * area, is rare (> 64 bytes for one 8x8 block): it clears its slot and packs straight into it
- * at the offsets just computed (atomics on block-boundary words). */
+ * A block longer than its private region (> 40 bytes: busy luma blocks of noisy images) is coded a second
+ * time, straight into the staged stream at its offset (StageSink) -- only that block, not its chunk.  A chunk
+ * whose stream is longer than the staging area (> 24 KB for 192 blocks) clears its slot and packs straight
+ * into it at the offsets just computed (atomics on block-boundary words). */
 struct KeParams {
     const int16_t *zz;
     long long coff1, coff2, n_mcu;
@@ -785,13 +820,11 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     typedef KeCfg<RATIO> L;
     extern __shared__ __align__(16) unsigned char ke_smem[];
     uint4(*sC)[KE_ROW_CHUNKS] = reinterpret_cast<uint4(*)[KE_ROW_CHUNKS]>(ke_smem);
-    uint32_t *sS = reinterpret_cast<uint32_t *>(ke_smem); /* chunk stream, over the rows */
     uint32_t *sP = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_PRIV);
     const HuffPack &sH = KE_TABLES_GLOBAL ? *huff : *reinterpret_cast<const HuffPack *>(ke_smem + L::OFF_H);
     uint32_t *sOff = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_OFF);
     uint32_t *sEx = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_EX);
     uint32_t *sWarp = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_WARP);
-    uint32_t *sFlag = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_FLAG);
     const int tid = threadIdx.x;
     const long long chunk = blockIdx.x;
     const long long m0 = chunk * EC_MCUS;
@@ -808,7 +841,6 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     ke_fill<RATIO, NT>(sC, p, m0, tid);
     if (!KE_TABLES_GLOBAL) ec_load_table<NT>(reinterpret_cast<HuffPack *>(ke_smem + L::OFF_H), huff, tid);
     const KeMap<RATIO> mp(p, m0, tid);
-    if (tid == 0) *sFlag = 0u;
     cp_async_wait_all();
     __syncthreads();
 
@@ -835,7 +867,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
             if (!mp.first_of_comp)
                 pred = (int)(short)(sC[mp.row - 1][(mp.row - 1) & 7].x & 0xffffu);
             else if (m0 == 0)
-                pred = p.dc_pred[mp.comp];
+                pred = mp.comp == 0 ? p.dc_pred[0] : (mp.comp == 1 ? p.dc_pred[1] : p.dc_pred[2]);
             else
                 pred = (int)p.zz[(mp.gabs - 1) * 64];
             diff = (int)(short)(sC[mp.row][sw].x & 0xffffu) - pred;
@@ -850,7 +882,6 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
         s.nwords = 0;
         ec_pack_masked(sC[mp.row], sw4, mp.part == 0, diff, mm, prev0, eob, tAc, tDc, tLut, s);
         nbits = s.finish();
-        if (nbits > (uint32_t)L::PRIV * 32u) *sFlag = 1u;
     }
     sOff[mp.e_local] = nbits; /* stream order */
     __syncthreads(); /* every entry is coded: the coefficient rows are dead from here on */
@@ -868,25 +899,53 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
         atomicAdd(&q.super_bits[chunk >> EC_SUPER_SHIFT], total);
     }
     const uint32_t nwords = (total + 31u) >> 5;
-    const bool staged = (*sFlag == 0u) && nwords < (uint32_t)L::STAGE_WORDS; /* word [nwords] may receive an empty OR */
+    /* The chunk stream is assembled in shared memory at the END of the (dead) coefficient rows, 16-byte aligned and
+     * zero-padded to whole 16-byte groups: the rows in front of it -- the luma rows, which are the ones that
+     * outgrow a private region -- stay readable. */
+    const uint32_t ngroups = (nwords + 4u) >> 2; /* covers word [nwords], which may receive an empty OR */
+    const bool staged = ngroups * 4u <= (uint32_t)L::STAGE_WORDS;
     uint32_t *slot = q.tmp + chunk * q.slot_words;
     const uint32_t loff = sEx[mp.e_local];
     if (staged) {
-        /* the chunk stream takes the place of the (dead) coefficient rows */
-        for (uint32_t i = tid; i < nwords + 1u; i += NT) sS[i] = 0u;
+        const uint32_t stage0 = (uint32_t)L::STAGE_WORDS - ngroups * 4u; /* first word of the stream */
+        uint32_t *sS = reinterpret_cast<uint32_t *>(ke_smem) + stage0;
+        uint4 *sS4 = reinterpret_cast<uint4 *>(sS);
+        /* a block that outgrew its private region is coded a second time, straight into the staged stream: from
+         * its row if the stream does not reach it, else from HBM/L2 */
+        const bool again = active && nbits > (uint32_t)L::PRIV * 32u;
+        const bool row_alive = ((uint32_t)mp.row + 1u) * 32u <= stage0;
+        for (uint32_t i = tid; i < ngroups; i += NT) sS4[i] = make_uint4(0u, 0u, 0u, 0u);
         __syncthreads();
-        if (active) {
+        if (active && !again) {
             const uint32_t sh = loff & 31u, nw = (nbits + 31u) >> 5;
-            uint32_t *dst = sS + (loff >> 5);
-            for (uint32_t i = 0; i < nw; i++) {
+            unsigned a0 = (unsigned)__cvta_generic_to_shared(sS + (loff >> 5));
+            uint32_t prevw = 0u;
+            for (uint32_t i = 0; i < nw; i++, a0 += 4u) {
                 const uint32_t v = priv[i];
-                const unsigned a0 = (unsigned)__cvta_generic_to_shared(dst + i);
-                asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a0), "r"(v >> sh) : "memory");
-                if (sh) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a0 + 4u), "r"(v << (32u - sh)) : "memory");
+                asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a0), "r"(__funnelshift_r(v, prevw, sh)) : "memory");
+                prevw = v;
             }
+            if (sh) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a0), "r"(prevw << (32u - sh)) : "memory");
+        } else if (again) {
+            StageSink s;
+            s.acc = 0;
+            s.nacc = (int)(loff & 31u);
+            s.wp = sS + (loff >> 5);
+            s.first = true;
+            if (row_alive)
+                ec_pack_masked(sC[mp.row], sw4, mp.part == 0, diff, mm, prev0, eob, tAc, tDc, tLut, s);
+            else
+                ec_pack_masked(reinterpret_cast<const uint4 *>(p.zz + mp.gabs * 64), 0u, mp.part == 0, diff, mm, prev0, eob, tAc,
+                               tDc, tLut, s);
+            s.finish();
         }
         __syncthreads();
-        for (uint32_t i = tid; i < nwords; i += NT) slot[i] = __byte_perm(sS[i], 0, 0x0123);
+        uint4 *slot4 = reinterpret_cast<uint4 *>(slot);
+        for (uint32_t i = tid; i < ((nwords + 3u) >> 2); i += NT) {
+            const uint4 v = sS4[i];
+            slot4[i] = make_uint4(__byte_perm(v.x, 0, 0x0123), __byte_perm(v.y, 0, 0x0123), __byte_perm(v.z, 0, 0x0123),
+                                  __byte_perm(v.w, 0, 0x0123));
+        }
         if (tid == 0) q.cta_tail[chunk] = stream_tail32(sS, total, false);
         return;
     }
