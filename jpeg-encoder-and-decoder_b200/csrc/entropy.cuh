@@ -932,11 +932,14 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
             s.nacc = (int)(loff & 31u);
             s.wp = sS + (loff >> 5);
             s.first = true;
-            if (row_alive)
-                ec_pack_masked(sC[mp.row], sw4, mp.part == 0, diff, mm, prev0, eob, tAc, tDc, tLut, s);
-            else
-                ec_pack_masked(reinterpret_cast<const uint4 *>(p.zz + mp.gabs * 64), 0u, mp.part == 0, diff, mm, prev0, eob, tAc,
-                               tDc, tLut, s);
+            /* the row goes to thread-local memory first (eight 16-byte loads in flight together): a dead row
+             * would otherwise cost one dependent L2 round trip per coefficient */
+            uint4 loc[8];
+            const uint4 *src = row_alive ? sC[mp.row] : reinterpret_cast<const uint4 *>(p.zz + mp.gabs * 64);
+            const int swz = row_alive ? sw : 0;
+#pragma unroll
+            for (int j = 0; j < 8; j++) loc[j] = src[j ^ swz];
+            ec_pack_masked(loc, 0u, mp.part == 0, diff, mm, prev0, eob, tAc, tDc, tLut, s);
             s.finish();
         }
         __syncthreads();

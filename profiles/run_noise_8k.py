@@ -4,6 +4,8 @@ import numpy as np, torch
 import __graft_entry__ as ge
 pkg = ge.load_package()
 enc = pkg.Encoder(0)
+enc.set_pipelined_batch(0)
+enc.set_batch_overlap(0)  # isolated kernel spans
 W, H = 7680, 4320
 planes = torch.empty((2, 3, H, W), dtype=torch.uint8, device="cuda")
 out = torch.empty((2, 3 * W * H), dtype=torch.uint8, device="cuda")
