@@ -59,6 +59,9 @@ struct EvPair {
     cudaEvent_t a, b;
 };
 
+#ifndef K1_FOUR_DEFAULT
+#define K1_FOUR_DEFAULT false /* 4:4:4 K1 with four transform warps per CTA (k1_transform_pc4) */
+#endif
 struct jpgb200_ctx {
     int device;
     int sm_count;
@@ -93,6 +96,7 @@ struct jpgb200_ctx {
     bool k1_ws;    /* the warp-autonomous K1 (k1_warp.cuh) */
     bool k1c_attr_set;
     bool k1_tmaload, k1t_attr_set; /* K1 fed by 2-D TMA tile loads (k1_transform_pct, JPGB200_K1=pct) */
+    bool k1_four, k1c4_attr_set;   /* 4:4:4: four transform warps per CTA taking component units in turn (k1_transform_pc4) */
     K1TLoad k1t_maps;
     bool no_tma_store; /* k1_pipe: copy the coefficients out with ordinary stores (A/B runs) */
     CUtensorMap tm32, tm16; /* tensor maps of the coefficient buffer, cached (two entries: the pipelined batch alternates buffers) */
@@ -467,6 +471,7 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
     ctx->q_cached = -1;
     ctx->legacy_entropy = true; /* measured faster than the fused K35 so far */
     ctx->k1_pc = true;          /* K1 default: the producer/consumer form (fastest measured) */
+    ctx->k1_four = K1_FOUR_DEFAULT;
     ctx->group_small = true;
     {
         const char *pz = getenv("JPGB200_PIPELINED"); /* "0": K1 and KE of a batch strictly one after the other */
@@ -486,6 +491,8 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         if (k && !strcmp(k, "plain")) ctx->k1_plain = true, ctx->k1_pc = false;
         if (k && !strcmp(k, "pc_notma")) ctx->no_tma_store = true;
         if (k && !strcmp(k, "pct")) ctx->k1_tmaload = true;
+        if (k && !strcmp(k, "pc4")) ctx->k1_four = true;
+        if (k && !strcmp(k, "pc3")) ctx->k1_four = false;
         if (jpgb200_has_ab_forms()) {
             if (k && !strcmp(k, "cta")) ctx->k1_cta = true, ctx->k1_pc = false;
             if (k && !strcmp(k, "pipe")) ctx->k1_pipe = true, ctx->k1_pc = false;
@@ -634,9 +641,10 @@ extern "C" int jpgb200_has_ab_forms(void)
 extern "C" int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;
-    if (on >= 2 && on <= 4 && !jpgb200_has_ab_forms()) return JPGB200_ERR_BAD_ARG; /* forms 2..4 are A/B builds only */
-    ctx->k1_pc = (on == 0 || on == 5 || on == 6);
+    if (((on >= 2 && on <= 4) || on == 7) && !jpgb200_has_ab_forms()) return JPGB200_ERR_BAD_ARG; /* forms 2..4 and 7 are A/B builds only */
+    ctx->k1_pc = (on == 0 || on == 5 || on == 6 || on == 7);
     ctx->k1_tmaload = (on == 6); /* 5: the cp.async-fed form explicitly, 6: the TMA-load-fed form */
+    ctx->k1_four = (on == 7) || (on == 0 && K1_FOUR_DEFAULT); /* 7: four transform warps (4:4:4, A/B builds), 5: three */
     ctx->k1_plain = (on == 1);
     ctx->k1_cta = (on == 2);
     ctx->k1_pipe = (on == 3);
@@ -1131,6 +1139,26 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
             k1_transform_pct<0, false><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st, ctx->k1t_maps);
         else
             k1_transform_pct<1, false><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st, ctx->k1t_maps);
+#ifdef JPGB200_AB
+    } else if (aligned16 && ctx->k1_pc && ctx->k1_four && ratio == 0 && !ctx->k1_plain) {
+        /* 4:4:4: four convert + four transform warps, component units handed round-robin (k1_pc.cuh: k1_transform_pc4) */
+        const size_t smem = sizeof(K1C4Smem) + 1024;
+        if (!ctx->k1c4_attr_set) {
+            CK(cudaFuncSetAttribute((k1_transform_pc4<false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute((k1_transform_pc4<true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->k1c4_attr_set = true;
+        }
+        const long long n_tiles = (long long)p.tiles_per_row * (h / 8) * nframes;
+        const long long resident = (long long)ctx->sm_count * (ctx->k1_ctas_per_sm > 0 ? ctx->k1_ctas_per_sm : K1C_MIN_CTAS);
+        const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+        K1PStore st;
+        make_store_maps(ctx, &st, zz, n, zz_stride, nframes);
+        LaunchScope ls(ctx, KI_K1);
+        if (ctx->std_mode)
+            k1_transform_pc4<true><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
+        else
+            k1_transform_pc4<false><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
+#endif
     } else if (aligned16 && ctx->k1_pc && !ctx->k1_plain) {
         /* eight specialised warps per CTA handing tiles over through mbarriers (k1_pc.cuh) */
         const size_t smem = sizeof(K1CSmem) + 1024;

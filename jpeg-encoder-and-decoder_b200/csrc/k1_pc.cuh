@@ -35,7 +35,9 @@ namespace jpgb200 {
 #ifndef K1C_SLEEP_NS
 #define K1C_SLEEP_NS 200
 #endif
+#ifndef K1C_MIN_CTAS
 #define K1C_MIN_CTAS 2
+#endif
 
 struct K1CSmem {
     K1Out coef[2][3];                       /* 24 KB, 1 KB aligned (TMA swizzle) */
@@ -242,6 +244,179 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pc(con
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
 }
+
+/* ---- K1, producer/consumer form with FOUR transform warps (k1_transform_pc4, 4:4:4) ---------------------------
+ * k1_transform_pc gives each of its three transform warps one component of every tile: with two CTAs per SM that is
+ * six transform warps on four schedulers (2, 2, 1, 1), and the store warp idles.  Here the tile's three components
+ * are UNITS handed round-robin to four transform warps (unit u = 3 * tile + component goes to warp u % 4): eight
+ * transform warps per SM, two per scheduler, each with 3/4 of a tile's arithmetic per tile time.  There is no store
+ * warp: the warp that transformed a unit issues its TMA tensor store (one 32-block box) itself and hands the
+ * coefficient buffer back -- after the next unit's samples are in its registers, when the store has long read
+ * shared memory -- through one mbarrier per (buffer, component).
+ * MEASURED (profiles/README.md, round 2): bit-identical, the four schedulers evenly loaded (issue active 58.4-59.7 %
+ * against 45.6-60.6 %), but 79.9 us per 8K frame against 77.1 us: the component index is no longer a per-warp
+ * constant (14 % more instructions) and the transform warps gain nothing from two more of their kind -- each one
+ * runs at its own pace of ~3.6 cycles per instruction either way.  An A/B form (JPGB200_AB=1), not in the product. */
+#ifdef JPGB200_AB
+struct K1C4Smem {
+    K1Out coef[2][3];
+    K1F samples[2][3];
+    uint8_t raw[4][K1C_STAGES][3][2][K1_ROW_BYTES];
+    float mul[2][64];
+    unsigned long long samples_full[2], samples_free[2], coef_free[2][3];
+};
+
+/* one component's 32 blocks of a tile cut short by the image's right edge: coalesced 16-byte stores by one warp */
+__device__ __forceinline__ void k1c4_copyout(const K1Out &sOut, const K1Params &p, const K1Tile &tl, int c, int lane)
+{
+    int16_t *z = (c == 0 ? p.zz_y : (c == 1 ? p.zz_cb : p.zz_cr)) + (long long)tl.frame * p.zz_stride;
+    uint4 *dst = reinterpret_cast<uint4 *>(z + ((long long)tl.by * p.BW + tl.tb0) * 64);
+    const int ch = lane & 7, jsub = lane >> 3;
+    const int nvalid = min(K1_TILE_BLOCKS, p.BW - tl.tb0);
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const int j = t * 4 + jsub;
+        if (j < nvalid) dst[j * 8 + ch] = sOut[j][ch ^ (j & 7)];
+    }
+}
+
+template <bool STD = false>
+__global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pc4(const K1Params p, long long n_tiles,
+                                                                               const __grid_constant__ K1PStore st)
+{
+    extern __shared__ unsigned char k1_smem_raw[];
+    unsigned char *k1_smem = k1_smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(k1_smem_raw) & 1023u)) & 1023u);
+    K1C4Smem &S = *reinterpret_cast<K1C4Smem *>(k1_smem);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+
+    if (tid < 128) S.mul[tid >> 6][tid & 63] = p.mul[tid >> 6][tid & 63];
+    if (blockIdx.x == 0)
+        for (int i = tid; i < p.clear_n; i += K1C_THREADS) p.clear[i] = 0u;
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&S.samples_full[b], 4);
+            mbar_init(&S.samples_free[b], 3);
+#pragma unroll
+            for (int c = 0; c < 3; c++) mbar_init(&S.coef_free[b][c], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (w < 4) {
+        /* ================= convert warp k: as in k1_transform_pc ================= */
+        const int k = w;
+        uint8_t(*ring)[3][2][K1_ROW_BYTES] = S.raw[k];
+#pragma unroll
+        for (int d = 0; d < K1C_STAGES - 1; d++) {
+            const long long td = (long long)blockIdx.x + (long long)d * gridDim.x;
+            if (td < n_tiles)
+                k1c_fetch<STD>(p, ring[d], k1_tile(p, td), k, lane);
+            else
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        int it = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+            const int b = it & 1;
+            const unsigned use = (unsigned)(it >> 1);
+            const K1Tile tl = k1_tile(p, t);
+            {
+                const long long tn = t + (long long)(K1C_STAGES - 1) * gridDim.x;
+                if (tn < n_tiles)
+                    k1c_fetch<STD>(p, ring[(it + K1C_STAGES - 1) % K1C_STAGES], k1_tile(p, tn), k, lane);
+                else
+                    asm volatile("cp.async.commit_group;\n" ::: "memory");
+            }
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(K1C_STAGES - 1) : "memory");
+            __syncwarp();
+            const uint8_t(*raw)[2][K1_ROW_BYTES] = ring[it % K1C_STAGES];
+            const int jl = STD ? -1 : p.BW - 1 - tl.tb0;
+            const bool top_oob = (tl.by == 0 && !p.has_halo && k == 0);
+            auto ld8 = [&](int c, int sel, int j) -> uint2 {
+                if (top_oob && sel == 0 && j == jl) return ld_oob(p.oob + 8 * c);
+                return *reinterpret_cast<const uint2 *>(&raw[c][sel][j * 8]);
+            };
+            uint2 pa[3], pb[3];
+#pragma unroll
+            for (int c = 0; c < 3; c++) {
+                pa[c] = ld8(c, 0, lane);
+                pb[c] = ld8(c, 1, lane);
+            }
+            mbar_wait_relaxed(&S.samples_free[b], (use & 1u) ^ 1u); /* the transform warps have taken tile it-2 */
+            k1_convert_full<0, STD>(S.samples[b], k, lane, pa, pb);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.samples_full[b]);
+        }
+    } else {
+        /* ================= transform warp x: units x, x + 4, x + 8, ... ================= */
+        const int x = w - 4;
+        const long long my_tiles = (n_tiles - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
+        const int n_units = (int)(my_tiles * 3);
+        int pend_b = -1, pend_c = 0; /* a TMA store of this warp that may still be reading shared memory */
+        for (int u = x; u < n_units; u += 4) {
+            const int it = (int)((unsigned)u / 3u);
+            const int c = u - 3 * it;
+            const int b = it & 1;
+            const unsigned use = (unsigned)(it >> 1);
+            const float4 *m4 = reinterpret_cast<const float4 *>(S.mul[c == 0 ? 0 : 1]);
+            f32x2 P[4][8], Q[8][4];
+            mbar_wait(&S.samples_full[b], use & 1u);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int xx = 0; xx < 8; xx++) P[k][xx] = S.samples[b][c][k][xx][lane];
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&S.samples_free[b]);
+                if (pend_b >= 0) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    mbar_arrive(&S.coef_free[pend_b][pend_c]);
+                }
+            }
+            pend_b = -1;
+            fdct8x8_p(P, Q);
+            float f[64];
+#pragma unroll
+            for (int v = 0; v < 8; v++)
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const float4 m = m4[v * 2 + hh];
+                    const f32x2 q0 = p_fma(Q[v][2 * hh], make_float2(m.x, m.y), p_bc(JPGB_ROUND_MAGIC));
+                    const f32x2 q1 = p_fma(Q[v][2 * hh + 1], make_float2(m.z, m.w), p_bc(JPGB_ROUND_MAGIC));
+                    f[v * 8 + 4 * hh + 0] = q0.x;
+                    f[v * 8 + 4 * hh + 1] = q0.y;
+                    f[v * 8 + 4 * hh + 2] = q1.x;
+                    f[v * 8 + 4 * hh + 3] = q1.y;
+                }
+            uint32_t o[32];
+            zigzag_pack(f, o);
+            mbar_wait(&S.coef_free[b][c], (use & 1u) ^ 1u); /* tile it-2's unit has left the buffer */
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                S.coef[b][c][lane][j ^ (lane & 7)] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            const K1Tile tl = k1_tile(p, (long long)blockIdx.x + (long long)it * gridDim.x);
+            if (st.enabled && tl.tb0 + K1_TILE_BLOCKS <= p.BW) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic writes -> the TMA's proxy */
+                __syncwarp();
+                if (lane == 0) {
+                    const long long ry = (long long)tl.frame * st.rows_per_frame + (long long)tl.by * p.BW + tl.tb0;
+                    tma_store_2d(&st.box32, &S.coef[b][c], 0, (int)(ry + (c == 0 ? 0ll : (c == 1 ? st.row_cb : st.row_cr))));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                pend_b = b;
+                pend_c = c;
+            } else {
+                __syncwarp();
+                k1c4_copyout(S.coef[b][c], p, tl, c, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.coef_free[b][c]);
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+#endif /* JPGB200_AB */
 
 /* ---- K1, producer/consumer form fed by 2-D TMA tile loads (k1_transform_pct) --------------------------------
  * k1_transform_pc's convert warps fetch their own two rows of the tile with cp.async: 27 LDGSTS and their

@@ -415,6 +415,13 @@ def test_tma_and_plain_transform_agree(enc, pkg, w, h, q, ratio, seed):
         enc.set_plain_transform(6)  # the producer/consumer form fed by 2-D TMA tile loads (UTMALDG)
         t6 = enc.coefficients(r, g, b, w, h, q, ratio)
         assert (a == t6).all()
+        if pkg.binding.has_ab_forms():
+            enc.set_plain_transform(7)  # four transform warps per CTA taking component units in turn (4:4:4; else = form 5)
+            t7 = enc.coefficients(r, g, b, w, h, q, ratio)
+            assert (a == t7).all()
+        enc.set_plain_transform(5)  # three transform warps, one per component
+        t5 = enc.coefficients(r, g, b, w, h, q, ratio)
+        assert (a == t5).all()
         c = d = e = a
         if pkg.binding.has_ab_forms():  # the three older forms exist in JPGB200_AB=1 builds only
             enc.set_plain_transform(2)
