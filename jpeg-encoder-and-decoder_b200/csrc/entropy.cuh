@@ -164,34 +164,42 @@ __device__ __forceinline__ void ec_fill(uint4 (*sC)[EC_ROW_CHUNKS], const EcPara
  * less shared memory than with 144-byte rows -- the sixth resident CTA per SM (KE lives on occupancy). */
 #define KE_ROW_CHUNKS 8
 
+__device__ __forceinline__ void cp_async16_sa(unsigned sa, const void *gmem)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(sa), "l"(gmem) : "memory");
+}
+
+/* Piece i = k * NT + tid of a component run goes to row i / 8, chunk (i & 7) ^ (row & 7).  NT is a multiple of 64,
+ * so row & 7 and i & 7 do not depend on k: a thread's shared address is ONE base plus k * NT * 16 bytes, and the
+ * global address likewise -- no per-copy address arithmetic. */
 template <int RATIO, int NTH>
 __device__ __forceinline__ void ke_fill(uint4 (*sC)[KE_ROW_CHUNKS], const EcParams &p, long long m0, int tid)
 {
     constexpr int NT = NTH;
+    static_assert(NT % 64 == 0, "ke_fill: the swizzle term must not depend on the iteration");
     const long long left = p.n_mcu - m0;
     const int nv = left < EC_MCUS ? (int)left : EC_MCUS; /* valid MCUs of this chunk */
     const uint4 *z = reinterpret_cast<const uint4 *>(p.zz);
+    const int r0 = tid >> 3;
+    const unsigned sa0 = (unsigned)__cvta_generic_to_shared(sC) + (unsigned)r0 * 128u + (unsigned)(((tid & 7) ^ (r0 & 7)) << 4);
     {
         constexpr int YPM = (RATIO == 0) ? 1 : (RATIO == 1 ? 2 : 4); /* luma blocks per MCU */
         const int n0 = YPM * nv * 8;
-        const uint4 *src = z + YPM * m0 * 8;
+        const uint4 *src = z + YPM * m0 * 8 + tid;
 #pragma unroll
-        for (int k = 0; k < (YPM * 64 * 8 + NT - 1) / NT; k++) {
-            const int i = k * NT + tid, r = i >> 3;
-            if (i < n0) cp_async16(&sC[r][(i & 7) ^ (r & 7)], src + i);
-        }
+        for (int k = 0; k < (YPM * 64 * 8 + NT - 1) / NT; k++)
+            if (k * NT + tid < n0) cp_async16_sa(sa0 + (unsigned)(k * NT * 16), src + k * NT);
     }
     {
-        const int n1 = nv * 8, r1 = (RATIO == 0 ? 64 : (RATIO == 1 ? 128 : 256));
-        const uint4 *s1 = z + (p.coff1 + m0) * 8, *s2 = z + (p.coff2 + m0) * 8;
+        constexpr int r1 = (RATIO == 0 ? 64 : (RATIO == 1 ? 128 : 256)); /* r1 and r1 + 64 are multiples of 8 */
+        const int n1 = nv * 8;
+        const uint4 *s1 = z + (p.coff1 + m0) * 8 + tid, *s2 = z + (p.coff2 + m0) * 8 + tid;
 #pragma unroll
-        for (int k = 0; k < (64 * 8 + NT - 1) / NT; k++) {
-            const int i = k * NT + tid, r = i >> 3; /* r1 and r1 + 64 are multiples of 8: the swizzle sees r & 7 */
-            if (i < n1) {
-                cp_async16(&sC[r1 + r][(i & 7) ^ (r & 7)], s1 + i);
-                cp_async16(&sC[r1 + 64 + r][(i & 7) ^ (r & 7)], s2 + i);
+        for (int k = 0; k < (64 * 8 + NT - 1) / NT; k++)
+            if (k * NT + tid < n1) {
+                cp_async16_sa(sa0 + (unsigned)(r1 * 128 + k * NT * 16), s1 + k * NT);
+                cp_async16_sa(sa0 + (unsigned)((r1 + 64) * 128 + k * NT * 16), s2 + k * NT);
             }
-        }
     }
 }
 
@@ -200,11 +208,11 @@ template <int NTH, class T>
 __device__ __forceinline__ void ec_load_table(T *sT, const T *g, int tid)
 {
     static_assert(sizeof(T) % 16 == 0, "table size");
+    const unsigned sa = (unsigned)__cvta_generic_to_shared(sT) + (unsigned)tid * 16u;
+    const uint4 *src = reinterpret_cast<const uint4 *>(g) + tid;
 #pragma unroll
-    for (int i = 0; i < ((int)(sizeof(T) / 16) + NTH - 1) / NTH; i++) {
-        const int j = i * NTH + tid;
-        if (j < (int)(sizeof(T) / 16)) cp_async16(reinterpret_cast<uint4 *>(sT) + j, reinterpret_cast<const uint4 *>(g) + j);
-    }
+    for (int i = 0; i < ((int)(sizeof(T) / 16) + NTH - 1) / NTH; i++)
+        if (i * NTH + tid < (int)(sizeof(T) / 16)) cp_async16_sa(sa + (unsigned)(i * NTH * 16), src + i * NTH);
 }
 
 /* DC predictor: the previous block of the same component (raster == scan order per
@@ -807,15 +815,15 @@ struct KeMap {
 template <int RATIO>
 __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KeParams q0, const HuffPack *huff)
 {
-    KeParams q = q0;
-    if (blockIdx.y) { /* frame of a multi-frame launch */
-        const long long f = blockIdx.y;
-        q.zz += f * q.zz_fstride;
-        q.tmp += f * q.tmp_fstride;
-        q.cta_bits += f * q.cta_fstride;
-        q.cta_tail += f * q.cta_fstride;
-        q.super_bits += f * q.super_fstride;
-    }
+    /* frame of a multi-frame launch (blockIdx.y): every array advances by its stride.  The parameters are read where
+     * they are used (constant bank) -- a copy of the struct would cost every warp its set-up. */
+    const KeParams &q = q0;
+    const long long fr = blockIdx.y;
+    const int16_t *const zz_f = q0.zz + fr * q0.zz_fstride;
+    uint32_t *const tmp_f = q0.tmp + fr * q0.tmp_fstride;
+    uint32_t *const cta_bits_f = q0.cta_bits + fr * q0.cta_fstride;
+    uint32_t *const cta_tail_f = q0.cta_tail + fr * q0.cta_fstride;
+    uint32_t *const super_bits_f = q0.super_bits + fr * q0.super_fstride;
     constexpr int BPM = EcCfg<RATIO>::BPM, NT = KeCfg<RATIO>::NT;
     typedef KeCfg<RATIO> L;
     extern __shared__ __align__(16) unsigned char ke_smem[];
@@ -830,7 +838,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     const long long m0 = chunk * EC_MCUS;
 
     EcParams p;
-    p.zz = q.zz;
+    p.zz = zz_f;
     p.coff1 = q.coff1;
     p.coff2 = q.coff2;
     p.n_mcu = q.n_mcu;
@@ -895,8 +903,8 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     __syncthreads();
     if (q.local_off && mp.valid && mp.blk_local >= 0) q.local_off[m0 * BPM + mp.blk_local] = sEx[mp.e_local];
     if (tid == 0) {
-        q.cta_bits[chunk] = total;
-        atomicAdd(&q.super_bits[chunk >> EC_SUPER_SHIFT], total);
+        cta_bits_f[chunk] = total;
+        atomicAdd(&super_bits_f[chunk >> EC_SUPER_SHIFT], total);
     }
     const uint32_t nwords = (total + 31u) >> 5;
     /* The chunk stream is assembled in shared memory at the END of the (dead) coefficient rows, 16-byte aligned and
@@ -904,7 +912,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
      * outgrow a private region -- stay readable. */
     const uint32_t ngroups = (nwords + 4u) >> 2; /* covers word [nwords], which may receive an empty OR */
     const bool staged = ngroups * 4u <= (uint32_t)L::STAGE_WORDS;
-    uint32_t *slot = q.tmp + chunk * q.slot_words;
+    uint32_t *slot = tmp_f + chunk * q.slot_words;
     const uint32_t loff = sEx[mp.e_local];
     if (staged) {
         const uint32_t stage0 = (uint32_t)L::STAGE_WORDS - ngroups * 4u; /* first word of the stream */
@@ -949,7 +957,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
             slot4[i] = make_uint4(__byte_perm(v.x, 0, 0x0123), __byte_perm(v.y, 0, 0x0123), __byte_perm(v.z, 0, 0x0123),
                                   __byte_perm(v.w, 0, 0x0123));
         }
-        if (tid == 0) q.cta_tail[chunk] = stream_tail32(sS, total, false);
+        if (tid == 0) cta_tail_f[chunk] = stream_tail32(sS, total, false);
         return;
     }
     /* rare: straight into the slot */
@@ -965,7 +973,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
         s.finish();
     }
     __syncthreads();
-    if (tid == 0) q.cta_tail[chunk] = stream_tail32(slot, total, true);
+    if (tid == 0) cta_tail_f[chunk] = stream_tail32(slot, total, true);
 }
 
 }  // namespace jpgb200
