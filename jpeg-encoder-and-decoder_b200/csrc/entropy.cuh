@@ -33,12 +33,16 @@ struct HuffDev {
 /* KE's pack tables: ((code << category) << 5) | (code_length + category): the code already
  * shifted to make room for the additional bits, and the total length, in one word */
 struct HuffPack {
-    uint32_t ac[2][256];
-    uint32_t dc[2][16];
     /* [lum|chr][run * 8 + value + 4], |value| <= 3 (99 % of the non-zero coefficients of the headline frames): the
-     * ac word of (run, category of value) with value's additional bits already merged */
+     * ac word of (run, category of value) with value's additional bits already merged.  value = 0 never occurs:
+     * entry [4] holds the end-of-block code and [12] the ZRL code (KE keeps lut + dc in shared memory and can
+     * leave the rarely used ac table in global memory: KE_AC_GLOBAL) */
     uint32_t lut[2][128];
+    uint32_t dc[2][16];
+    uint32_t ac[2][256];
 };
+#define HP_LUT_EOB 4
+#define HP_LUT_ZRL 12
 /* count tables: total bits of one symbol incl. its additional bits; the AC table is
  * extended to runs of up to 62 zeros, folding in the ZRL codes a long run needs */
 struct HuffBits {
@@ -204,15 +208,20 @@ __device__ __forceinline__ void ke_fill(uint4 (*sC)[KE_ROW_CHUNKS], const EcPara
 }
 
 /* tables -> shared memory, 16 bytes per copy, NTH threads */
-template <int NTH, class T>
-__device__ __forceinline__ void ec_load_table(T *sT, const T *g, int tid)
+template <int NTH, int BYTES>
+__device__ __forceinline__ void ec_load_bytes(void *sT, const void *g, int tid)
 {
-    static_assert(sizeof(T) % 16 == 0, "table size");
+    static_assert(BYTES % 16 == 0, "table size");
     const unsigned sa = (unsigned)__cvta_generic_to_shared(sT) + (unsigned)tid * 16u;
     const uint4 *src = reinterpret_cast<const uint4 *>(g) + tid;
 #pragma unroll
-    for (int i = 0; i < ((int)(sizeof(T) / 16) + NTH - 1) / NTH; i++)
-        if (i * NTH + tid < (int)(sizeof(T) / 16)) cp_async16_sa(sa + (unsigned)(i * NTH * 16), src + i * NTH);
+    for (int i = 0; i < (BYTES / 16 + NTH - 1) / NTH; i++)
+        if (i * NTH + tid < BYTES / 16) cp_async16_sa(sa + (unsigned)(i * NTH * 16), src + i * NTH);
+}
+template <int NTH, class T>
+__device__ __forceinline__ void ec_load_table(T *sT, const T *g, int tid)
+{
+    ec_load_bytes<NTH, (int)sizeof(T)>(sT, g, tid);
 }
 
 /* DC predictor: the previous block of the same component (raster == scan order per
@@ -504,7 +513,7 @@ __device__ __forceinline__ void ec_pack_masked(const uint4 *row, unsigned sw4, b
                 continue;
             }
             if (run > 15) { /* rare: one ZRL code per 16 zeros */
-                const uint32_t zrl = sAc[0xF0];
+                const uint32_t zrl = lut[HP_LUT_ZRL];
                 do {
                     s.put(zrl >> 5, (int)(zrl & 31u));
                     run -= 16;
@@ -517,7 +526,7 @@ __device__ __forceinline__ void ec_pack_masked(const uint4 *row, unsigned sw4, b
         }
     }
     if (eob && prev != 63) {
-        const uint32_t eobc = sAc[0x00];
+        const uint32_t eobc = lut[HP_LUT_EOB];
         s.put(eobc >> 5, (int)(eobc & 31u));
     }
 }
@@ -713,16 +722,25 @@ struct KeCfg {
 #ifndef KE_TABLES_GLOBAL
 #define KE_TABLES_GLOBAL 0 /* 1: the code tables are read from global memory (L1) instead of a per-CTA copy in shared memory */
 #endif
-#ifndef KE_PRIV
-#define KE_PRIV 10 /* 4:4:4, one lane per block: 37.8 KB per CTA, six CTAs per SM */
+#ifndef KE_AC_GLOBAL
+#define KE_AC_GLOBAL 1 /* 1: only lut + dc (1152 bytes) are copied to shared memory, the (run, category) table stays in global memory */
 #endif
-    static const int PRIV = KE_PRIV;                     /* words of private stream per entry */
+#define KE_TABLE_BYTES (KE_TABLES_GLOBAL ? 0 : (KE_AC_GLOBAL ? (int)(sizeof(uint32_t) * (2 * 128 + 2 * 16)) : (int)sizeof(HuffPack)))
+    /* words of private stream per entry.  KE lives on occupancy (shared memory per CTA): 4:4:4 with 5 words and the
+     * (run, category) table left in global memory is 31.9 KB -> SEVEN CTAs per SM (72.6 us per 8K frame against
+     * 77.0 us with 10 words and all tables in shared memory: six CTAs); 4:2:2 with 8 words is 45.2 KB -> five CTAs.
+     * A block that outgrows its region is coded a second time, alone (see below). */
+#ifdef KE_PRIV
+    static const int PRIV = KE_PRIV;
+#else
+    static const int PRIV = (RATIO == 0) ? 5 : (RATIO == 1 ? 8 : 10);
+#endif
     static const int PSTRIDE = PRIV + 1;                 /* odd: lanes hit distinct banks */
     static const int ROW_BYTES = ROWS * KE_ROW_CHUNKS * 16;
     static const int STAGE_WORDS = ROW_BYTES / 4;        /* the chunk stream reuses the coefficient rows */
     static const int OFF_PRIV = ROW_BYTES;
     static const int OFF_H = OFF_PRIV + NT * PSTRIDE * 4;
-    static const int OFF_OFF = OFF_H + (KE_TABLES_GLOBAL ? 0 : (int)sizeof(HuffPack));
+    static const int OFF_OFF = OFF_H + KE_TABLE_BYTES;
     static const int OFF_EX = OFF_OFF + NT * 4;
     static const int OFF_WARP = OFF_EX + NT * 4;
     static const int OFF_FLAG = OFF_WARP + (NT / 32) * 4;
@@ -847,7 +865,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     p.dc_pred[2] = q.dc_pred_dev ? q.dc_pred_dev[2] : q.dc_pred[2];
 
     ke_fill<RATIO, NT>(sC, p, m0, tid);
-    if (!KE_TABLES_GLOBAL) ec_load_table<NT>(reinterpret_cast<HuffPack *>(ke_smem + L::OFF_H), huff, tid);
+    if (!KE_TABLES_GLOBAL) ec_load_bytes<NT, KE_TABLE_BYTES>(ke_smem + L::OFF_H, huff, tid); /* lut and dc come first in HuffPack */
     const KeMap<RATIO> mp(p, m0, tid);
     cp_async_wait_all();
     __syncthreads();
@@ -868,7 +886,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     else
         active = ec_entry_masks<true>(sC[mp.row], sw, 0, mm, prev0, eob);
     active = active && mp.valid;
-    const uint32_t *tAc = sH.ac[mp.luma ? 0 : 1], *tDc = sH.dc[mp.luma ? 0 : 1], *tLut = sH.lut[mp.luma ? 0 : 1];
+    const uint32_t *tAc = (KE_AC_GLOBAL ? huff->ac : sH.ac)[mp.luma ? 0 : 1], *tDc = sH.dc[mp.luma ? 0 : 1], *tLut = sH.lut[mp.luma ? 0 : 1];
     if (mp.valid) {
         if (mp.part == 0) {
             int pred;

@@ -351,6 +351,8 @@ static void build_huff_pack(const HuffDev *h, HuffPack *k)
                 const uint32_t w = k->ac[t][(run << 4) | c];
                 k->lut[t][run * 8 + v + 4] = w ? (w | (extra << 5)) : 0u;
             }
+        k->lut[t][HP_LUT_EOB] = k->ac[t][0x00]; /* value 0 never indexes the lut: two of its spare entries */
+        k->lut[t][HP_LUT_ZRL] = k->ac[t][0xF0];
     }
 }
 
