@@ -124,6 +124,11 @@ SYN_CASES = [
     (1024, 1032, 97, 1, 1, 17),  # highest quality, noise: longest codes, many 0xFF bytes
     (640, 480, 75, 0, 0, 18),
     (640, 480, 75, 1, 0, 19),
+    (1024, 64, 75, 0, 1, 20),    # noise: strings longer than the private regions continue over their own rows (SpillSink)
+    (1024, 64, 90, 0, 1, 21),    # ... and the Cr blocks, whose rows the staged stream replaces, are coded a second time
+    (1024, 64, 97, 0, 1, 22),    # chunk streams of more than 8 KB: every block coded again, straight into the slot
+    (1024, 64, 85, 1, 1, 23),
+    (1024, 64, 90, 2, 1, 24),
 ]
 
 
