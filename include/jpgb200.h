@@ -76,6 +76,17 @@ int jpgb200_has_ab_forms(void);
  * byte-identical and slower, kept as a cross-check; K35 takes 4:4:4 and 4:2:2 only and disables the
  * batch overlap and the fused transform below. */
 int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on);
+/* KE's form.  The chunk encoder (what src/huffman.c:182-235 does per block, with the bit writer the reference
+ * lacks) keeps every block's code string in a small private region of shared memory and lives on occupancy:
+ *   1 = tight: 5-word regions at 4:4:4 (8 at 4:2:2): seven (five) CTAs per SM; a block with a longer string is
+ *       coded a second time -- right for ordinary images, slow when most blocks are that busy
+ *   2 = roomy: 10-word regions, six (four) CTAs per SM
+ *   0 = automatic (default): either form counts the blocks whose string outgrows the tight region, the host reads
+ *       that counter every fourth launch without ever waiting for it, and switches to the roomy form above 5 % of
+ *       the blocks and back below 2 %.
+ * Identical bytes in every mode.  jpgb200_entropy_form returns the form the next launch would use (1 or 2). */
+int jpgb200_set_entropy_form(jpgb200_ctx *ctx, int mode);
+int jpgb200_entropy_form(jpgb200_ctx *ctx);
 /* Transform/entropy fusion: 1 = K1E, one persistent kernel from pixels to chunk streams
  * (csrc/k1_fused.cuh; the chain dct -> quantise -> zig_zag -> dpcm -> huffman_encode of
  * src/jpg_encode.c:36-50 without the coefficients ever reaching HBM: 3.3 B/pixel of DRAM traffic

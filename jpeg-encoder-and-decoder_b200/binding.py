@@ -32,6 +32,8 @@ _SIGS = {
     "jpgb200_sync": (C.c_int, [_vp]),
     "jpgb200_set_oob_bytes": (C.c_int, [_vp, _vp]),
     "jpgb200_set_staged_entropy": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_set_entropy_form": (C.c_int, [_vp, C.c_int]),
+    "jpgb200_entropy_form": (C.c_int, [_vp]),
     "jpgb200_set_plain_transform": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_optimized_huffman": (C.c_int, [_vp, C.c_int]),
     "jpgb200_set_standard_mode": (C.c_int, [_vp, C.c_int]),
@@ -185,6 +187,13 @@ class Encoder:
     def set_staged_entropy(self, on):
         self._ck(lib().jpgb200_set_staged_entropy(self._h, 1 if on else 0))
 
+    def set_entropy_form(self, mode):
+        """KE's form: 0 automatic (follows the content), 1 tight (7 CTAs per SM at 4:4:4), 2 roomy"""
+        self._ck(lib().jpgb200_set_entropy_form(self._h, int(mode)))
+
+    def entropy_form(self):
+        return int(lib().jpgb200_entropy_form(self._h))
+
     def set_optimized_huffman(self, on):
         self._ck(lib().jpgb200_set_optimized_huffman(self._h, 1 if on else 0))
 
@@ -228,7 +237,7 @@ class Encoder:
         self._ck(lib().jpgb200_set_batch_overlap(self._h, 1 if on else 0))
 
     def set_fused_transform(self, on):
-        """K1E (transform + chunk encode in one kernel, the default) on/off"""
+        """K1E (transform + chunk encode in one kernel; opt-in, measured slower than K1 -> KE) on/off"""
         self._ck(lib().jpgb200_set_fused_transform(self._h, 1 if on else 0))
 
     def set_pipelined_batch(self, on):

@@ -702,12 +702,13 @@ struct KeParams {
     long long zz_fstride, tmp_fstride; /* int16 elements, words */
     int cta_fstride, super_fstride;    /* elements */
     const int *dc_pred_dev;            /* optional: the predictors in device memory (multi-GPU bands) */
+    unsigned int *recode_count;        /* optional: += the number of blocks the tight form codes twice (the host picks KE's form from it) */
 };
 
 /* KE's threads: "entries" in component-major order -- two per luma block (part 0, part 1), one per
  * chroma block -- so that warps are component-pure; e_local is the entry's position in stream
  * order inside the chunk (4:4:4: Y.0 Y.1 Cb Cr per MCU; 4:2:2: Y0.0 Y0.1 Y1.0 Y1.1 Cb Cr). */
-template <int RATIO>
+template <int RATIO, bool ROOMY = false>
 struct KeCfg {
     static const int NY = (RATIO == 0) ? 64 : (RATIO == 1 ? 128 : 256); /* luma blocks per chunk */
     static const int ROWS = NY + 128;                    /* coefficient rows (blocks) per chunk */
@@ -729,11 +730,13 @@ struct KeCfg {
     /* words of private stream per entry.  KE lives on occupancy (shared memory per CTA): 4:4:4 with 5 words and the
      * (run, category) table left in global memory is 31.9 KB -> SEVEN CTAs per SM (72.6 us per 8K frame against
      * 77.0 us with 10 words and all tables in shared memory: six CTAs); 4:2:2 with 8 words is 45.2 KB -> five CTAs.
-     * A block that outgrows its region is coded a second time, alone (see below). */
+     * A block that outgrows its region is coded a second time, alone (see below).
+     * ROOMY: 10 words for every sampling (4:4:4: six CTAs per SM) -- the form for busy content, where most luma blocks
+     * would outgrow 5 words and be coded twice; the host switches between the two forms from the re-code count. */
 #ifdef KE_PRIV
     static const int PRIV = KE_PRIV;
 #else
-    static const int PRIV = (RATIO == 0) ? 5 : (RATIO == 1 ? 8 : 10);
+    static const int PRIV = ROOMY ? 10 : ((RATIO == 0) ? 5 : (RATIO == 1 ? 8 : 10));
 #endif
     static const int PSTRIDE = PRIV + 1;                 /* odd: lanes hit distinct banks */
     static const int ROW_BYTES = ROWS * KE_ROW_CHUNKS * 16;
@@ -749,8 +752,8 @@ struct KeCfg {
 #endif
     static const int BYTES = OFF_FLAG + 16 + KE_PAD_BYTES;
 };
-template <int RATIO>
-using KeSmem = KeCfg<RATIO>;
+template <int RATIO, bool ROOMY = false>
+using KeSmem = KeCfg<RATIO, ROOMY>;
 
 template <int RATIO>
 struct KeMap {
@@ -830,8 +833,8 @@ struct KeMap {
     }
 };
 
-template <int RATIO>
-__global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KeParams q0, const HuffPack *huff)
+template <int RATIO, bool ROOMY = false>
+__global__ void __launch_bounds__(KeCfg<RATIO, ROOMY>::NT) k_encode_chunks(const KeParams q0, const HuffPack *huff)
 {
     /* frame of a multi-frame launch (blockIdx.y): every array advances by its stride.  The parameters are read where
      * they are used (constant bank) -- a copy of the struct would cost every warp its set-up. */
@@ -842,8 +845,8 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
     uint32_t *const cta_bits_f = q0.cta_bits + fr * q0.cta_fstride;
     uint32_t *const cta_tail_f = q0.cta_tail + fr * q0.cta_fstride;
     uint32_t *const super_bits_f = q0.super_bits + fr * q0.super_fstride;
-    constexpr int BPM = EcCfg<RATIO>::BPM, NT = KeCfg<RATIO>::NT;
-    typedef KeCfg<RATIO> L;
+    constexpr int BPM = EcCfg<RATIO>::BPM, NT = KeCfg<RATIO, ROOMY>::NT;
+    typedef KeCfg<RATIO, ROOMY> L;
     extern __shared__ __align__(16) unsigned char ke_smem[];
     uint4(*sC)[KE_ROW_CHUNKS] = reinterpret_cast<uint4(*)[KE_ROW_CHUNKS]>(ke_smem);
     uint32_t *sP = reinterpret_cast<uint32_t *>(ke_smem + L::OFF_PRIV);
@@ -941,6 +944,14 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
         const bool again = active && nbits > (uint32_t)L::PRIV * 32u;
         const bool row_alive = ((uint32_t)mp.row + 1u) * 32u <= stage0;
         for (uint32_t i = tid; i < ngroups; i += NT) sS4[i] = make_uint4(0u, 0u, 0u, 0u);
+        /* the count the host picks KE's form from: blocks whose string outgrows the TIGHT form's region, in either form */
+        /* The count the host picks KE's form from: blocks whose string outgrows the TIGHT form's region.  The tight
+         * form counts them where it codes them again (below: nothing on the common path -- a ballot here was measured
+         * at 1.9 us per 8K frame); the roomy form, whose own overflows are fewer, counts them here. */
+        if (ROOMY && KeCfg<RATIO, false>::PRIV != L::PRIV) {
+            const unsigned busy = __ballot_sync(0xffffffffu, active && nbits > (uint32_t)KeCfg<RATIO, false>::PRIV * 32u);
+            if (busy && (tid & 31) == 0 && q.recode_count) atomicAdd(q.recode_count, (unsigned)__popc(busy));
+        }
         __syncthreads();
         if (active && !again) {
             const uint32_t sh = loff & 31u, nw = (nbits + 31u) >> 5;
@@ -953,6 +964,10 @@ __global__ void __launch_bounds__(KeCfg<RATIO>::NT) k_encode_chunks(const KePara
             }
             if (sh) asm volatile("red.shared.or.b32 [%0], %1;" ::"r"(a0), "r"(prevw << (32u - sh)) : "memory");
         } else if (again) {
+            if (!(ROOMY && KeCfg<RATIO, false>::PRIV != L::PRIV) && q.recode_count) {
+                const unsigned am = __activemask();
+                if ((tid & 31) == __ffs((int)am) - 1) atomicAdd(q.recode_count, (unsigned)__popc(am));
+            }
             StageSink s;
             s.acc = 0;
             s.nacc = (int)(loff & 31u);

@@ -96,6 +96,18 @@ struct jpgb200_ctx {
     bool k1_ws;    /* the warp-autonomous K1 (k1_warp.cuh) */
     bool k1c_attr_set;
     bool k1_tmaload, k1t_attr_set; /* K1 fed by 2-D TMA tile loads (k1_transform_pct, JPGB200_K1=pct) */
+    /* KE's form follows the content: the tight form (7 CTAs per SM at 4:4:4) codes blocks that outgrow their private
+     * region a second time; when a sample of the device-side re-code counter says that happens to more than 5 % of
+     * the blocks, the roomy form (10-word regions) takes over until the rate -- counted the same way by both forms -- falls
+     * below 2 % (jpgb200_set_entropy_form) */
+    bool ke_roomy;
+    int ke_form_mode;             /* 0 = automatic, 1 = always tight, 2 = always roomy */
+    unsigned int *d_recode, *h_recode;
+    cudaEvent_t ev_recode;
+    bool recode_pending;
+    unsigned int recode_last;
+    unsigned long long ke_blocks, ke_blocks_sampled, ke_blocks_last;
+    int ke_since_sample;
     bool k1_four, k1c4_attr_set;   /* 4:4:4: four transform warps per CTA taking component units in turn (k1_transform_pc4) */
     K1TLoad k1t_maps;
     bool no_tma_store; /* k1_pipe: copy the coefficients out with ordinary stores (A/B runs) */
@@ -493,6 +505,9 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         if (k && !strcmp(k, "plain")) ctx->k1_plain = true, ctx->k1_pc = false;
         if (k && !strcmp(k, "pc_notma")) ctx->no_tma_store = true;
         if (k && !strcmp(k, "pct")) ctx->k1_tmaload = true;
+        const char *kf = getenv("JPGB200_KE_FORM"); /* "tight" | "roomy": pin KE's form (default: follows the content) */
+        ctx->ke_form_mode = kf ? (!strcmp(kf, "tight") ? 1 : (!strcmp(kf, "roomy") ? 2 : 0)) : 0;
+        ctx->ke_roomy = ctx->ke_form_mode == 2;
         if (k && !strcmp(k, "pc4")) ctx->k1_four = true;
         if (k && !strcmp(k, "pc3")) ctx->k1_four = false;
         if (jpgb200_has_ab_forms()) {
@@ -559,6 +574,11 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         CK(cudaMalloc(&ctx->d_len, 2 * sizeof(unsigned long long)));
         CK(cudaHostAlloc(&ctx->h_len, 2 * sizeof(unsigned long long), cudaHostAllocMapped));
         CK(cudaMalloc(&ctx->d_freq, 4 * 257 * sizeof(int)));
+        CK(cudaMalloc(&ctx->d_recode, sizeof(unsigned int)));
+        CK(cudaMemset(ctx->d_recode, 0, sizeof(unsigned int)));
+        CK(cudaHostAlloc(&ctx->h_recode, sizeof(unsigned int), cudaHostAllocDefault));
+        *ctx->h_recode = 0u;
+        CK(cudaEventCreateWithFlags(&ctx->ev_recode, cudaEventDisableTiming));
         return JPGB200_OK;
     }();
     if (rc != JPGB200_OK) {
@@ -582,6 +602,9 @@ extern "C" void jpgb200_destroy(jpgb200_ctx *ctx)
     for (void *p : ptrs)
         if (p) cudaFree(p);
     if (ctx->h_len) cudaFreeHost(ctx->h_len);
+    if (ctx->d_recode) cudaFree(ctx->d_recode);
+    if (ctx->h_recode) cudaFreeHost(ctx->h_recode);
+    if (ctx->ev_recode) cudaEventDestroy(ctx->ev_recode);
     for (auto &e : ctx->pending) {
         cudaEventDestroy(e.a);
         cudaEventDestroy(e.b);
@@ -652,6 +675,19 @@ extern "C" int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on)
     ctx->k1_pipe = (on == 3);
     ctx->k1_ws = (on == 4);
     return JPGB200_OK;
+}
+
+extern "C" int jpgb200_set_entropy_form(jpgb200_ctx *ctx, int mode)
+{
+    if (!ctx || mode < 0 || mode > 2) return JPGB200_ERR_BAD_ARG;
+    ctx->ke_form_mode = mode;
+    if (mode) ctx->ke_roomy = (mode == 2);
+    return JPGB200_OK;
+}
+
+extern "C" int jpgb200_entropy_form(jpgb200_ctx *ctx)
+{
+    return ctx ? (ctx->ke_roomy ? 2 : 1) : JPGB200_ERR_BAD_ARG;
 }
 
 extern "C" int jpgb200_set_staged_entropy(jpgb200_ctx *ctx, int on)
@@ -1360,6 +1396,60 @@ static int launch_k1e(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, 
     return JPGB200_OK;
 }
 
+/* KE in the form the content asks for.  Every fourth launch a copy of the device-side re-code counter is queued
+ * behind the kernel; its arrival is polled (never waited for) before a later launch and moves ctx->ke_roomy. */
+static int launch_ke(jpgb200_ctx *ctx, const KeParams &e0, int ratio, dim3 grid, cudaStream_t st, unsigned long long blocks)
+{
+    if (!ctx->ke_attr_set) {
+        CK(cudaFuncSetAttribute((k_encode_chunks<0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<0, false>::BYTES));
+        CK(cudaFuncSetAttribute((k_encode_chunks<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<1, false>::BYTES));
+        CK(cudaFuncSetAttribute((k_encode_chunks<2, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<2, false>::BYTES));
+        CK(cudaFuncSetAttribute((k_encode_chunks<0, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<0, true>::BYTES));
+        CK(cudaFuncSetAttribute((k_encode_chunks<1, true>), cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<1, true>::BYTES));
+        ctx->ke_attr_set = true;
+    }
+    if (ctx->recode_pending && cudaEventQuery(ctx->ev_recode) == cudaSuccess) {
+        const unsigned int now = *ctx->h_recode;
+        const unsigned long long nb = ctx->ke_blocks_sampled - ctx->ke_blocks_last;
+        const double rate = nb ? (double)(unsigned int)(now - ctx->recode_last) / (double)nb : 0.0;
+        ctx->recode_last = now;
+        ctx->ke_blocks_last = ctx->ke_blocks_sampled;
+        ctx->recode_pending = false;
+        if (ctx->ke_form_mode == 0) {
+            if (!ctx->ke_roomy && rate > 0.05) ctx->ke_roomy = true;
+            else if (ctx->ke_roomy && rate < 0.02) ctx->ke_roomy = false;
+        }
+    }
+    KeParams e = e0;
+    e.recode_count = ctx->d_recode;
+    const bool roomy = ctx->ke_roomy && ratio != 2; /* 4:2:0 has one form */
+    {
+        LaunchScope ls(ctx, KI_KE);
+        if (ratio == 0) {
+            if (roomy)
+                k_encode_chunks<0, true><<<grid, KeCfg<0, true>::NT, KeSmem<0, true>::BYTES, st>>>(e, ctx->d_hpack);
+            else
+                k_encode_chunks<0, false><<<grid, KeCfg<0, false>::NT, KeSmem<0, false>::BYTES, st>>>(e, ctx->d_hpack);
+        } else if (ratio == 1) {
+            if (roomy)
+                k_encode_chunks<1, true><<<grid, KeCfg<1, true>::NT, KeSmem<1, true>::BYTES, st>>>(e, ctx->d_hpack);
+            else
+                k_encode_chunks<1, false><<<grid, KeCfg<1, false>::NT, KeSmem<1, false>::BYTES, st>>>(e, ctx->d_hpack);
+        } else
+            k_encode_chunks<2, false><<<grid, KeCfg<2, false>::NT, KeSmem<2, false>::BYTES, st>>>(e, ctx->d_hpack);
+    }
+    CK(cudaGetLastError());
+    ctx->ke_blocks += blocks;
+    if (ctx->ke_form_mode == 0 && !ctx->recode_pending && ++ctx->ke_since_sample >= 4) {
+        ctx->ke_since_sample = 0;
+        CK(cudaMemcpyAsync(ctx->h_recode, ctx->d_recode, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+        CK(cudaEventRecord(ctx->ev_recode, st));
+        ctx->ke_blocks_sampled = ctx->ke_blocks;
+        ctx->recode_pending = true;
+    }
+    return JPGB200_OK;
+}
+
 /* KE: every chunk's bit lengths and its packed, chunk-local stream; two-level sums of the lengths */
 static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const long long n[3], const int *pred = NULL,
                        bool clear_supers = false)
@@ -1383,20 +1473,9 @@ static int launch_bits(jpgb200_ctx *ctx, const int16_t *zz, int ratio, const lon
     const unsigned nc = (unsigned)n_chunks(n);
     ctx->geo_chunks = n_chunks(n);
     ctx->geo_slot_words = slot_words(n);
-    if (!ctx->ke_attr_set) {
-        CK(cudaFuncSetAttribute(k_encode_chunks<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<0>::BYTES));
-        CK(cudaFuncSetAttribute(k_encode_chunks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<1>::BYTES));
-        CK(cudaFuncSetAttribute(k_encode_chunks<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<2>::BYTES));
-        ctx->ke_attr_set = true;
-    }
     {
-        LaunchScope ls(ctx, KI_KE);
-        if (ratio == 0)
-            k_encode_chunks<0><<<nc, KeCfg<0>::NT, KeSmem<0>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
-        else if (ratio == 1)
-            k_encode_chunks<1><<<nc, KeCfg<1>::NT, KeSmem<1>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
-        else
-            k_encode_chunks<2><<<nc, KeCfg<2>::NT, KeSmem<2>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
+        const int rc = launch_ke(ctx, e, ratio, dim3(nc), ctx->stream, (unsigned long long)(n[0] + n[1] + n[2]));
+        if (rc) return rc;
     }
     CK(cudaGetLastError());
     ctx->have_bits = true;
@@ -1668,21 +1747,9 @@ static int encode_group(jpgb200_ctx *ctx, const uint8_t *d_planes, int G, int w,
     e.cta_fstride = (int)nc;
     e.super_fstride = S;
     e.dc_pred_dev = NULL;
-    if (!ctx->ke_attr_set) {
-        CK(cudaFuncSetAttribute(k_encode_chunks<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<0>::BYTES));
-        CK(cudaFuncSetAttribute(k_encode_chunks<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<1>::BYTES));
-        CK(cudaFuncSetAttribute(k_encode_chunks<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, KeSmem<2>::BYTES));
-        ctx->ke_attr_set = true;
-    }
     {
-        const dim3 grid((unsigned)nc, (unsigned)G);
-        LaunchScope ls(ctx, KI_KE);
-        if (ratio == 0)
-            k_encode_chunks<0><<<grid, KeCfg<0>::NT, KeSmem<0>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
-        else if (ratio == 1)
-            k_encode_chunks<1><<<grid, KeCfg<1>::NT, KeSmem<1>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
-        else
-            k_encode_chunks<2><<<grid, KeCfg<2>::NT, KeSmem<2>::BYTES, ctx->stream>>>(e, ctx->d_hpack);
+        const int rc = launch_ke(ctx, e, ratio, dim3((unsigned)nc, (unsigned)G), ctx->stream, (unsigned long long)nb * (unsigned long long)G);
+        if (rc) return rc;
     }
     CK(cudaGetLastError());
     TailParams q;
@@ -2385,11 +2452,12 @@ extern "C" int jpgb200_mgpu_encode(jpgb200_mgpu *mg, const uint8_t *d_r, const u
         e.zz_fstride = e.tmp_fstride = 0;
         e.cta_fstride = e.super_fstride = 0;
         e.dc_pred_dev = mg->state->pred;
+        e.recode_count = NULL;
         LaunchScope ls(ctx, KI_KE);
         if (ratio == 0)
-            k_encode_chunks<0><<<1, KeCfg<0>::NT, KeSmem<0>::BYTES, st>>>(e, ctx->d_hpack);
+            k_encode_chunks<0, false><<<1, KeCfg<0>::NT, KeSmem<0>::BYTES, st>>>(e, ctx->d_hpack);
         else
-            k_encode_chunks<1><<<1, KeCfg<1>::NT, KeSmem<1>::BYTES, st>>>(e, ctx->d_hpack);
+            k_encode_chunks<1, false><<<1, KeCfg<1>::NT, KeSmem<1>::BYTES, st>>>(e, ctx->d_hpack);
     }
     ctx->in_batch = was_batch;
     CK(cudaGetLastError());

@@ -715,3 +715,34 @@ def test_pipelined_batch_is_invisible(enc, w, h, ratio, nf):
         enc.free(d_pl)
         enc.free(d_out)
         enc.free(d_len)
+
+
+def test_entropy_form_follows_content(enc):
+    """KE has a tight form (5-word private regions at 4:4:4: seven CTAs per SM, busy blocks coded twice) and a roomy
+    one (10 words); in automatic mode the host follows the kernel's re-code counter.  Same bytes in every mode,
+    equal to the oracle's; iid noise moves the context to the roomy form, ordinary content moves it back."""
+    w, h, q = 1024, 128, 75
+    want = {}
+    for kind in (0, 1):
+        r, g, b = O.synth_planes(w, h, 77, 0, kind)
+        got = []
+        for mode in (1, 2):
+            enc.set_entropy_form(mode)
+            assert enc.entropy_form() == mode
+            got.append(enc.encode_planar(r, g, b, w, h, q, 0))
+        assert got[0].shape == got[1].shape and (got[0] == got[1]).all()
+        zz = enc.coefficients(r, g, b, w, h, q, 0)
+        scan, _ = O.encode_scan(zz, w, h, 0)
+        ref = np.concatenate([O.jfif_header(w, h, q, 0), scan, np.array([0xFF, 0xD9], np.uint8)])
+        assert got[0].shape == ref.shape and (got[0] == ref).all()
+        want[kind] = (r, g, b, got[0])
+    enc.set_entropy_form(1)
+    enc.set_entropy_form(0)  # automatic, starting from the tight form
+    assert enc.entropy_form() == 1
+    for kind, form in ((1, 2), (0, 1), (1, 2)):
+        r, g, b, ref = want[kind]
+        for _ in range(12):  # the counter is sampled every fourth launch and read at a later one
+            jf = enc.encode_planar(r, g, b, w, h, q, 0)
+            assert jf.shape == ref.shape and (jf == ref).all()
+        assert enc.entropy_form() == form
+    enc.set_entropy_form(0)
