@@ -135,6 +135,8 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pc(con
 
     if (w < 4) {
         /* ================= convert warp k ================= */
+        /* (setmaxnreg.dec on this warpgroup -- 72 / 56 / 40 registers, to make room for a CTA of the neighbouring frames'
+         * entropy kernels beside K1 -- was measured: K1 80.8 / 88.8 / 91.1 us against 78.3 us, the batch slower each time) */
         const int k = w;
         uint8_t(*ring)[3][2][K1_ROW_BYTES] = S.raw[k];
 #pragma unroll

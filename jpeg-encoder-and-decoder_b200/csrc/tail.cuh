@@ -29,7 +29,9 @@
 
 namespace jpgb200 {
 
+#ifndef TAIL_THREADS
 #define TAIL_THREADS 256
+#endif
 #define TAIL_WARPS (TAIL_THREADS / 32)
 
 /* what the band's own kernels read instead of host-side launch parameters */
