@@ -539,10 +539,17 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         CK(cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_in, cudaStreamNonBlocking));
         CK(cudaStreamCreateWithFlags(&ctx->copy_out, cudaStreamNonBlocking));
-        CK(cudaStreamCreateWithFlags(&ctx->tail_stream, cudaStreamNonBlocking));
         {
             int lo = 0, hi = 0;
             CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+            {
+                /* the tails go first too: K1 of frame f+2 waits for the tails of frame f (it clears the two-level sums
+                 * they read).  Measured: 156.2 us per 8K frame against 158.2 us with the tails at the lowest priority;
+                 * a THIRD set of entropy workspaces, which takes the tails off K1's dependencies altogether, was
+                 * slower again (157.7 us): K1 then starts before the chunk encode it displaces has drained. */
+                const char *tp = getenv("JPGB200_TAIL_PRIO"); /* "lo": A/B runs */
+                CK(cudaStreamCreateWithPriority(&ctx->tail_stream, cudaStreamNonBlocking, (tp && !strcmp(tp, "lo")) ? lo : hi));
+            }
             CK(cudaStreamCreateWithPriority(&ctx->k1_stream, cudaStreamNonBlocking, hi)); /* K1's few persistent CTAs go first */
             CK(cudaStreamCreateWithPriority(&ctx->ke_stream, cudaStreamNonBlocking, lo));
             for (int sl = 0; sl < 2; sl++) {
