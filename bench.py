@@ -11,9 +11,13 @@ scatter -> complete JFIF streams) over one batch of synthetic frames.
           pinned host frames in, JFIF bytes out, H2D and D2H inside the timed region; beside it
           the PCIe ceiling of this host at this N: the same copies with no kernel (jpgb200_copy_probe)
   roofline : the dominant kernel (the longest when each runs alone) against the measured HBM copy
-          bandwidth in MEASURED_PEAKS.json, from CUDA events on the kernel's own stream inside the
-          timed region; all_timed_kernels holds K1 (north_star's target kernel: 9 B/pixel) and KE
-          (6 B/pixel + stream); pipeline = (3 B/pixel + stream) / frame time against the same peak
+          bandwidth in MEASURED_PEAKS.json.  The timed region is a three-stream pipeline in which K1 and KE
+          of neighbouring frames queue for the same SMs, so an event pair on a kernel's stream brackets a
+          span that includes that queueing (span_in_timed_region_us); the kernel's DURATION (avg_launch_us,
+          frac) comes from CUDA events around every launch of one extra step of the same run with the
+          frames' kernels one after the other.  all_timed_kernels holds K1 (north_star's target kernel:
+          9 B/pixel) and KE (6 B/pixel + stream); pipeline = (3 B/pixel + stream) / frame time against the
+          same peak
   config.strong_scaling / small_frame / worst_case_distribution / config5 : BASELINE.json configs[3] as
           written (256 frames in total), configs[1] (1080p batch), iid-noise frames, configs[4] (one
           32768x32768 image partitioned over the ranks, N > 1 only)
@@ -341,21 +345,33 @@ def run_b200(args):
             traffic_file = {}
 
     def roof(kname, label, alg_bytes, what):
+        """One kernel against the roofline.  Its DURATION is measured in this run with CUDA events around every launch
+        of one extra step in which the frames' kernels run one after the other (the same kernels, the same inputs, right
+        after the timed region).  Inside the timed region itself the batch is pipelined over three streams: an event
+        pair on a kernel's stream then brackets a SPAN that includes the time its CTAs queue for SM resources behind
+        the other frames' kernels (K1 and KE take turns on the SMs) -- reported beside it, not used for `frac`."""
         ms, n = ktimes.get(kname, (0.0, 0))
         if n == 0:
             return None
-        avg = ms * 1e-3 / n
+        span = ms * 1e-3 / n
         iso_ms = kbreak.get(kname, (0.0, 0))
         iso = iso_ms[0] * 1e-3 / max(iso_ms[1], 1) if iso_ms[1] else None
+        dur = iso if iso else span
         tr = traffic_file.get(kname, {})
-        return {"bound": "hbm", "kernel": label, "achieved": alg_bytes / avg / 1e9, "peak": peak, "unit": "GB/s",
-                "frac": alg_bytes / avg / 1e9 / peak, "frac_of_nominal_8000": alg_bytes / avg / 1e9 / 8000.0,
+        return {"bound": "hbm", "kernel": label, "achieved": alg_bytes / dur / 1e9, "peak": peak, "unit": "GB/s",
+                "frac": alg_bytes / dur / 1e9 / peak, "frac_of_nominal_8000": alg_bytes / dur / 1e9 / 8000.0,
                 "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"), "peak_source": peak_src,
-                "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes": what, "avg_launch_us": avg * 1e6,
-                "launches_timed": n, "event_sampling": "every 8th launch of the timed region, CUDA events on the kernel's own stream; in the "
-                "pipelined batch the span of a launch includes the time its CTAs wait for room beside the other frames' kernels",
-                "share_of_step": avg * 1e3 * F / ms_per_step,
-                # the same kernel with nothing beside it: one extra, untimed step without pipelining, events around every launch
+                "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes": what, "avg_launch_us": dur * 1e6,
+                "launches_timed": iso_ms[1] if iso else n,
+                "duration_source": ("CUDA events around every launch of one extra step of this run with the frames' kernels one after "
+                                    "the other (no other kernel on the GPU), right after the timed region") if iso else
+                                   "CUDA events around every 8th launch of the timed region",
+                "share_of_step": dur * 1e3 * F / ms_per_step,
+                # the event-to-event span of a launch inside the (pipelined) timed region
+                "span_in_timed_region_us": span * 1e6, "span_launches_timed": n,
+                "frac_of_span": alg_bytes / span / 1e9 / peak,
+                "span_what": "every 8th launch of the timed region, CUDA events on the kernel's own stream; in the pipelined batch "
+                             "the span of a launch includes the time its CTAs wait for room behind the other frames' kernels",
                 "avg_launch_us_isolated": iso * 1e6 if iso else None,
                 "frac_isolated": (alg_bytes / iso / 1e9 / peak) if iso else None}
 

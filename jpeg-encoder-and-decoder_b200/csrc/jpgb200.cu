@@ -542,16 +542,16 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         {
             int lo = 0, hi = 0;
             CK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
-            {
-                /* the tails go first too: K1 of frame f+2 waits for the tails of frame f (it clears the two-level sums
-                 * they read).  Measured: 156.2 us per 8K frame against 158.2 us with the tails at the lowest priority;
-                 * a THIRD set of entropy workspaces, which takes the tails off K1's dependencies altogether, was
-                 * slower again (157.7 us): K1 then starts before the chunk encode it displaces has drained. */
-                const char *tp = getenv("JPGB200_TAIL_PRIO"); /* "lo": A/B runs */
-                CK(cudaStreamCreateWithPriority(&ctx->tail_stream, cudaStreamNonBlocking, (tp && !strcmp(tp, "lo")) ? lo : hi));
-            }
-            CK(cudaStreamCreateWithPriority(&ctx->k1_stream, cudaStreamNonBlocking, hi)); /* K1's few persistent CTAs go first */
-            CK(cudaStreamCreateWithPriority(&ctx->ke_stream, cudaStreamNonBlocking, lo));
+            /* Stream priorities of the pipelined batch, measured on 8K frames (profiles/README.md): K1 and KE EQUAL and
+             * the tails above them: 152.2 us per frame = K1 + KE + 2.5 us.  K1 above KE (the first design: "K1's few
+             * persistent CTAs go first") lets K1 of frame f+1 move in before the chunk encode of frame f has drained:
+             * 156.2 us; with the tails at the lowest priority as well 158.2 us (K1 of frame f+2 waits for the tails of
+             * frame f: it clears the two-level sums they read); KE above the tails: 160 us.  A third set of entropy
+             * workspaces, which takes the tails off K1's dependencies, was slower too (157.7 us). */
+            const char *p1 = getenv("JPGB200_K1_PRIO"), *p2 = getenv("JPGB200_KE_PRIO"), *tp = getenv("JPGB200_TAIL_PRIO"); /* A/B runs */
+            CK(cudaStreamCreateWithPriority(&ctx->tail_stream, cudaStreamNonBlocking, (tp && !strcmp(tp, "lo")) ? lo : hi));
+            CK(cudaStreamCreateWithPriority(&ctx->k1_stream, cudaStreamNonBlocking, (p1 && !strcmp(p1, "hi")) ? hi : lo));
+            CK(cudaStreamCreateWithPriority(&ctx->ke_stream, cudaStreamNonBlocking, (p2 && !strcmp(p2, "hi")) ? hi : lo));
             for (int sl = 0; sl < 2; sl++) {
                 CK(cudaEventCreateWithFlags(&ctx->ev_k1[sl], cudaEventDisableTiming));
                 CK(cudaEventCreateWithFlags(&ctx->ev_ked[sl], cudaEventDisableTiming));
