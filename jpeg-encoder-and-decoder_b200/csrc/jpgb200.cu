@@ -1713,13 +1713,19 @@ static int encode_core(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g,
 /* A group of G small frames in four launches (K1, KE, KF, KS over all of them: blockIdx.y = frame for the
  * entropy kernels, K1's tile index runs over the frames): what a 1080p frame needs is a sixteenth of an 8K
  * frame's work, and four launches per frame leave the GPU waiting for the next launch most of the time. */
+/* pipe != NULL: the group's three stages go to the pipelined batch's three streams (K1 | KE | KF, KS), handed over
+ * through the parity's events, and its coefficients to half `par` of a buffer of 2 * zz_group frames */
+struct GroupPipe {
+    int par, zz_group;
+};
+
 static int encode_group(jpgb200_ctx *ctx, const uint8_t *d_planes, int G, int w, int h, int quality, int ratio, uint8_t *d_out,
-                        size_t out_stride, unsigned long long *d_lens)
+                        size_t out_stride, unsigned long long *d_lens, const GroupPipe *pipe = NULL)
 {
     long long n[3];
     int rc = validate(w, h, quality, ratio, n);
     if (rc) return rc;
-    if ((rc = ensure_workspace(ctx, n, G))) return rc;
+    if ((rc = ensure_workspace(ctx, n, pipe ? 2 * pipe->zz_group : G))) return rc;
     if ((rc = ensure_tables(ctx, w, h, quality, ratio))) return rc;
     ctx->w = w;
     ctx->h = h;
@@ -1732,13 +1738,20 @@ static int encode_group(jpgb200_ctx *ctx, const uint8_t *d_planes, int G, int w,
     /* K1 over all frames; it also clears every frame's two-level sums */
     const size_t keep_b = ctx->n_super_bits, keep_f = ctx->n_super_ff;
     ctx->n_super_ff = (size_t)S * (size_t)G - keep_b; /* launch_k1 clears n_super_bits + n_super_ff words */
-    rc = launch_k1(ctx, d_planes, d_planes + npx, d_planes + 2 * npx, w, h, ratio, n, G, (long long)(3 * npx), ctx->d_zz, nb * 64, 0);
+    int16_t *zz = ctx->d_zz + (pipe ? (size_t)pipe->par * (size_t)pipe->zz_group * (size_t)nb * 64 : 0);
+    if (pipe) ctx->stream = ctx->k1_stream;
+    rc = launch_k1(ctx, d_planes, d_planes + npx, d_planes + 2 * npx, w, h, ratio, n, G, (long long)(3 * npx), zz, nb * 64, 0);
     ctx->n_super_ff = keep_f;
     if (rc) return rc;
+    if (pipe) {
+        CK(cudaEventRecord(ctx->ev_k1[pipe->par], ctx->k1_stream));
+        CK(cudaStreamWaitEvent(ctx->ke_stream, ctx->ev_k1[pipe->par], 0));
+        ctx->stream = ctx->ke_stream;
+    }
     ctx->geo_chunks = nc;
     ctx->geo_slot_words = sw;
     KeParams e;
-    e.zz = ctx->d_zz;
+    e.zz = zz;
     e.coff1 = n[0];
     e.coff2 = n[0] + n[1];
     e.n_mcu = n[1];
@@ -1759,6 +1772,11 @@ static int encode_group(jpgb200_ctx *ctx, const uint8_t *d_planes, int G, int w,
         if (rc) return rc;
     }
     CK(cudaGetLastError());
+    if (pipe) {
+        CK(cudaEventRecord(ctx->ev_ked[pipe->par], ctx->ke_stream));
+        CK(cudaStreamWaitEvent(ctx->tail_stream, ctx->ev_ked[pipe->par], 0));
+        ctx->stream = ctx->tail_stream;
+    }
     TailParams q;
     q.tmp = ctx->d_tmp;
     q.slot_words = sw;
@@ -1797,8 +1815,51 @@ static int encode_group(jpgb200_ctx *ctx, const uint8_t *d_planes, int G, int w,
         k_scatter<<<tgrid, TAIL_THREADS, 0, ctx->stream>>>(q);
     }
     CK(cudaGetLastError());
+    if (pipe) CK(cudaEventRecord(ctx->ev_ks[pipe->par], ctx->tail_stream));
     ctx->have_bits = false;
     return JPGB200_OK;
+}
+
+/* Batch of small frames, pipelined like the large ones below: K1 of group g+1, KE of group g and the tails of group g-1
+ * on three streams, two coefficient buffers (of one group each) and two sets of entropy workspaces by group parity. */
+static int encode_groups_pipelined(jpgb200_ctx *ctx, const uint8_t *d_planes, int n_frames, int G, int w, int h, int quality, int ratio,
+                                   uint8_t *d_out, size_t out_stride, unsigned long long *d_lens)
+{
+    long long n[3];
+    int rc = validate(w, h, quality, ratio, n);
+    if (rc) return rc;
+    const size_t npx = (size_t)w * h;
+    cudaStream_t user = ctx->stream;
+    for (int k = 0; k < 2; k++) { /* both sets of workspaces exist before anything is enqueued (growing one synchronises) */
+        swap_entropy_ws(ctx);
+        if ((rc = ensure_workspace(ctx, n, 2 * G))) return rc;
+    }
+    if ((rc = ensure_tables(ctx, w, h, quality, ratio))) return rc;
+    CK(cudaEventRecord(ctx->ev_start, user));
+    CK(cudaStreamWaitEvent(ctx->k1_stream, ctx->ev_start, 0));
+    CK(cudaStreamWaitEvent(ctx->ke_stream, ctx->ev_start, 0));
+    CK(cudaStreamWaitEvent(ctx->tail_stream, ctx->ev_start, 0));
+    ctx->in_batch = true;
+    int g = 0;
+    for (int f0 = 0; f0 < n_frames && rc == JPGB200_OK; f0 += G, g++) {
+        swap_entropy_ws(ctx);
+        GroupPipe pipe = {ctx->ws_parity, G};
+        if (g >= 2) { /* this parity's coefficients were last read by KE of group g-2, its sums by that group's tails */
+            CK(cudaStreamWaitEvent(ctx->k1_stream, ctx->ev_ked[pipe.par], 0));
+            CK(cudaStreamWaitEvent(ctx->k1_stream, ctx->ev_ks[pipe.par], 0));
+        }
+        const int gg = n_frames - f0 < G ? n_frames - f0 : G;
+        rc = encode_group(ctx, d_planes + (size_t)f0 * 3 * npx, gg, w, h, quality, ratio, d_out + (size_t)f0 * out_stride, out_stride,
+                          d_lens ? d_lens + f0 : NULL, &pipe);
+    }
+    ctx->stream = user;
+    ctx->in_batch = false;
+    ctx->have_bits = false;
+    cudaStreamWaitEvent(user, ctx->ev_ks[0], 0);
+    cudaStreamWaitEvent(user, ctx->ev_ks[1], 0);
+    cudaStreamWaitEvent(user, ctx->ev_ked[0], 0);
+    cudaStreamWaitEvent(user, ctx->ev_ked[1], 0);
+    return rc;
 }
 
 /* Batch, pipelined over three streams: K1 of frame f+1 (persistent CTAs, high priority) is in flight together with
@@ -1904,6 +1965,8 @@ extern "C" int jpgb200_encode_batch_device(jpgb200_ctx *ctx, const uint8_t *d_pl
     {
         /* small frames: groups of frames per launch (identical bytes, a fraction of the launches) */
         const int G = group_frames(ctx, n_frames, w, h);
+        if (G > 1 && ctx->pipelined && ratio != 2 && (w % 16 == 0) && (n_frames + G - 1) / G >= 3)
+            return encode_groups_pipelined(ctx, d_planes, n_frames, G, w, h, quality, ratio, d_out, out_stride, d_lens);
         if (G > 1) {
             int rc = JPGB200_OK;
             for (int f0 = 0; f0 < n_frames && rc == JPGB200_OK; f0 += G) {

@@ -613,12 +613,14 @@ def test_batch_overlap_is_invisible(enc, w, h, ratio, nf):
         enc.free(d_len)
 
 
-@pytest.mark.parametrize("w,h,ratio,nf", [(1920, 1080, 0, 21), (640, 64, 1, 9), (256, 16, 0, 300), (1280, 720, 2, 6), (264, 40, 0, 5)])
+@pytest.mark.parametrize("w,h,ratio,nf", [(1920, 1080, 0, 21), (640, 64, 1, 9), (256, 16, 0, 300), (1280, 720, 2, 6), (264, 40, 0, 5),
+                                          (1920, 1080, 0, 50), (640, 64, 1, 600)])
 def test_frame_groups_equal_per_frame(enc, w, h, ratio, nf):
     """Batches of small frames share kernel launches (jpgb200_set_frame_groups: K1's tile index and the
     entropy kernels' blockIdx.y run over the frames of a group): same streams and lengths as four
     launches per frame, including a group count that does not divide the batch, more frames than one
-    group holds, a ragged last tile and a width the fast K1 declines (264 = 33 blocks)."""
+    group holds, a ragged last tile and a width the fast K1 declines (264 = 33 blocks).  Three groups or more
+    (the last two cases) run as a three-stream pipeline of groups, with a ragged last group."""
     if ratio == 2:
         h = (h + 15) // 16 * 16
     q, npx = 75, w * h
