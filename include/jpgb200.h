@@ -114,7 +114,10 @@ int jpgb200_set_fused_tap(jpgb200_ctx *ctx, int on);
  *   4           autonomous warps, per-warp cp.async ring (csrc/k1_warp.cuh)
  *   6           form 0 fed by 2-D TMA tile loads (cp.async.bulk.tensor.2d, one per plane and tile, issued by the
  *               store warp: k1_transform_pct in csrc/k1_pc.cuh); measured 9 % slower than form 0; needs width >= 256
- * Forms 2..4 exist in A/B builds only (jpgb200_has_ab_forms). */
+ *   5           form 0 named explicitly
+ *   7           form 0 with FOUR transform warps per CTA taking the tile's components in turn and issuing their own
+ *               TMA stores (k1_transform_pc4, 4:4:4 only; measured 3 % slower than form 0)
+ * Forms 2..4 and 7 exist in A/B builds only (jpgb200_has_ab_forms). */
 int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on);
 /* Arithmetic of the transform: 0 (default) = bug-compatible with the reference (its Cb sign slip,
  * src/preprocess.c:161, and the last block column read one pixel row higher, :199-211); 1 =
