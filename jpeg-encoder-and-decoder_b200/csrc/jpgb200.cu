@@ -1965,7 +1965,7 @@ extern "C" int jpgb200_encode_batch_device(jpgb200_ctx *ctx, const uint8_t *d_pl
     {
         /* small frames: groups of frames per launch (identical bytes, a fraction of the launches) */
         const int G = group_frames(ctx, n_frames, w, h);
-        if (G > 1 && ctx->pipelined && ratio != 2 && (w % 16 == 0) && (n_frames + G - 1) / G >= 3)
+        if (G > 1 && ctx->pipelined && (w % 16 == 0) && (n_frames + G - 1) / G >= 3)
             return encode_groups_pipelined(ctx, d_planes, n_frames, G, w, h, quality, ratio, d_out, out_stride, d_lens);
         if (G > 1) {
             int rc = JPGB200_OK;
@@ -1977,7 +1977,7 @@ extern "C" int jpgb200_encode_batch_device(jpgb200_ctx *ctx, const uint8_t *d_pl
             return rc;
         }
     }
-    if (ctx->pipelined && ctx->legacy_entropy && !ctx->opt_huff && !ctx->fused_k1e && ratio != 2 && n_frames >= 3 && (w % 16 == 0))
+    if (ctx->pipelined && ctx->legacy_entropy && !ctx->opt_huff && !ctx->fused_k1e && n_frames >= 3 && (w % 16 == 0))
         return encode_batch_pipelined(ctx, d_planes, n_frames, w, h, quality, ratio, d_out, out_stride, d_lens);
     /* Overlap (default): frame f's tail (KF, KS: small, latency-bound) runs on a second stream
      * beside frame f+1's KE (it is launched behind frame f+1's K1, which fills the register files

@@ -614,7 +614,7 @@ def test_batch_overlap_is_invisible(enc, w, h, ratio, nf):
 
 
 @pytest.mark.parametrize("w,h,ratio,nf", [(1920, 1080, 0, 21), (640, 64, 1, 9), (256, 16, 0, 300), (1280, 720, 2, 6), (264, 40, 0, 5),
-                                          (1920, 1080, 0, 50), (640, 64, 1, 600)])
+                                          (1920, 1080, 0, 50), (640, 64, 1, 600), (1280, 720, 2, 120)])
 def test_frame_groups_equal_per_frame(enc, w, h, ratio, nf):
     """Batches of small frames share kernel launches (jpgb200_set_frame_groups: K1's tile index and the
     entropy kernels' blockIdx.y run over the frames of a group): same streams and lengths as four
@@ -681,7 +681,7 @@ def test_encode_coefficients_rejects_out_of_range_values(enc, pkg):
         assert ei.value.code == -6
 
 
-@pytest.mark.parametrize("w,h,ratio,nf", [(4096, 2320, 0, 5), (4112, 2304, 1, 4), (7680, 4320, 0, 3)])
+@pytest.mark.parametrize("w,h,ratio,nf", [(4096, 2320, 0, 5), (4112, 2304, 1, 4), (7680, 4320, 0, 3), (4112, 2320, 2, 4)])
 def test_pipelined_batch_is_invisible(enc, w, h, ratio, nf):
     """jpgb200_set_pipelined_batch: K1 of frame f+1 beside KE of frame f on three streams, two coefficient buffers and
     two sets of entropy workspaces alternating -- the same streams and lengths as the sequential batch, twice in a row
