@@ -117,7 +117,9 @@ int jpgb200_set_fused_tap(jpgb200_ctx *ctx, int on);
  *   5           form 0 named explicitly
  *   7           form 0 with FOUR transform warps per CTA taking the tile's components in turn and issuing their own
  *               TMA stores (k1_transform_pc4, 4:4:4 only; measured 3 % slower than form 0)
- * Forms 2..4 and 7 exist in A/B builds only (jpgb200_has_ab_forms). */
+ *   8           twelve warps per CTA: eight convert warps with one pixel row each, four transform warps, registers
+ *               re-divided with setmaxnreg (k1_transform_pc12, 4:4:4 only; measured 10 % slower than form 0)
+ * Forms 2..4, 7 and 8 exist in A/B builds only (jpgb200_has_ab_forms). */
 int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on);
 /* Arithmetic of the transform: 0 (default) = bug-compatible with the reference (its Cb sign slip,
  * src/preprocess.c:161, and the last block column read one pixel row higher, :199-211); 1 =

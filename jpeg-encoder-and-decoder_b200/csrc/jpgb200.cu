@@ -59,6 +59,9 @@ struct EvPair {
     cudaEvent_t a, b;
 };
 
+#ifndef K1_TWELVE_DEFAULT
+#define K1_TWELVE_DEFAULT false /* 4:4:4 K1 with eight one-row convert warps and four transform warps per CTA (k1_transform_pc12) */
+#endif
 #ifndef K1_FOUR_DEFAULT
 #define K1_FOUR_DEFAULT false /* 4:4:4 K1 with four transform warps per CTA (k1_transform_pc4) */
 #endif
@@ -108,7 +111,8 @@ struct jpgb200_ctx {
     unsigned int recode_last;
     unsigned long long ke_blocks, ke_blocks_sampled, ke_blocks_last;
     int ke_since_sample;
-    bool k1_four, k1c4_attr_set;   /* 4:4:4: four transform warps per CTA taking component units in turn (k1_transform_pc4) */
+    bool k1_four, k1c4_attr_set;
+    bool k1_twelve, k1d_attr_set; /* 4:4:4: eight one-row convert warps + four transform warps per CTA (k1_transform_pc12) */   /* 4:4:4: four transform warps per CTA taking component units in turn (k1_transform_pc4) */
     K1TLoad k1t_maps;
     bool no_tma_store; /* k1_pipe: copy the coefficients out with ordinary stores (A/B runs) */
     CUtensorMap tm32, tm16; /* tensor maps of the coefficient buffer, cached (two entries: the pipelined batch alternates buffers) */
@@ -486,6 +490,7 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
     ctx->legacy_entropy = true; /* measured faster than the fused K35 so far */
     ctx->k1_pc = true;          /* K1 default: the producer/consumer form (fastest measured) */
     ctx->k1_four = K1_FOUR_DEFAULT;
+    ctx->k1_twelve = K1_TWELVE_DEFAULT;
     ctx->group_small = true;
     {
         const char *pz = getenv("JPGB200_PIPELINED"); /* "0": K1 and KE of a batch strictly one after the other */
@@ -509,6 +514,8 @@ extern "C" int jpgb200_create(jpgb200_ctx **out, int device)
         ctx->ke_form_mode = kf ? (!strcmp(kf, "tight") ? 1 : (!strcmp(kf, "roomy") ? 2 : 0)) : 0;
         ctx->ke_roomy = ctx->ke_form_mode == 2;
         if (k && !strcmp(k, "pc4")) ctx->k1_four = true;
+        if (k && !strcmp(k, "pc12")) ctx->k1_twelve = true;
+        if (k && !strcmp(k, "pc8")) ctx->k1_twelve = false;
         if (k && !strcmp(k, "pc3")) ctx->k1_four = false;
         if (jpgb200_has_ab_forms()) {
             if (k && !strcmp(k, "cta")) ctx->k1_cta = true, ctx->k1_pc = false;
@@ -673,8 +680,9 @@ extern "C" int jpgb200_has_ab_forms(void)
 extern "C" int jpgb200_set_plain_transform(jpgb200_ctx *ctx, int on)
 {
     if (!ctx) return JPGB200_ERR_BAD_ARG;
-    if (((on >= 2 && on <= 4) || on == 7) && !jpgb200_has_ab_forms()) return JPGB200_ERR_BAD_ARG; /* forms 2..4 and 7 are A/B builds only */
-    ctx->k1_pc = (on == 0 || on == 5 || on == 6 || on == 7);
+    if (((on >= 2 && on <= 4) || on == 7 || on == 8) && !jpgb200_has_ab_forms()) return JPGB200_ERR_BAD_ARG; /* forms 2..4, 7 and 8 are A/B builds only */
+    ctx->k1_pc = (on == 0 || on == 5 || on == 6 || on == 7 || on == 8);
+    ctx->k1_twelve = (on == 8) || (on == 0 && K1_TWELVE_DEFAULT); /* 8: twelve warps per CTA (4:4:4), 5: eight */
     ctx->k1_tmaload = (on == 6); /* 5: the cp.async-fed form explicitly, 6: the TMA-load-fed form */
     ctx->k1_four = (on == 7) || (on == 0 && K1_FOUR_DEFAULT); /* 7: four transform warps (4:4:4, A/B builds), 5: three */
     ctx->k1_plain = (on == 1);
@@ -1203,6 +1211,26 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
             k1_transform_pc4<true><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
         else
             k1_transform_pc4<false><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
+#endif
+#ifdef JPGB200_AB
+    } else if (aligned16 && ctx->k1_pc && ctx->k1_twelve && ratio == 0 && !ctx->k1_plain) {
+        /* 4:4:4: eight one-row convert warps + four transform warps, registers re-divided with setmaxnreg (k1_transform_pc12) */
+        const size_t smem = sizeof(K1DSmem) + 1024;
+        if (!ctx->k1d_attr_set) {
+            CK(cudaFuncSetAttribute((k1_transform_pc12<false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            CK(cudaFuncSetAttribute((k1_transform_pc12<true>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            ctx->k1d_attr_set = true;
+        }
+        const long long n_tiles = (long long)p.tiles_per_row * (h / 8) * nframes;
+        const long long resident = (long long)ctx->sm_count * (ctx->k1_ctas_per_sm > 0 ? ctx->k1_ctas_per_sm : K1C_MIN_CTAS);
+        const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+        K1PStore st;
+        make_store_maps(ctx, &st, zz, n, zz_stride, nframes);
+        LaunchScope ls(ctx, KI_K1);
+        if (ctx->std_mode)
+            k1_transform_pc12<true><<<grid, K1D_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
+        else
+            k1_transform_pc12<false><<<grid, K1D_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
 #endif
     } else if (aligned16 && ctx->k1_pc && !ctx->k1_plain) {
         /* eight specialised warps per CTA handing tiles over through mbarriers (k1_pc.cuh) */

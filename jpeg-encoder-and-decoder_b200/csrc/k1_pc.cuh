@@ -420,6 +420,233 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pc4(co
 }
 #endif /* JPGB200_AB */
 
+/* ---- K1 with TWELVE warps per CTA (k1_transform_pc12, 4:4:4) -------------------------------------------------
+ * In k1_transform_pc both roles -- four convert warps with two pixel rows each, three transform warps with one
+ * component each -- need about the same ~1300 cycles per tile, each warp at its own dependency-limited pace; giving only
+ * the transform role a fourth warp (k1_transform_pc4) therefore changes nothing.  Here BOTH roles get more warps:
+ *   convert warps 0..7   warp k owns pixel row k of the tile's 32 blocks: lane j fetches the 8 bytes of its block's
+ *                        row from each plane itself (cp.async, private ring: no hand-over inside the warp), converts
+ *                        them as four pairs of neighbouring pixels (the same IEEE operations per sample) and stores
+ *                        the eight samples of each component into half k < 4 ? .x : .y of the row pair min(k, 7-k)
+ *   transform warps 8..11 the tile's components as units handed round-robin (unit u = 3 * tile + component -> warp u % 4),
+ *                        each warp issuing the TMA tensor store of its own unit (as in k1_transform_pc4)
+ * 384 threads, two CTAs per SM: the launch bound is 80 registers per thread and setmaxnreg re-divides them -- the two
+ * convert warpgroups keep 48, the transform warpgroup takes 144 (no spills; 56 / 128 spills 32 registers).
+ * MEASURED (profiles/README.md, round 2): bit-identical and SLOWER, 85.3 us per 8K frame against 77.3 us.  The convert
+ * warps now wait for the transform warps (20 % of all stall samples), but the kernel executes 60.4 M warp
+ * instructions instead of 42.6 M (eight warps repeat the per-tile address and tile-index arithmetic, the component
+ * index of the transform warps is no longer a constant), issue is active 68 % of the time, and the 4-byte sample
+ * stores collide two ways in shared memory (4.1 M bank conflicts against 1.0 M, LSU wavefronts at 67 % of peak).
+ * K1 behaves like an instruction-issue-bound kernel as soon as more warps are given to it: the 47 % of idle issue
+ * slots of the eight-warp form are not there to be filled.  An A/B form (JPGB200_AB=1, form 8), not in the product. */
+#ifdef JPGB200_AB
+#define K1D_THREADS 384
+#define K1D_REG_CONVERT 48
+#define K1D_REG_TRANSFORM 144
+
+struct K1DSmem {
+    K1Out coef[2][3];
+    K1F samples[2][3];
+    uint8_t raw[8][K1C_STAGES][3][K1_ROW_BYTES]; /* [convert warp = row][slot][plane][x] */
+    float mul[2][64];
+    unsigned long long samples_full[2], samples_free[2], coef_free[2][3];
+};
+
+/* convert warp k, lane j: the 8 bytes of row k of block tb0 + j from every plane (the block of column BW-1 one
+ * pixel row higher; row -1 of an image without halo is left alone: the caller's out-of-bounds bytes) */
+template <bool STD>
+__device__ __forceinline__ void k1d_fetch(const K1Params &p, uint8_t (*raw)[K1_ROW_BYTES], const K1Tile &tl, int k, int lane)
+{
+    const int bx = tl.tb0 + lane;
+    if (bx < p.BW) {
+        long long row = (long long)tl.by * 8 + k;
+        bool ok = true;
+        if (!STD && bx == p.BW - 1) {
+            row -= 1;
+            ok = (row >= 0) || p.has_halo;
+        }
+        if (ok) {
+            const long long off = (long long)tl.frame * p.plane_stride + row * p.W + (long long)bx * 8;
+#pragma unroll
+            for (int c = 0; c < 3; c++) cp_async8(&raw[c][lane * 8], (c == 0 ? p.r : (c == 1 ? p.g : p.b)) + off);
+        }
+    }
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
+}
+
+/* bytes 2i, 2i+1 of a word pair (lo, hi = the row's 8 bytes) -> two exact FP32 values */
+__device__ __forceinline__ f32x2 k1d_pair(const uint2 w, int i)
+{
+    const uint32_t src = (i < 2) ? w.x : w.y;
+    const int b0 = (2 * i) & 3;
+    f32x2 v;
+    v.x = __uint_as_float(__byte_perm(JPGB_BYTE_MAGIC, src, 0x3104u + (uint32_t)b0));
+    v.y = __uint_as_float(__byte_perm(JPGB_BYTE_MAGIC, src, 0x3104u + (uint32_t)b0 + 1u));
+    return p_add(v, p_bc(-8388608.0f));
+}
+
+/* one component's 32 blocks of a tile cut short by the image's right edge: coalesced 16-byte stores by one warp */
+__device__ __forceinline__ void k1d_copyout(const K1Out &sOut, const K1Params &p, const K1Tile &tl, int c, int lane)
+{
+    int16_t *z = (c == 0 ? p.zz_y : (c == 1 ? p.zz_cb : p.zz_cr)) + (long long)tl.frame * p.zz_stride;
+    uint4 *dst = reinterpret_cast<uint4 *>(z + ((long long)tl.by * p.BW + tl.tb0) * 64);
+    const int ch = lane & 7, jsub = lane >> 3;
+    const int nvalid = min(K1_TILE_BLOCKS, p.BW - tl.tb0);
+#pragma unroll
+    for (int t = 0; t < 8; t++) {
+        const int j = t * 4 + jsub;
+        if (j < nvalid) dst[j * 8 + ch] = sOut[j][ch ^ (j & 7)];
+    }
+}
+
+template <bool STD = false>
+__global__ void __launch_bounds__(K1D_THREADS, K1C_MIN_CTAS) k1_transform_pc12(const K1Params p, long long n_tiles,
+                                                                                const __grid_constant__ K1PStore st)
+{
+    extern __shared__ unsigned char k1_smem_raw[];
+    unsigned char *k1_smem = k1_smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(k1_smem_raw) & 1023u)) & 1023u);
+    K1DSmem &S = *reinterpret_cast<K1DSmem *>(k1_smem);
+    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+
+    if (tid < 128) S.mul[tid >> 6][tid & 63] = p.mul[tid >> 6][tid & 63];
+    if (blockIdx.x == 0)
+        for (int i = tid; i < p.clear_n; i += K1D_THREADS) p.clear[i] = 0u;
+    if (tid == 0) {
+#pragma unroll
+        for (int b = 0; b < 2; b++) {
+            mbar_init(&S.samples_full[b], 8);
+            mbar_init(&S.samples_free[b], 3);
+#pragma unroll
+            for (int c = 0; c < 3; c++) mbar_init(&S.coef_free[b][c], 1);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (w < 8) {
+        /* ================= convert warp k: one pixel row ================= */
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;\n" ::"n"(K1D_REG_CONVERT));
+        const int k = w;
+        const int kk = k < 4 ? k : 7 - k, half = k < 4 ? 0 : 1;
+        uint8_t(*ring)[3][K1_ROW_BYTES] = S.raw[k];
+#pragma unroll
+        for (int d = 0; d < K1C_STAGES - 1; d++) {
+            const long long td = (long long)blockIdx.x + (long long)d * gridDim.x;
+            if (td < n_tiles)
+                k1d_fetch<STD>(p, ring[d], k1_tile(p, td), k, lane);
+            else
+                asm volatile("cp.async.commit_group;\n" ::: "memory");
+        }
+        int it = 0;
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+            const int b = it & 1;
+            const unsigned use = (unsigned)(it >> 1);
+            const K1Tile tl = k1_tile(p, t);
+            {
+                const long long tn = t + (long long)(K1C_STAGES - 1) * gridDim.x;
+                if (tn < n_tiles)
+                    k1d_fetch<STD>(p, ring[(it + K1C_STAGES - 1) % K1C_STAGES], k1_tile(p, tn), k, lane);
+                else
+                    asm volatile("cp.async.commit_group;\n" ::: "memory");
+            }
+            asm volatile("cp.async.wait_group %0;\n" ::"n"(K1C_STAGES - 1) : "memory"); /* this lane's own copies */
+            const uint8_t(*raw)[K1_ROW_BYTES] = ring[it % K1C_STAGES];
+            uint2 px[3];
+            const bool oob = !STD && (tl.by == 0 && !p.has_halo && k == 0 && tl.tb0 + lane == p.BW - 1);
+#pragma unroll
+            for (int c = 0; c < 3; c++) px[c] = oob ? ld_oob(p.oob + 8 * c) : *reinterpret_cast<const uint2 *>(&raw[c][lane * 8]);
+            mbar_wait_relaxed(&S.samples_free[b], (use & 1u) ^ 1u); /* the transform warps have taken tile it-2 */
+            float *sy = reinterpret_cast<float *>(&S.samples[b][0][kk][0][lane]) + half;
+            float *scb = reinterpret_cast<float *>(&S.samples[b][1][kk][0][lane]) + half;
+            float *scr = reinterpret_cast<float *>(&S.samples[b][2][kk][0][lane]) + half;
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const f32x2 r = k1d_pair(px[0], i), g = k1d_pair(px[1], i), bl = k1d_pair(px[2], i);
+                const f32x2 y = colour_y_p(r, g, bl);
+                const f32x2 cb = STD ? colour_cb_std_p(r, g, bl) : colour_cb_p(r, g, bl);
+                const f32x2 cr = colour_cr_p(r, g, bl);
+                /* [x][slot] of float2: sample x of this row sits 64 floats after sample x - 1 */
+                sy[(2 * i) * 64] = y.x;
+                sy[(2 * i + 1) * 64] = y.y;
+                scb[(2 * i) * 64] = cb.x;
+                scb[(2 * i + 1) * 64] = cb.y;
+                scr[(2 * i) * 64] = cr.x;
+                scr[(2 * i + 1) * 64] = cr.y;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&S.samples_full[b]);
+        }
+    } else {
+        /* ================= transform warp x: units x, x + 4, x + 8, ... ================= */
+        asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;\n" ::"n"(K1D_REG_TRANSFORM));
+        const int x = w - 8;
+        const long long my_tiles = (n_tiles - (long long)blockIdx.x + gridDim.x - 1) / gridDim.x;
+        const int n_units = (int)(my_tiles * 3);
+        int pend_b = -1, pend_c = 0; /* a TMA store of this warp that may still be reading shared memory */
+        for (int u = x; u < n_units; u += 4) {
+            const int it = (int)((unsigned)u / 3u);
+            const int c = u - 3 * it;
+            const int b = it & 1;
+            const unsigned use = (unsigned)(it >> 1);
+            const float4 *m4 = reinterpret_cast<const float4 *>(S.mul[c == 0 ? 0 : 1]);
+            f32x2 P[4][8], Q[8][4];
+            mbar_wait(&S.samples_full[b], use & 1u);
+#pragma unroll
+            for (int k = 0; k < 4; k++)
+#pragma unroll
+                for (int xx = 0; xx < 8; xx++) P[k][xx] = S.samples[b][c][k][xx][lane];
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(&S.samples_free[b]);
+                if (pend_b >= 0) {
+                    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    mbar_arrive(&S.coef_free[pend_b][pend_c]);
+                }
+            }
+            pend_b = -1;
+            fdct8x8_p(P, Q);
+            float f[64];
+#pragma unroll
+            for (int v = 0; v < 8; v++)
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    const float4 m = m4[v * 2 + hh];
+                    const f32x2 q0 = p_fma(Q[v][2 * hh], make_float2(m.x, m.y), p_bc(JPGB_ROUND_MAGIC));
+                    const f32x2 q1 = p_fma(Q[v][2 * hh + 1], make_float2(m.z, m.w), p_bc(JPGB_ROUND_MAGIC));
+                    f[v * 8 + 4 * hh + 0] = q0.x;
+                    f[v * 8 + 4 * hh + 1] = q0.y;
+                    f[v * 8 + 4 * hh + 2] = q1.x;
+                    f[v * 8 + 4 * hh + 3] = q1.y;
+                }
+            uint32_t o[32];
+            zigzag_pack(f, o);
+            mbar_wait(&S.coef_free[b][c], (use & 1u) ^ 1u); /* tile it-2's unit has left the buffer */
+#pragma unroll
+            for (int j = 0; j < 8; j++)
+                S.coef[b][c][lane][j ^ (lane & 7)] = make_uint4(o[4 * j], o[4 * j + 1], o[4 * j + 2], o[4 * j + 3]);
+            const K1Tile tl = k1_tile(p, (long long)blockIdx.x + (long long)it * gridDim.x);
+            if (st.enabled && tl.tb0 + K1_TILE_BLOCKS <= p.BW) {
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); /* generic writes -> the TMA's proxy */
+                __syncwarp();
+                if (lane == 0) {
+                    const long long ry = (long long)tl.frame * st.rows_per_frame + (long long)tl.by * p.BW + tl.tb0;
+                    tma_store_2d(&st.box32, &S.coef[b][c], 0, (int)(ry + (c == 0 ? 0ll : (c == 1 ? st.row_cb : st.row_cr))));
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                }
+                pend_b = b;
+                pend_c = c;
+            } else {
+                __syncwarp();
+                k1d_copyout(S.coef[b][c], p, tl, c, lane);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&S.coef_free[b][c]);
+            }
+        }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+    }
+}
+#endif /* JPGB200_AB */
+
 /* ---- K1, producer/consumer form fed by 2-D TMA tile loads (k1_transform_pct) --------------------------------
  * k1_transform_pc's convert warps fetch their own two rows of the tile with cp.async: 27 LDGSTS and their
  * address arithmetic per lane and tile, issued on the schedulers the transform warps need.  Here the (otherwise

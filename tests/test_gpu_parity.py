@@ -424,6 +424,10 @@ def test_tma_and_plain_transform_agree(enc, pkg, w, h, q, ratio, seed):
             enc.set_plain_transform(7)  # four transform warps per CTA taking component units in turn (4:4:4; else = form 5)
             t7 = enc.coefficients(r, g, b, w, h, q, ratio)
             assert (a == t7).all()
+        if pkg.binding.has_ab_forms():
+            enc.set_plain_transform(8)  # twelve warps per CTA: eight one-row convert warps, four transform warps (4:4:4; else = form 5)
+            t8 = enc.coefficients(r, g, b, w, h, q, ratio)
+            assert (a == t8).all()
         enc.set_plain_transform(5)  # three transform warps, one per component
         t5 = enc.coefficients(r, g, b, w, h, q, ratio)
         assert (a == t5).all()
