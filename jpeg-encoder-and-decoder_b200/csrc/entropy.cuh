@@ -757,7 +757,6 @@ struct KeCfg {
 #ifndef KE_AC_GLOBAL
 #define KE_AC_GLOBAL 1 /* 1: only lut + dc (1152 bytes) are copied to shared memory, the (run, category) table stays in global memory */
 #endif
-#define KE_TABLE_BYTES (KE_TABLES_GLOBAL ? 0 : (KE_AC_GLOBAL ? (int)(sizeof(uint32_t) * (2 * 128 + 2 * 16)) : (int)sizeof(HuffPack)))
     /* words of private stream per entry.  KE lives on occupancy (shared memory per CTA): 4:4:4 with 5 words and the
      * (run, category) table left in global memory is 31.9 KB -> SEVEN CTAs per SM (72.6 us per 8K frame against
      * 77.0 us with 10 words and all tables in shared memory: six CTAs); 4:2:2 with 8 words is 45.2 KB -> five CTAs.
@@ -774,7 +773,11 @@ struct KeCfg {
     static const int STAGE_WORDS = ROW_BYTES / 4;        /* the chunk stream reuses the coefficient rows */
     static const int OFF_PRIV = ROW_BYTES;
     static const int OFF_H = OFF_PRIV + NT * PSTRIDE * 4;
-    static const int OFF_OFF = OFF_H + KE_TABLE_BYTES;
+    /* the roomy form has the shared memory for the whole table set (and busy content uses the (run, category) table
+     * for most of its symbols); the tight form keeps lut + dc only */
+    static const bool AC_GLOBAL = KE_AC_GLOBAL && !(ROOMY && RATIO != 2);
+    static const int TABLE_BYTES = KE_TABLES_GLOBAL ? 0 : (AC_GLOBAL ? (int)(sizeof(uint32_t) * (2 * 128 + 2 * 16)) : (int)sizeof(HuffPack));
+    static const int OFF_OFF = OFF_H + TABLE_BYTES;
     static const int OFF_EX = OFF_OFF + NT * 4;
     static const int OFF_WARP = OFF_EX + NT * 4;
     static const int OFF_FLAG = OFF_WARP + (NT / 32) * 4;
@@ -901,7 +904,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO, ROOMY>::NT, KeCfg<RATIO, ROOMY>::
     p.dc_pred[2] = q.dc_pred_dev ? q.dc_pred_dev[2] : q.dc_pred[2];
 
     ke_fill<RATIO, NT>(sC, p, m0, tid);
-    if (!KE_TABLES_GLOBAL) ec_load_bytes<NT, KE_TABLE_BYTES>(ke_smem + L::OFF_H, huff, tid); /* lut and dc come first in HuffPack */
+    if (!KE_TABLES_GLOBAL) ec_load_bytes<NT, L::TABLE_BYTES>(ke_smem + L::OFF_H, huff, tid); /* lut and dc come first in HuffPack */
     const KeMap<RATIO> mp(p, m0, tid);
     cp_async_wait_all();
     __syncthreads();
@@ -922,7 +925,7 @@ __global__ void __launch_bounds__(KeCfg<RATIO, ROOMY>::NT, KeCfg<RATIO, ROOMY>::
     else
         active = ec_entry_masks<true>(sC[mp.row], sw, 0, mm, prev0, eob);
     active = active && mp.valid;
-    const uint32_t *tAc = (KE_AC_GLOBAL ? huff->ac : sH.ac)[mp.luma ? 0 : 1], *tDc = sH.dc[mp.luma ? 0 : 1], *tLut = sH.lut[mp.luma ? 0 : 1];
+    const uint32_t *tAc = (L::AC_GLOBAL ? huff->ac : sH.ac)[mp.luma ? 0 : 1], *tDc = sH.dc[mp.luma ? 0 : 1], *tLut = sH.lut[mp.luma ? 0 : 1];
     if (mp.valid) {
         if (mp.part == 0) {
             int pred;
