@@ -75,6 +75,58 @@ __device__ __forceinline__ void mbar_arrive(unsigned long long *bar)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(a) : "memory");
 }
 
+/* Tile coordinates of a persistent CTA's tile sequence t, t + D, t + 2D, ... (D = gridDim.x) without a division per
+ * tile: the step is a fixed (block rows, tiles) pair.  Falls back to k1_tile when a step spans whole frames. */
+struct K1TileIter {
+    int frame, by, tbx, d_by, d_tb, tpr, rows;
+    long long t;
+    unsigned step;
+    bool fast;
+    __device__ __forceinline__ void init(const K1Params &p, long long t0, unsigned step_)
+    {
+        t = t0;
+        step = step_;
+        tpr = p.tiles_per_row;
+        rows = p.H >> 3;
+        const K1Tile o = k1_tile(p, t0);
+        frame = o.frame;
+        by = o.by;
+        tbx = o.tb0 / K1_TILE_BLOCKS;
+        d_by = (int)(step / (unsigned)tpr);
+        d_tb = (int)(step - (unsigned)d_by * (unsigned)tpr);
+        fast = d_by < rows - 1;
+    }
+    __device__ __forceinline__ K1Tile get() const
+    {
+        K1Tile o;
+        o.frame = frame;
+        o.by = by;
+        o.tb0 = tbx * K1_TILE_BLOCKS;
+        return o;
+    }
+    __device__ __forceinline__ void next(const K1Params &p)
+    {
+        t += step;
+        if (fast) {
+            tbx += d_tb;
+            by += d_by;
+            if (tbx >= tpr) {
+                tbx -= tpr;
+                by++;
+            }
+            if (by >= rows) { /* d_by < rows - 1: at most one frame boundary per step */
+                by -= rows;
+                frame++;
+            }
+        } else {
+            const K1Tile o = k1_tile(p, t);
+            frame = o.frame;
+            by = o.by;
+            tbx = o.tb0 / K1_TILE_BLOCKS;
+        }
+    }
+};
+
 /* convert warp k: its two rows of one tile, 16 bytes per copy (3 per lane).  The block of column
  * BW-1 is fetched one pixel row higher; row -1 of an image without halo is left
  * alone and replaced by the caller's out-of-bounds bytes at conversion time. */
@@ -148,14 +200,16 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pc(con
                 asm volatile("cp.async.commit_group;\n" ::: "memory");
         }
         int it = 0;
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+        K1TileIter cur, pre; /* this tile and the one fetched now, K1C_STAGES - 1 tiles ahead */
+        cur.init(p, blockIdx.x, gridDim.x);
+        pre.init(p, (long long)blockIdx.x + (long long)(K1C_STAGES - 1) * gridDim.x, gridDim.x);
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++, cur.next(p), pre.next(p)) {
             const int b = it & 1;
             const unsigned use = (unsigned)(it >> 1);
-            const K1Tile tl = k1_tile(p, t);
+            const K1Tile tl = cur.get();
             {
-                const long long tn = t + (long long)(K1C_STAGES - 1) * gridDim.x;
-                if (tn < n_tiles)
-                    k1c_fetch<STD>(p, ring[(it + K1C_STAGES - 1) % K1C_STAGES], k1_tile(p, tn), k, lane);
+                if (pre.t < n_tiles)
+                    k1c_fetch<STD>(p, ring[(it + K1C_STAGES - 1) % K1C_STAGES], pre.get(), k, lane);
                 else
                     asm volatile("cp.async.commit_group;\n" ::: "memory");
             }
@@ -234,10 +288,12 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pc(con
     } else if (w == 7) {
         /* ================= store warp ================= */
         int it = 0;
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+        K1TileIter cur;
+        cur.init(p, blockIdx.x, gridDim.x);
+        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++, cur.next(p)) {
             const int b = it & 1;
             const unsigned use = (unsigned)(it >> 1);
-            const K1Tile tl = k1_tile(p, t);
+            const K1Tile tl = cur.get();
             mbar_wait_relaxed(&S.coef_full[b], use & 1u);
             k1p_store<RATIO>(S.coef[b], p, st, tl, lane); /* returns when shared memory has been read */
             __syncwarp();
