@@ -1234,7 +1234,7 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
 #endif
     } else if (aligned16 && ctx->k1_pc && !ctx->k1_plain) {
         /* eight specialised warps per CTA handing tiles over through mbarriers (k1_pc.cuh) */
-        const size_t smem = sizeof(K1CSmem) + 1024;
+        const size_t smem = K1C_PIPES * sizeof(K1CSmem) + 1024;
         if (!ctx->k1c_attr_set) {
             CK(cudaFuncSetAttribute((k1_transform_pc<0, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
             CK(cudaFuncSetAttribute((k1_transform_pc<1, false>), cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1244,19 +1244,20 @@ static int launch_k1(jpgb200_ctx *ctx, const uint8_t *d_r, const uint8_t *d_g, c
         }
         const long long n_tiles = (long long)p.tiles_per_row * (h / 8) * nframes;
         const long long resident = (long long)ctx->sm_count * (ctx->k1_ctas_per_sm > 0 ? ctx->k1_ctas_per_sm : K1C_MIN_CTAS);
-        const unsigned grid = (unsigned)(n_tiles < resident ? n_tiles : resident);
+        /* pipelines (eight warps each) in flight; a CTA holds K1C_PIPES of them */
+        const unsigned grid = (unsigned)(((n_tiles < resident ? n_tiles : resident) + K1C_PIPES - 1) / K1C_PIPES);
         K1PStore st;
         make_store_maps(ctx, &st, zz, n, zz_stride, nframes);
         LaunchScope ls(ctx, KI_K1);
         if (ctx->std_mode) {
             if (ratio == 0)
-                k1_transform_pc<0, true><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
+                k1_transform_pc<0, true><<<grid, K1C_CTA_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
             else
-                k1_transform_pc<1, true><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
+                k1_transform_pc<1, true><<<grid, K1C_CTA_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
         } else if (ratio == 0)
-            k1_transform_pc<0, false><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
+            k1_transform_pc<0, false><<<grid, K1C_CTA_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
         else
-            k1_transform_pc<1, false><<<grid, K1C_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
+            k1_transform_pc<1, false><<<grid, K1C_CTA_THREADS, smem, ctx->stream>>>(p, n_tiles, st);
 #ifdef JPGB200_AB
     } else if (aligned16 && ctx->k1_pipe && !ctx->k1_plain) {
         /* persistent CTAs, warps specialised and software-pipelined over tiles (k1_pipe.cuh) */

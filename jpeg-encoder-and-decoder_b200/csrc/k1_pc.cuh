@@ -38,8 +38,32 @@ namespace jpgb200 {
 #ifndef K1C_MIN_CTAS
 #define K1C_MIN_CTAS 2
 #endif
+/* K1C_DUAL: ONE CTA of sixteen warps per SM running the two eight-warp pipelines that otherwise live in two CTAs.
+ * Same code, same tiles (pipeline q of CTA x takes the tile sequence of CTA 2x + q of the two-CTA form), same shared
+ * memory per pipeline -- but the place of every warp on the SM's four schedulers (warp q -> scheduler q % 4) is now
+ * ours to choose: with two CTAs both put their three transform warps on schedulers 0..2 (FMA-pipe cycles per tile
+ * pair 1472 / 1472 / 1472 / 384); here it is 1120 / 1280 / 1280 / 1120 with the two pipelines' transform warps never
+ * more than one of each per scheduler. */
+#ifndef K1C_DUAL
+#define K1C_DUAL 1 /* measured: 68.5-68.9 us per 8K frame against 76.4 us for two CTAs of eight warps (-DK1C_DUAL=0) */
+#endif
+#if K1C_DUAL
+#define K1C_CTA_THREADS 512
+#define K1C_LB_CTAS 1
+#define K1C_PIPES 2
+/* nibble q = (pipeline << 3) | role of warp q; roles 0..3 convert warp k, 4..6 transform warp c, 7 store warp
+ *   S0: q0 = A.C0  q4 = A.C1  q8  = B.C0  q12 = A.T0      S1: q1 = A.St  q5 = A.C2  q9  = B.T0  q13 = A.T1
+ *   S2: q2 = B.St  q6 = B.C1  q10 = B.T1  q14 = A.T2      S3: q3 = A.C3  q7 = B.C2  q11 = B.C3  q15 = B.T2 */
+#ifndef K1C_DUAL_MAP
+#define K1C_DUAL_MAP 0xE654BDC8A9213F70ull
+#endif
+#else
+#define K1C_CTA_THREADS K1C_THREADS
+#define K1C_LB_CTAS K1C_MIN_CTAS
+#define K1C_PIPES 1
+#endif
 
-struct K1CSmem {
+struct alignas(1024) K1CSmem {
     K1Out coef[2][3];                       /* 24 KB, 1 KB aligned (TMA swizzle) */
     K1F samples[2][3];                      /* 48 KB */
     uint8_t raw[4][K1C_STAGES][3][2][K1_ROW_BYTES]; /* [convert warp][slot][plane][row k | row 7-k][x]  18 KB */
@@ -159,27 +183,36 @@ __device__ __forceinline__ void k1c_fetch(const K1Params &p, uint8_t (*raw)[2][K
 }
 
 template <int RATIO, bool STD = false>
-__global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pc(const K1Params p, long long n_tiles,
-                                                                              const __grid_constant__ K1PStore st)
+__global__ void __launch_bounds__(K1C_CTA_THREADS, K1C_LB_CTAS) k1_transform_pc(const K1Params p, long long n_tiles,
+                                                                                 const __grid_constant__ K1PStore st)
 {
     extern __shared__ unsigned char k1_smem_raw[];
     unsigned char *k1_smem = k1_smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(k1_smem_raw) & 1023u)) & 1023u);
-    K1CSmem &S = *reinterpret_cast<K1CSmem *>(k1_smem);
+    K1CSmem *const SP = reinterpret_cast<K1CSmem *>(k1_smem);
     /* (a scheduler-aware permutation of the roles -- FMA-heavy warps spread 2,3,3,2 over the four
      * schedulers of an SM instead of 2,2,2,0 -- was measured and made no difference) */
-    const int tid = threadIdx.x, lane = tid & 31, w = tid >> 5;
+    const int tid = threadIdx.x, lane = tid & 31;
+#if K1C_DUAL
+    const unsigned role = (unsigned)((K1C_DUAL_MAP >> (4 * (tid >> 5))) & 15ull);
+    const int w = (int)(role & 7u), pipe = (int)(role >> 3);
+#else
+    const int w = tid >> 5, pipe = 0;
+#endif
+    K1CSmem &S = SP[pipe];
+    /* this pipeline's place in the persistent tile sequence: first tile and stride */
+    const unsigned vb = blockIdx.x * K1C_PIPES + (unsigned)pipe, vg = gridDim.x * K1C_PIPES;
     constexpr int NT = (RATIO == 0) ? 3 : 2; /* transform warps with work */
 
-    if (tid < 128) S.mul[tid >> 6][tid & 63] = p.mul[tid >> 6][tid & 63];
+    if (tid < 128 * K1C_PIPES) SP[tid >> 7].mul[(tid >> 6) & 1][tid & 63] = p.mul[(tid >> 6) & 1][tid & 63];
     if (blockIdx.x == 0)
-        for (int i = tid; i < p.clear_n; i += K1C_THREADS) p.clear[i] = 0u;
-    if (tid == 0) {
+        for (int i = tid; i < p.clear_n; i += K1C_CTA_THREADS) p.clear[i] = 0u;
+    if (tid < K1C_PIPES) {
 #pragma unroll
         for (int b = 0; b < 2; b++) {
-            mbar_init(&S.samples_full[b], 4);
-            mbar_init(&S.samples_free[b], NT);
-            mbar_init(&S.coef_full[b], NT);
-            mbar_init(&S.coef_free[b], 1);
+            mbar_init(&SP[tid].samples_full[b], 4);
+            mbar_init(&SP[tid].samples_free[b], NT);
+            mbar_init(&SP[tid].coef_full[b], NT);
+            mbar_init(&SP[tid].coef_free[b], 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -193,7 +226,7 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pc(con
         uint8_t(*ring)[3][2][K1_ROW_BYTES] = S.raw[k];
 #pragma unroll
         for (int d = 0; d < K1C_STAGES - 1; d++) {
-            const long long td = (long long)blockIdx.x + (long long)d * gridDim.x;
+            const long long td = (long long)vb + (long long)d * vg;
             if (td < n_tiles)
                 k1c_fetch<STD>(p, ring[d], k1_tile(p, td), k, lane);
             else
@@ -201,9 +234,9 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pc(con
         }
         int it = 0;
         K1TileIter cur, pre; /* this tile and the one fetched now, K1C_STAGES - 1 tiles ahead */
-        cur.init(p, blockIdx.x, gridDim.x);
-        pre.init(p, (long long)blockIdx.x + (long long)(K1C_STAGES - 1) * gridDim.x, gridDim.x);
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++, cur.next(p), pre.next(p)) {
+        cur.init(p, vb, vg);
+        pre.init(p, (long long)vb + (long long)(K1C_STAGES - 1) * vg, vg);
+        for (long long t = vb; t < n_tiles; t += vg, it++, cur.next(p), pre.next(p)) {
             const int b = it & 1;
             const unsigned use = (unsigned)(it >> 1);
             const K1Tile tl = cur.get();
@@ -250,7 +283,7 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pc(con
         const int c = w - 4;
         const float4 *m4 = reinterpret_cast<const float4 *>(S.mul[c == 0 ? 0 : 1]);
         int it = 0;
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++) {
+        for (long long t = vb; t < n_tiles; t += vg, it++) {
             const int b = it & 1;
             const unsigned use = (unsigned)(it >> 1);
             f32x2 P[4][8], Q[8][4];
@@ -289,8 +322,8 @@ __global__ void __launch_bounds__(K1C_THREADS, K1C_MIN_CTAS) k1_transform_pc(con
         /* ================= store warp ================= */
         int it = 0;
         K1TileIter cur;
-        cur.init(p, blockIdx.x, gridDim.x);
-        for (long long t = blockIdx.x; t < n_tiles; t += gridDim.x, it++, cur.next(p)) {
+        cur.init(p, vb, vg);
+        for (long long t = vb; t < n_tiles; t += vg, it++, cur.next(p)) {
             const int b = it & 1;
             const unsigned use = (unsigned)(it >> 1);
             const K1Tile tl = cur.get();
