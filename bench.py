@@ -357,16 +357,21 @@ def run_b200(args):
         iso_ms = kbreak.get(kname, (0.0, 0))
         iso = iso_ms[0] * 1e-3 / max(iso_ms[1], 1) if iso_ms[1] else None
         dur = iso if iso else span
+        # frames per launch: batches run as multi-frame launch groups (one K1 / KE / KF / KS launch per group of frames)
+        fpl = max(1, int(round(F / iso_ms[1]))) if iso_ms[1] else 1
+        alg_frame = alg_bytes
+        alg_bytes = alg_bytes * fpl
         tr = traffic_file.get(kname, {})
         return {"bound": "hbm", "kernel": label, "achieved": alg_bytes / dur / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": alg_bytes / dur / 1e9 / peak, "frac_of_nominal_8000": alg_bytes / dur / 1e9 / 8000.0,
                 "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes": what, "avg_launch_us": dur * 1e6,
+                "frames_per_launch": fpl, "algorithmic_bytes_per_frame": alg_frame, "us_per_frame": dur * 1e6 / fpl,
                 "launches_timed": iso_ms[1] if iso else n,
                 "duration_source": ("CUDA events around every launch of one extra step of this run with the frames' kernels one after "
                                     "the other (no other kernel on the GPU), right after the timed region") if iso else
                                    "CUDA events around every 8th launch of the timed region",
-                "share_of_step": dur * 1e3 * F / ms_per_step,
+                "share_of_step": dur * 1e3 * (F / fpl) / ms_per_step,
                 # the event-to-event span of a launch inside the (pipelined) timed region
                 "span_in_timed_region_us": span * 1e6, "span_launches_timed": n,
                 "frac_of_span": alg_bytes / span / 1e9 / peak,

@@ -1962,12 +1962,28 @@ static int encode_batch_pipelined(jpgb200_ctx *ctx, const uint8_t *d_planes, int
     return rc;
 }
 
-/* frames per multi-frame launch group: about one 8K frame's worth of pixels, 1 = frame-by-frame */
+/* frames per multi-frame launch group, 1 = frame-by-frame.  Small frames: about one 8K frame's worth of pixels per
+ * launch (a 1080p frame is launch-bound on its own).  Large frames fill the GPU on their own, but every launch still
+ * pays for filling and draining 148 SMs (K1's CTAs take a whole SM each: they start when the last chunk-encode CTA of
+ * the frame before has left theirs) -- with eight 8K frames per launch the batch runs at 244 k Mpixel/s against 229 k
+ * frame by frame (2: 240 k, 4: 243 k; profiles/README.md).  A batch is cut into at least three groups, which is what
+ * the pipelined group path wants; with pipelining off the groups run one after the other (bench.py's per-kernel pass).
+ * JPGB200_GROUP_LARGE=n overrides the group size of large frames (A/B). */
 static int group_frames(const jpgb200_ctx *ctx, int n_frames, int w, int h)
 {
     if (!ctx->group_small || !ctx->legacy_entropy || ctx->opt_huff || ctx->fused_k1e || n_frames < 2) return 1;
     const long long npx = (long long)w * h;
-    if (npx > 4096ll * 2304ll) return 1; /* large frames fill the GPU on their own */
+    if (npx > 4096ll * 2304ll) {
+        static int g_large = -1;
+        if (g_large < 0) {
+            const char *e = getenv("JPGB200_GROUP_LARGE");
+            g_large = e ? atoi(e) : 0;
+            if (g_large < 0) g_large = 0;
+        }
+        int g = g_large ? g_large : 8;
+        if (g > n_frames / 3) g = n_frames / 3;
+        return g < 2 ? 1 : g;
+    }
     long long g = (7680ll * 4320ll) / npx;
     if (g > 256) g = 256;
     if (g > n_frames) g = n_frames;

@@ -283,6 +283,9 @@ __global__ void __launch_bounds__(K1C_CTA_THREADS, K1C_LB_CTAS) k1_transform_pc(
         const int c = w - 4;
         const float4 *m4 = reinterpret_cast<const float4 *>(S.mul[c == 0 ? 0 : 1]);
         int it = 0;
+#if K1C_DUAL && defined(K1C_PHASE_NS)
+        if (pipe == 1) __nanosleep(K1C_PHASE_NS); /* experiment: start the second pipeline's transform warps half a tile late */
+#endif
         for (long long t = vb; t < n_tiles; t += vg, it++) {
             const int b = it & 1;
             const unsigned use = (unsigned)(it >> 1);
