@@ -525,7 +525,10 @@ __device__ __forceinline__ void ec_pack_masked(const uint4 *row, unsigned sw4, b
             }
             /* ONE put for both kinds of symbol.  (Fetching the NEXT coefficient's position and value before this one is
              * coded -- software pipelining of find-bit -> address -> load against table word -> shift -> accumulate --
-             * was measured: 73.1 us against 72.2 us.) */
+             * was measured: 73.1 us against 72.2 us.  So was a form of this loop with the position arithmetic folded
+             * into one shift and one XOR on 32-bit shared addresses -- three instructions fewer per symbol, LDS.S16
+             * instead of LDS.U16 + PRMT: 57.9-58.1 us against 57.9-58.0 us, no difference; what did count was the
+             * bit writer's own chain, see PrivSinkBF.) */
             s.put(e >> 5, (int)(e & 31u));
         }
     }
@@ -681,23 +684,25 @@ struct PrivSink {
  * completed, else to the pad word behind the region -- and the bookkeeping is selects. */
 struct PrivSinkBF {
     unsigned long long acc;
-    int nacc;
-    uint32_t *wp, *end; /* end = the region's pad word: always writable */
+    unsigned nacc;   /* bits of acc not stored yet: < 32 */
+    unsigned wa, ea; /* shared-window addresses: the next word of the region, the region's pad word (always writable) */
+    /* 32-bit shared addresses and arithmetic selects only: full = (nacc + n) >> 5 is 0 or 1, the destination is
+     * min(wa | (full - 1), ea) -- the pad word when no word was completed or the region is used up */
     __device__ __forceinline__ void put(uint32_t v, int n)
     {
         acc = (acc << n) | (unsigned long long)v;
-        nacc += n;
-        const bool full = nacc >= 32;
-        nacc -= full ? 32 : 0;
-        uint32_t *dst = (full && wp < end) ? wp : end;
-        *dst = (uint32_t)(acc >> nacc); /* meaningful only when `full` */
-        wp += full ? 1 : 0;
+        const unsigned t = nacc + (unsigned)n; /* < 64 */
+        const unsigned full = t >> 5;
+        nacc = t & 31u;
+        const unsigned dst = min(wa | (full - 1u), ea);
+        asm volatile("st.shared.b32 [%0], %1;" ::"r"(dst), "r"((uint32_t)(acc >> nacc)) : "memory"); /* meaningful only when `full` */
+        wa += full << 2;
     }
-    /* returns the number of bits written; `base` = the region's first word */
-    __device__ __forceinline__ uint32_t finish(const uint32_t *base)
+    /* returns the number of bits written; `base` = shared-window address of the region's first word */
+    __device__ __forceinline__ uint32_t finish(unsigned base)
     {
-        const uint32_t bits = (uint32_t)(wp - base) * 32u + (uint32_t)nacc;
-        if (nacc > 0 && wp < end) *wp = (uint32_t)(acc << (32 - nacc));
+        const uint32_t bits = ((wa - base) << 3) + nacc;
+        if (nacc > 0 && wa < ea) asm volatile("st.shared.b32 [%0], %1;" ::"r"(wa), "r"((uint32_t)(acc << (32u - nacc))) : "memory");
         return bits;
     }
 };
@@ -940,12 +945,13 @@ __global__ void __launch_bounds__(KeCfg<RATIO, ROOMY>::NT, KeCfg<RATIO, ROOMY>::
     }
     if (active) {
         PrivSinkBF s;
+        const unsigned pa = (unsigned)__cvta_generic_to_shared(priv);
         s.acc = 0;
         s.nacc = 0;
-        s.wp = priv;
-        s.end = priv + L::PRIV; /* PSTRIDE = PRIV + 1: the pad word */
+        s.wa = pa;
+        s.ea = pa + 4u * (unsigned)L::PRIV; /* PSTRIDE = PRIV + 1: the pad word */
         ec_pack_masked(sC[mp.row], sw4, mp.part == 0, diff, mm, prev0, eob, tAc, tDc, tLut, s);
-        nbits = s.finish(priv);
+        nbits = s.finish(pa);
     }
     sOff[mp.e_local] = nbits; /* stream order */
     __syncthreads(); /* every entry is coded: the coefficient rows are dead from here on */

@@ -1,11 +1,11 @@
 /*
- * K1, producer/consumer form (k1_transform_pc): eight specialised warps per CTA, two CTAs per SM,
- * no CTA-wide barrier -- every hand-over is an mbarrier.
+ * K1, producer/consumer form (k1_transform_pc): PIPELINES of eight specialised warps, no CTA-wide barrier --
+ * every hand-over is an mbarrier.  One CTA of sixteen warps per SM runs two pipelines (K1C_DUAL, below).
  *
- *   convert warps 0..3  (k = warp)  fetch rows k and 7-k of the tile's 32 blocks two tiles ahead
+ *   convert warps 0..3  (k = role)  fetch rows k and 7-k of the tile's 32 blocks two tiles ahead
  *                       (cp.async, private ring), turn them into FP32 row pairs (PRMT + FADD2,
  *                       FFMA2) and fill sample buffer b          -> arrive  samples_full[b]
- *   transform warps 4..6 (c = warp - 4)  wait samples_full[b], pull their 32 blocks (one per
+ *   transform warps 4..6 (c = role - 4)  wait samples_full[b], pull their 32 blocks (one per
  *                       lane, 64 samples) into registers          -> arrive  samples_free[b]
  *                       packed FDCT, FFMA2 quantise, zig-zag pack; wait coef_free[o], store the
  *                       rows (128-byte swizzle)                   -> arrive  coef_full[o]
@@ -20,6 +20,16 @@
  * operations: 78.6 us) into the convert warps, which own whole rows, was measured against doing
  * it all in the transform warps (76.5 us): both roles are already equally busy.  Three CTAs per SM
  * (two convert warps with two row pairs each, one sample buffer, 96 registers) ran at 95 us.
+ *
+ * WHERE a warp runs matters more than any of that.  A warp is bound to one of the SM's four schedulers (and its
+ * FMA pipe) for life: warp q of a CTA to scheduler q % 4.  As two CTAs of eight warps, both pipelines of an SM put
+ * their three transform warps on schedulers 0..2 and their store warps on scheduler 3: per pair of tiles the FMA
+ * pipes of schedulers 0..2 carry 1472 cycles of packed arithmetic each, scheduler 3's 384 (ncu: issue active
+ * 46-61 % per scheduler, profiles/r2_final_ncu_full.csv) -- 76.4 us per 8K frame.  Measured on the way
+ * (profiles/README.md): two transform warps of the SAME pipeline on one scheduler are ruinous (they work in phase:
+ * 90-95 us), one CTA of sixteen warps with the two-CTA layout is 72.5 us, and the layout of K1C_DUAL_MAP below --
+ * no scheduler holds two transform warps of one pipeline, the two that hold two transform warps (one of each
+ * pipeline) hold one convert warp, the other two hold three -- is 68.5 us: 1120 / 1280 / 1280 / 1120 cycles.
  */
 #ifndef JPGB200_K1_PC_CUH
 #define JPGB200_K1_PC_CUH
@@ -189,8 +199,6 @@ __global__ void __launch_bounds__(K1C_CTA_THREADS, K1C_LB_CTAS) k1_transform_pc(
     extern __shared__ unsigned char k1_smem_raw[];
     unsigned char *k1_smem = k1_smem_raw + ((1024u - ((unsigned)__cvta_generic_to_shared(k1_smem_raw) & 1023u)) & 1023u);
     K1CSmem *const SP = reinterpret_cast<K1CSmem *>(k1_smem);
-    /* (a scheduler-aware permutation of the roles -- FMA-heavy warps spread 2,3,3,2 over the four
-     * schedulers of an SM instead of 2,2,2,0 -- was measured and made no difference) */
     const int tid = threadIdx.x, lane = tid & 31;
 #if K1C_DUAL
     const unsigned role = (unsigned)((K1C_DUAL_MAP >> (4 * (tid >> 5))) & 15ull);
@@ -283,9 +291,6 @@ __global__ void __launch_bounds__(K1C_CTA_THREADS, K1C_LB_CTAS) k1_transform_pc(
         const int c = w - 4;
         const float4 *m4 = reinterpret_cast<const float4 *>(S.mul[c == 0 ? 0 : 1]);
         int it = 0;
-#if K1C_DUAL && defined(K1C_PHASE_NS)
-        if (pipe == 1) __nanosleep(K1C_PHASE_NS); /* experiment: start the second pipeline's transform warps half a tile late */
-#endif
         for (long long t = vb; t < n_tiles; t += vg, it++) {
             const int b = it & 1;
             const unsigned use = (unsigned)(it >> 1);
