@@ -364,7 +364,8 @@ def run_b200(args):
         tr = traffic_file.get(kname, {})
         return {"bound": "hbm", "kernel": label, "achieved": alg_bytes / dur / 1e9, "peak": peak, "unit": "GB/s",
                 "frac": alg_bytes / dur / 1e9 / peak, "frac_of_nominal_8000": alg_bytes / dur / 1e9 / 8000.0,
-                "traffic": tr.get("dram_bytes_per_launch"), "traffic_source": tr.get("source"), "peak_source": peak_src,
+                "traffic": (tr["dram_bytes_per_launch"] * fpl / max(1, tr.get("frames_per_launch", 1))) if tr.get("dram_bytes_per_launch") else None,
+                "traffic_source": tr.get("source"), "peak_source": peak_src,
                 "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes": what, "avg_launch_us": dur * 1e6,
                 "frames_per_launch": fpl, "algorithmic_bytes_per_frame": alg_frame, "us_per_frame": dur * 1e6 / fpl,
                 "launches_timed": iso_ms[1] if iso else n,

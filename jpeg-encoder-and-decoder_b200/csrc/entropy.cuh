@@ -687,7 +687,9 @@ struct PrivSinkBF {
     unsigned nacc;   /* bits of acc not stored yet: < 32 */
     unsigned wa, ea; /* shared-window addresses: the next word of the region, the region's pad word (always writable) */
     /* 32-bit shared addresses and arithmetic selects only: full = (nacc + n) >> 5 is 0 or 1, the destination is
-     * min(wa | (full - 1), ea) -- the pad word when no word was completed or the region is used up */
+     * min(wa | (full - 1), ea) -- the pad word when no word was completed or the region is used up.  (58.0 us per 8K
+     * frame against 60.7 us with generic pointers and compare-and-select; a PREDICATED store of completed words
+     * only -- two instructions fewer -- was measured at 59.2 us.) */
     __device__ __forceinline__ void put(uint32_t v, int n)
     {
         acc = (acc << n) | (unsigned long long)v;

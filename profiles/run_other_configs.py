@@ -5,7 +5,7 @@ import __graft_entry__ as ge
 pkg = ge.load_package(); enc = pkg.Encoder(0)
 for (W, H, q, ratio, name) in [(3840, 2160, 90, 1, "config3 4K 4:2:2 q90"), (1920, 1080, 75, 0, "config2 1080p 4:4:4 q75"), (3840, 2160, 75, 2, "4K 4:2:0 q75 (16-row padded: 2176)")]:
     if ratio == 2: H = 2176
-    F = 16
+    F = 64
     planes = torch.empty((F, 3, H, W), dtype=torch.uint8, device="cuda")
     out = torch.empty((F, 2 * W * H), dtype=torch.uint8, device="cuda"); lens = torch.zeros(F, dtype=torch.int64, device="cuda")
     for f in range(F): enc.synth_device(planes.data_ptr() + f * 3 * W * H, W, H, 1002, f, 0)
