@@ -74,18 +74,59 @@ def measured_peak():
 
 
 class ClockSampler:
-    """nvidia-smi clocks and throttle reasons DURING the timed region."""
+    """SM clocks and throttle reasons DURING the timed region: an NVML thread sampling every 5 ms (the timed region of a
+    fast run is tens of milliseconds: `nvidia-smi -lms 100` misses it), nvidia-smi as the fallback."""
 
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    # NVML clocks-event-reason bits
+    REASONS = {0x8: "hw_slowdown", 0x40: "hw_thermal_slowdown", 0x20: "sw_thermal_slowdown", 0x4: "sw_power_cap"}
 
     def __init__(self, index):
         self.index = index
         self.rows = []
         self.proc = None
+        self.nvml = None
+        self.samples = []  # (sm MHz, reasons bitmask)
+        self.max_mhz = None
+        self.stop_flag = False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            import torch
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            if not uuid.startswith("GPU-"):
+                uuid = "GPU-" + uuid
+            return pynvml, pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, "encode") else uuid)
+        except Exception:
+            return pynvml, pynvml.nvmlDeviceGetHandleByIndex(self.index)
+
+    def _nvml_loop(self):
+        pynvml, h = self.nvml
+        while not self.stop_flag:
+            try:
+                mhz = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:
+                    rs = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                self.samples.append((float(mhz), int(rs)))
+            except Exception:
+                pass
+            time.sleep(0.005)
 
     def start(self):
+        try:
+            self.nvml = self._nvml_handle()
+            self.max_mhz = float(self.nvml[0].nvmlDeviceGetMaxClockInfo(self.nvml[1], self.nvml[0].NVML_CLOCK_SM))
+            self.thread = threading.Thread(target=self._nvml_loop, daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.nvml = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "100",
                                           "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
@@ -99,6 +140,17 @@ class ClockSampler:
             self.rows.append(line.strip())
 
     def stop(self):
+        if self.nvml:
+            self.stop_flag = True
+            self.thread.join(timeout=1)
+            sm = [a for a, _ in self.samples]
+            reasons = set()
+            for _, rs in self.samples:
+                for bit, nm in self.REASONS.items():
+                    if rs & bit:
+                        reasons.add(nm)
+            return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(reasons),
+                    "samples": len(sm), "source": "NVML, one sample per 5 ms of the timed region"}
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         time.sleep(0.15)
@@ -122,7 +174,7 @@ class ClockSampler:
                 if f[5 + i].lower().startswith("active"):
                     reasons.add(nm)
         return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm), "source": "nvidia-smi -lms 100"}
 
 
 # ---------------------------------------------------------------------------------------------
