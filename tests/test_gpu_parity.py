@@ -618,13 +618,16 @@ def test_batch_overlap_is_invisible(enc, w, h, ratio, nf):
 
 
 @pytest.mark.parametrize("w,h,ratio,nf", [(1920, 1080, 0, 21), (640, 64, 1, 9), (256, 16, 0, 300), (1280, 720, 2, 6), (264, 40, 0, 5),
-                                          (1920, 1080, 0, 50), (640, 64, 1, 600), (1280, 720, 2, 120)])
+                                          (1920, 1080, 0, 50), (640, 64, 1, 600), (1280, 720, 2, 120),
+                                          (4096, 2320, 0, 7), (4112, 2304, 1, 6), (4096, 2320, 0, 25)])
 def test_frame_groups_equal_per_frame(enc, w, h, ratio, nf):
     """Batches of small frames share kernel launches (jpgb200_set_frame_groups: K1's tile index and the
     entropy kernels' blockIdx.y run over the frames of a group): same streams and lengths as four
     launches per frame, including a group count that does not divide the batch, more frames than one
     group holds, a ragged last tile and a width the fast K1 declines (264 = 33 blocks).  Three groups or more
-    (the last two cases) run as a three-stream pipeline of groups, with a ragged last group."""
+    (the last two cases) run as a three-stream pipeline of groups, with a ragged last group.  LARGE frames (more than
+    4096 x 2304 pixels) are grouped as well -- n / 3 frames per launch, at most eight: groups of two (2, 2, 2, 1 and
+    2, 2, 2) and of eight (8, 8, 8, 1) against the frame-by-frame pipeline."""
     if ratio == 2:
         h = (h + 15) // 16 * 16
     q, npx = 75, w * h
