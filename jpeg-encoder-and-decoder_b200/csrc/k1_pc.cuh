@@ -67,6 +67,13 @@ namespace jpgb200 {
 #ifndef K1C_DUAL_MAP
 #define K1C_DUAL_MAP 0xE654BDC8A9213F70ull
 #endif
+/* 4:2:2 has two transform warps per pipeline (luma; Cb + Cr), role 6 idles: one transform warp and two convert warps
+ * (one of each pipeline) per scheduler
+ *   S0: q0 = A.C0  q4 = B.C0  q8  = A.St  q12 = A.T0      S1: q1 = A.C1  q5 = B.C1  q9  = (A.6)  q13 = A.T1
+ *   S2: q2 = A.C2  q6 = B.C2  q10 = B.St  q14 = B.T0      S3: q3 = A.C3  q7 = B.C3  q11 = (B.6)  q15 = B.T1 */
+#ifndef K1C_DUAL_MAP_422
+#define K1C_DUAL_MAP_422 0xDC54EF67BA983210ull
+#endif
 #else
 #define K1C_CTA_THREADS K1C_THREADS
 #define K1C_LB_CTAS K1C_MIN_CTAS
@@ -201,7 +208,7 @@ __global__ void __launch_bounds__(K1C_CTA_THREADS, K1C_LB_CTAS) k1_transform_pc(
     K1CSmem *const SP = reinterpret_cast<K1CSmem *>(k1_smem);
     const int tid = threadIdx.x, lane = tid & 31;
 #if K1C_DUAL
-    const unsigned role = (unsigned)((K1C_DUAL_MAP >> (4 * (tid >> 5))) & 15ull);
+    const unsigned role = (unsigned)(((RATIO == 1 ? K1C_DUAL_MAP_422 : K1C_DUAL_MAP) >> (4 * (tid >> 5))) & 15ull);
     const int w = (int)(role & 7u), pipe = (int)(role >> 3);
 #else
     const int w = tid >> 5, pipe = 0;
