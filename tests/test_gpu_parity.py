@@ -619,7 +619,7 @@ def test_batch_overlap_is_invisible(enc, w, h, ratio, nf):
 
 @pytest.mark.parametrize("w,h,ratio,nf", [(1920, 1080, 0, 21), (640, 64, 1, 9), (256, 16, 0, 300), (1280, 720, 2, 6), (264, 40, 0, 5),
                                           (1920, 1080, 0, 50), (640, 64, 1, 600), (1280, 720, 2, 120),
-                                          (4096, 2320, 0, 7), (4112, 2304, 1, 6), (4096, 2320, 0, 25)])
+                                          (4096, 2320, 0, 7), (4112, 2304, 1, 6), (4096, 2320, 0, 25), (4104, 2320, 0, 6), (4112, 2320, 2, 7)])
 def test_frame_groups_equal_per_frame(enc, w, h, ratio, nf):
     """Batches of small frames share kernel launches (jpgb200_set_frame_groups: K1's tile index and the
     entropy kernels' blockIdx.y run over the frames of a group): same streams and lengths as four
