@@ -184,7 +184,18 @@ __device__ __forceinline__ uint32_t ff_mask(uint32_t v, int nvalid)
     return m;
 }
 
+/* number of 0xFF bytes in v, exactly: a byte of ~v is zero iff bit 7 of ((~v & 0x7f..) + 0x7f..) | ~v is clear */
+__device__ __forceinline__ uint32_t ff_count4(uint32_t v)
+{
+    const uint32_t t = ~v;
+    const uint32_t y = (t & 0x7f7f7f7fu) + 0x7f7f7f7fu;
+    return (uint32_t)__popc(~(y | t) & 0x80808080u);
+}
+
 /* ---- KF ---- */
+#ifndef KF_WIDE
+#define KF_WIDE 1 /* 0: every round through the general path (32 groups of 4 bytes per round) */
+#endif
 __global__ void __launch_bounds__(TAIL_THREADS) k_count_ff(const TailParams q0)
 {
     const TailParams q = tail_frame(q0);
@@ -193,19 +204,52 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_count_ff(const TailParams q0)
     if (chunk >= q.n_chunks) return;
     const uint32_t *slot = q.tmp + chunk * q.slot_words;
     /* everything this warp needs is requested before anything is waited for */
+#if KF_WIDE
+    /* the first WIDE round's words: 16 bytes per lane (slots are 16-byte aligned and never shorter than 128 words) */
+    uint4 w4 = reinterpret_cast<const uint4 *>(slot)[lane];
+#else
     uint32_t rc[TAIL_BATCH];
     tail_fetch(q, slot, 0u, lane, rc);
+#endif
     uint32_t carry_word = chunk == 0 ? q.carry : q.cta_tail[chunk - 1];
     const uint32_t T = q.cta_bits[chunk];
     const unsigned long long g0 = (unsigned long long)q.bit_phase + tail_prefix(q.cta_bits, q.super_bits, chunk, lane);
     const TailGeom g(q, chunk, g0, T);
     const uint32_t groups = (g.nB + 3u) >> 2;
     uint32_t c = 0;
-    for (uint32_t base = 0; base < groups; base += 32u * TAIL_BATCH) {
-        if (base) tail_fetch(q, slot, base, lane, rc);
+    uint32_t base = 0;
+#if KF_WIDE
+    /* WIDE rounds: 128 groups (512 owned bytes) per round, four consecutive groups per lane from one 16-byte load.
+     * A round qualifies when all its bytes are owned and the chunk's final byte (the only one that can hold pad bits)
+     * lies behind it: then every group is the plain funnel of two stream words -- W(i-1), W(i) in numeric form, W(-1)
+     * being the 32 bits in front of the chunk -- and bounds, validity masks and pad handling fall away. */
+    {
+        const uint32_t nd = (uint32_t)(-g.d); /* 0..7 */
+        uint32_t carry_num = carry_word;      /* numeric word in front of the round */
+        while ((base + 128u) * 4u < g.nB) {
+            const uint32_t W0 = be32(w4.x), W1 = be32(w4.y), W2 = be32(w4.z), W3 = be32(w4.w);
+            const uint32_t up = __shfl_up_sync(0xffffffffu, W3, 1);
+            const uint32_t Wm = lane == 0 ? carry_num : up;
+            carry_num = __shfl_sync(0xffffffffu, W3, 31);
+            base += 128u;
+            if ((base + 128u) * 4u < g.nB) w4 = reinterpret_cast<const uint4 *>(slot)[(base >> 2) + lane]; /* the next round's */
+            c += ff_count4(__funnelshift_r(W0, Wm, nd)) + ff_count4(__funnelshift_r(W1, W0, nd)) +
+                 ff_count4(__funnelshift_r(W2, W1, nd)) + ff_count4(__funnelshift_r(W3, W2, nd));
+        }
+        if (base) carry_word = be32(carry_num); /* the general path takes the word in front of a later round raw */
+    }
+    uint32_t rc[TAIL_BATCH];
+    if (base < groups) tail_fetch(q, slot, base, lane, rc);
+    const uint32_t base0 = base;
+#else
+    const uint32_t base0 = 0u;
+#endif
+    for (; base < groups; base += 32u * TAIL_BATCH) {
+        if (base != base0) tail_fetch(q, slot, base, lane, rc);
 #pragma unroll
         for (int r = 0; r < TAIL_BATCH; r++) {
             const uint32_t i = base + 32u * (uint32_t)r + (uint32_t)lane;
+            if (base + 32u * (uint32_t)r >= groups) break; /* warp-uniform */
             const uint32_t rp = tail_prev(rc[r], carry_word, lane);
             carry_word = __shfl_sync(0xffffffffu, rc[r], 31);
             if (i < groups) {
