@@ -269,6 +269,9 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_count_ff(const TailParams q0)
 }
 
 /* ---- KS ---- */
+#ifndef KS_INTERIOR
+#define KS_INTERIOR 1 /* 0: every round through the general geometry (bounds, validity masks, pad) */
+#endif
 __global__ void __launch_bounds__(TAIL_THREADS) k_scatter(const TailParams q0)
 {
     const TailParams q = tail_frame(q0);
@@ -300,16 +303,28 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_scatter(const TailParams q0)
                 if (base + 32u * (uint32_t)r >= groups) break; /* warp-uniform */
                 const uint32_t rp = tail_prev(rc[r], carry_word, lane);
                 carry_word = __shfl_sync(0xffffffffu, rc[r], 31);
-                uint32_t v = 0;
-                int nvalid = 0;
-                if (i < groups) {
-                    v = g.group(i, rp, rc[r]);
-                    const int left = (int)(g.nB - 4u * i);
-                    nvalid = left >= 4 ? 4 : left;
-                }
-                const uint32_t m = ff_mask(v, nvalid);
                 const uint32_t round0 = base + 32u * (uint32_t)r;
                 const bool full_round = (round0 + 32u) * 4u <= g.nB; /* warp-uniform: 128 owned bytes */
+                uint32_t v = 0, m;
+                int nvalid = 0;
+#if KS_INTERIOR
+                if ((round0 + 32u) * 4u < g.nB) {
+                    /* warp-uniform: 128 owned bytes and the chunk's final byte (the only one that can hold pad bits)
+                     * behind them -- every group is the plain funnel of two stream words, all four bytes count */
+                    const uint32_t wp = i == 0u ? rp : be32(rp);
+                    v = __funnelshift_r(be32(rc[r]), wp, (uint32_t)(-g.d));
+                    nvalid = 4;
+                    m = __vcmpeq4(v, 0xffffffffu);
+                } else
+#endif
+                {
+                    if (i < groups) {
+                        v = g.group(i, rp, rc[r]);
+                        const int left = (int)(g.nB - 4u * i);
+                        nvalid = left >= 4 ? 4 : left;
+                    }
+                    m = ff_mask(v, nvalid);
+                }
                 if (full_round && __ballot_sync(0xffffffffu, m != 0u) == 0u) {
                     /* no 0xFF in these 128 bytes (the common case): they go out as they are, with
                      * aligned 32-bit stores -- words straddling two lanes are assembled by shuffle */
@@ -320,12 +335,20 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_scatter(const TailParams q0)
                     if (a == 0u) {
                         reinterpret_cast<uint32_t *>(d)[lane] = own;
                     } else {
-                        if (lane > 0)
+                        /* a = 1..3: lane 0 writes the 4 - a bytes in front of the first aligned word, lane 31 the a bytes
+                         * behind the last one -- predicated single stores, no loops with a lane-dependent trip count */
+                        if (lane > 0) {
                             reinterpret_cast<uint32_t *>(d - a)[lane] = __funnelshift_r(prv, own, 8u * (4u - a));
-                        else
-                            for (unsigned t = 0; t < 4u - a; t++) d[t] = (uint8_t)(own >> (8u * t));
-                        if (lane == 31)
-                            for (unsigned t = 0; t < a; t++) d[128u - a + t] = (uint8_t)(own >> (8u * (4u - a + t)));
+                        } else {
+#pragma unroll
+                            for (unsigned t = 0; t < 3u; t++)
+                                if (t < 4u - a) d[t] = (uint8_t)(own >> (8u * t));
+                        }
+                        if (lane == 31) {
+#pragma unroll
+                            for (unsigned t = 0; t < 3u; t++)
+                                if (t < a) d[128u - a + t] = (uint8_t)(own >> (8u * (4u - a + t)));
+                        }
                     }
                     P += 128ull;
                     continue;
