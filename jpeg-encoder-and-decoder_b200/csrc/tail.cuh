@@ -304,55 +304,73 @@ __global__ void __launch_bounds__(TAIL_THREADS) k_scatter(const TailParams q0)
                 const uint32_t rp = tail_prev(rc[r], carry_word, lane);
                 carry_word = __shfl_sync(0xffffffffu, rc[r], 31);
                 const uint32_t round0 = base + 32u * (uint32_t)r;
-                const bool full_round = (round0 + 32u) * 4u <= g.nB; /* warp-uniform: 128 owned bytes */
-                uint32_t v = 0, m;
-                int nvalid = 0;
 #if KS_INTERIOR
                 if ((round0 + 32u) * 4u < g.nB) {
                     /* warp-uniform: 128 owned bytes and the chunk's final byte (the only one that can hold pad bits)
                      * behind them -- every group is the plain funnel of two stream words, all four bytes count */
                     const uint32_t wp = i == 0u ? rp : be32(rp);
-                    v = __funnelshift_r(be32(rc[r]), wp, (uint32_t)(-g.d));
-                    nvalid = 4;
-                    m = __vcmpeq4(v, 0xffffffffu);
-                } else
-#endif
-                {
-                    if (i < groups) {
-                        v = g.group(i, rp, rc[r]);
-                        const int left = (int)(g.nB - 4u * i);
-                        nvalid = left >= 4 ? 4 : left;
-                    }
-                    m = ff_mask(v, nvalid);
-                }
-                if (full_round && __ballot_sync(0xffffffffu, m != 0u) == 0u) {
-                    /* no 0xFF in these 128 bytes (the common case): they go out as they are, with
-                     * aligned 32-bit stores -- words straddling two lanes are assembled by shuffle */
-                    uint8_t *d = q.out + P;
-                    const unsigned a = (unsigned)((unsigned long long)(uintptr_t)d & 3ull);
-                    const uint32_t own = __byte_perm(v, 0, 0x0123); /* memory order */
-                    const uint32_t prv = __shfl_up_sync(0xffffffffu, own, 1);
-                    if (a == 0u) {
-                        reinterpret_cast<uint32_t *>(d)[lane] = own;
-                    } else {
-                        /* a = 1..3: lane 0 writes the 4 - a bytes in front of the first aligned word, lane 31 the a bytes
-                         * behind the last one -- predicated single stores, no loops with a lane-dependent trip count */
-                        if (lane > 0) {
-                            reinterpret_cast<uint32_t *>(d - a)[lane] = __funnelshift_r(prv, own, 8u * (4u - a));
+                    const uint32_t v = __funnelshift_r(be32(rc[r]), wp, (uint32_t)(-g.d));
+                    const uint32_t m = __vcmpeq4(v, 0xffffffffu);
+                    unsigned busy = __ballot_sync(0xffffffffu, m != 0u);
+                    if (busy == 0u) {
+                        /* no 0xFF in these 128 bytes (40 % of the rounds): they go out as they are, with aligned 32-bit
+                         * stores -- words straddling two lanes are assembled by shuffle */
+                        uint8_t *d = q.out + P;
+                        const unsigned a = (unsigned)((unsigned long long)(uintptr_t)d & 3ull);
+                        const uint32_t own = __byte_perm(v, 0, 0x0123); /* memory order */
+                        const uint32_t prv = __shfl_up_sync(0xffffffffu, own, 1);
+                        if (a == 0u) {
+                            reinterpret_cast<uint32_t *>(d)[lane] = own;
                         } else {
+                            /* a = 1..3: lane 0 writes the 4 - a bytes in front of the first aligned word, lane 31 the a
+                             * bytes behind the last one -- predicated single stores, no loops with a lane-dependent trip count */
+                            if (lane > 0) {
+                                reinterpret_cast<uint32_t *>(d - a)[lane] = __funnelshift_r(prv, own, 8u * (4u - a));
+                            } else {
 #pragma unroll
-                            for (unsigned t = 0; t < 3u; t++)
-                                if (t < 4u - a) d[t] = (uint8_t)(own >> (8u * t));
-                        }
-                        if (lane == 31) {
+                                for (unsigned t = 0; t < 3u; t++)
+                                    if (t < 4u - a) d[t] = (uint8_t)(own >> (8u * t));
+                            }
+                            if (lane == 31) {
 #pragma unroll
-                            for (unsigned t = 0; t < 3u; t++)
-                                if (t < a) d[128u - a + t] = (uint8_t)(own >> (8u * (4u - a + t)));
+                                for (unsigned t = 0; t < 3u; t++)
+                                    if (t < a) d[128u - a + t] = (uint8_t)(own >> (8u * (4u - a + t)));
+                            }
                         }
+                        P += 128ull;
+                        continue;
                     }
-                    P += 128ull;
+                    /* some lane holds a 0xFF (typically one or two): every lane writes its four bytes at 4 * lane plus the
+                     * zeros stuffed by the lanes below it -- summed over the FEW busy lanes, not scanned over all 32 */
+                    const uint32_t e = (uint32_t)__popc(m) >> 3;
+                    uint32_t below = 0u, extra = 0u;
+                    do {
+                        const int j = __ffs((int)busy) - 1;
+                        busy &= busy - 1u;
+                        const uint32_t ej = __shfl_sync(0xffffffffu, e, j);
+                        below += lane > j ? ej : 0u;
+                        extra += ej;
+                    } while (busy);
+                    uint8_t *dst = q.out + P + 4u * (uint32_t)lane + below;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const uint32_t byte = (v >> (24 - 8 * k)) & 0xffu;
+                        *dst++ = (uint8_t)byte;
+                        if (byte == 0xffu) *dst++ = 0;
+                    }
+                    P += 128ull + extra;
                     continue;
                 }
+#endif
+                /* the chunk's last round(s): bounds, validity masks, pad */
+                uint32_t v = 0;
+                int nvalid = 0;
+                if (i < groups) {
+                    v = g.group(i, rp, rc[r]);
+                    const int left = (int)(g.nB - 4u * i);
+                    nvalid = left >= 4 ? 4 : left;
+                }
+                const uint32_t m = ff_mask(v, nvalid);
                 const uint32_t n_out = (uint32_t)nvalid + ((uint32_t)__popc(m) >> 3);
                 uint32_t inc = n_out;
 #pragma unroll
