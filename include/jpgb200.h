@@ -101,7 +101,7 @@ int jpgb200_set_pipelined_batch(jpgb200_ctx *ctx, int on);
 /* jpgb200_encode_batch_device: 1 (default) = groups of frames share kernel launches (K1's tile index and the entropy
  * kernels' blockIdx.y run over the frames of a group: four launches per group).  Frames of up to 4096x2304 pixels are
  * grouped to about one 8K frame's worth of pixels per launch; larger frames by n_frames / 3, at most eight (a launch
- * pays ~10 us for filling and draining the GPU whatever its size: 250 k against 233 k Mpixel/s on 8K frames).  Three
+ * pays ~10 us for filling and draining the GPU whatever its size: 260 k against 238 k Mpixel/s on 8K frames).  Three
  * or more groups run through the three-stream pipeline.  0 = four launches per frame.  Identical bytes. */
 int jpgb200_set_frame_groups(jpgb200_ctx *ctx, int on);
 /* 1 = K1E also stores its coefficients (jpgb200_last_coefficients reads them): the parity tap of
